@@ -1,0 +1,179 @@
+"""Generate the golden fixtures in this directory FROM THE REFERENCE ITSELF.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU
+box):  ``python tests/golden/make_golden.py``
+
+Everything stored here is an output of unmodified reference code imported from
+``/root/reference``:
+
+* ``cs.cartesian_mask``      compressed_sensing.py:82-123
+* ``cs.undersample``         compressed_sensing.py:460-512
+* ``cs.data_consistency``    compressed_sensing.py:515-529
+* ``myfft.data_consistency`` myfft.py:131-142 (pure blend; ``pytorch_fft`` is
+  stubbed only so that the module imports - the stub is never called)
+* ``Undersample.__call__``   myImageTransformations.py:1196-1238
+* ``models.recnet.RecNet``   models/recnet.py:65-161 with ``dc_layers`` (a plain
+  list, recnet.py:128-134) swapped for an op that chains the reference blend
+  with ``torch.fft`` (the reference's own FFT wrapper is CUDA-only).
+
+The fixtures are small (< 1 MB in total) and are what pins ``oracle/``.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = '/root/reference'
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    pkg = types.ModuleType('pytorch_fft')
+    sub = types.ModuleType('pytorch_fft.fft')
+    for name in ('fft,ifft,fft2,ifft2,fft3,ifft3,rfft,irfft,rfft2,irfft2,'
+                 'rfft3,irfft3').split(','):
+        setattr(sub, name, None)
+    pkg.fft = sub
+    sys.modules['pytorch_fft'] = pkg
+    sys.modules['pytorch_fft.fft'] = sub
+    import data.reconstruction.deep_med_lib.utils.compressed_sensing as cs
+    import data.reconstruction.deep_med_lib.my_pytorch.myfft as myfft
+    import data.reconstruction.deep_med_lib.my_pytorch.myImageTransformations as mit
+    import models.recnet as recnet
+    return cs, myfft, mit, recnet
+
+
+def main():
+    cs, myfft, mit, recnet = import_reference()
+
+    # ---- 1. masks: sampled rows for every sweep size / acceleration ----------
+    masks = {}
+    for n in (32, 64, 128, 256, 320, 512):
+        for acc in (4, 8, 12):
+            if n // acc <= 8:
+                continue
+            m = cs.cartesian_mask((3, n, n), acc, 8, centred=False,
+                                  rng=np.random.RandomState(0))
+            assert (m == m[:, :, :1]).all()
+            masks['rows_n%d_acc%d' % (n, acc)] = m[:, :, 0].astype(np.uint8)
+    masks['full_n32_acc4'] = cs.cartesian_mask(
+        (2, 32, 32), 4, 8, centred=False, rng=np.random.RandomState(0))
+    masks['full_n32_acc4_centred'] = cs.cartesian_mask(
+        (2, 32, 32), 4, 8, centred=True, rng=np.random.RandomState(0))
+    # the default sample_n=10 and a non-integer acceleration
+    masks['full_n64_acc3p5_s10'] = cs.cartesian_mask(
+        (2, 64, 64), 3.5, centred=False, rng=np.random.RandomState(7))
+    np.savez_compressed(os.path.join(HERE, 'masks.npz'), **masks)
+
+    # ---- 2. undersample + numpy DC ------------------------------------------
+    rs = np.random.RandomState(1)
+    n = 32
+    img = rs.uniform(0, 1, (2, n, n))
+    mask = cs.cartesian_mask((2, n, n), 4, 8, centred=False,
+                             rng=np.random.RandomState(0))
+    rng = np.random.RandomState(5)
+    x_u, x_fu = cs.undersample(img, mask, centred=False, norm='ortho', rng=rng)
+    after = rng.normal()                    # pins how much RNG was consumed
+    x_u_nz, x_fu_nz = cs.undersample(img, mask, centred=False, norm='ortho',
+                                     noise=0.01, rng=np.random.RandomState(5))
+    xin = rs.normal(size=(2, n, n)) + 1j * rs.normal(size=(2, n, n))
+    xd = cs.data_consistency(xin, x_fu, mask, centered=False, norm='ortho')
+    # general (non row-constant) mask too
+    gmask = (rs.uniform(size=(2, n, n)) < 0.3).astype(np.float64)
+    gk0 = gmask * np.fft.fft2(img, norm='ortho')
+    xd_g = cs.data_consistency(xin, gk0, gmask, centered=False, norm='ortho')
+    np.savez_compressed(
+        os.path.join(HERE, 'undersample_dc.npz'), img=img, mask=mask,
+        x_u=x_u, x_fu=x_fu, rng_after=after, x_u_nz=x_u_nz, x_fu_nz=x_fu_nz,
+        xin=xin, xd=xd, gmask=gmask, gk0=gk0, xd_g=xd_g)
+
+    # ---- 3. reference torch blend (fp32) -------------------------------------
+    g = torch.Generator().manual_seed(3)
+    k = torch.randn(2, 2, n, n, generator=g)
+    k0 = torch.randn(2, 2, n, n, generator=g)
+    m = torch.from_numpy(np.stack([mask, mask], 1).astype(np.float32))
+    k0 = k0 * m
+    blend = {
+        'k': k.numpy(), 'k0': k0.numpy(), 'mask': m.numpy(),
+        'out_none': myfft.data_consistency(k, k0, m, None).numpy(),
+        'out_zero': myfft.data_consistency(k, k0, m, 0).numpy(),
+        'out_0p1': myfft.data_consistency(k, k0, m, 0.1).numpy(),
+        'out_2p5': myfft.data_consistency(k, k0, m, 2.5).numpy(),
+    }
+    np.savez_compressed(os.path.join(HERE, 'blend.npz'), **blend)
+
+    # ---- 4. Undersample transform group (fixed masks, RandomState(0)) --------
+    tr = mit.Undersample('varden', (1, n, n), acceleration_rate=4,
+                         fixed_mask=True, num_fixed_masks=2)
+    im1 = rs.uniform(0, 1, (n, n, 1))
+    im2 = rs.uniform(0, 1, (n, n, 1))
+    grp1 = tr(im1.copy())
+    grp2 = tr(im2.copy())
+    np.savez_compressed(os.path.join(HERE, 'undersample_group.npz'),
+                        im1=im1, im2=im2, grp1=grp1, grp2=grp2)
+
+    # ---- 5. reference RecNet, DC = reference blend + torch.fft ---------------
+    class RefBlendDC(object):
+        def __init__(self, noise_lvl=None):
+            self.noise_lvl = noise_lvl
+
+        def perform(self, x, k0, mask):
+            kc = torch.fft.fft2(torch.complex(x[:, 0], x[:, 1]), norm='ortho')
+            kk = torch.stack([kc.real, kc.imag], 1)
+            out = myfft.data_consistency(kk, k0, mask, self.noise_lvl)
+            oc = torch.fft.ifft2(torch.complex(out[:, 0], out[:, 1]),
+                                 norm='ortho')
+            return torch.stack([oc.real, oc.imag], 1)
+
+    torch.manual_seed(0)
+    net = recnet.RecNet(num_blocks=2, num_convs=3, num_filters=4)
+    from models.weight_inits import initialize_weights
+    for blk in net.conv_blocks:
+        initialize_weights(blk, {})
+    net.dc_layers = [RefBlendDC() for _ in net.dc_layers]
+    nn_ = 16
+    img = torch.from_numpy(rs.uniform(0, 1, (2, nn_, nn_)))
+    mk = cs.cartesian_mask((2, nn_, nn_), 2, 4, centred=False,
+                           rng=np.random.RandomState(0))
+    xu, xfu = cs.undersample(img.numpy(), mk, centred=False, norm='ortho',
+                             rng=np.random.RandomState(0))
+    inp = torch.from_numpy(np.stack([xu.real, xu.imag], 1).astype(np.float32))
+    ksp = torch.from_numpy(np.stack([xfu.real, xfu.imag], 1).astype(np.float32))
+    msk = torch.from_numpy(np.stack([mk, mk], 1).astype(np.float32))
+    tgt = torch.stack([img.float(), torch.zeros_like(img).float()], 1)
+    out = net(inp, ksp, msk)
+    loss = torch.nn.functional.mse_loss(out, tgt)
+    loss.backward()
+    fix = {'inp': inp.numpy(), 'kspace': ksp.numpy(), 'mask': msk.numpy(),
+           'target': tgt.numpy(), 'out': out.detach().numpy(),
+           'loss': np.float64(loss.item())}
+    for name, p in net.state_dict().items():
+        fix['w:' + name] = p.numpy()
+    for name, p in net.named_parameters():
+        fix['g:' + name] = p.grad.numpy()
+    # residual ("use_refinement") variant and the dict-returning variant
+    torch.manual_seed(0)
+    net2 = recnet.RecNet(num_blocks=2, num_convs=3, num_filters=4,
+                         use_refinement=True, return_intermediate_recs=True,
+                         skip_final_dc=True)
+    net2.load_state_dict(net.state_dict())
+    net2.dc_layers = [RefBlendDC() for _ in net2.dc_layers]
+    o2 = net2(inp, ksp, msk)
+    fix['out_refine_pred'] = o2['pred'].detach().numpy()
+    fix['out_refine_rec0'] = o2['reconstructions'][0].detach().numpy()
+    fix['n_refine_recs'] = np.int64(len(o2['reconstructions']))
+    # full DC with the noisy branch
+    dcn = RefBlendDC(0.1).perform(inp * 0.5 + 0.1, ksp, msk)
+    fix['dc_noisy_0p1'] = dcn.numpy()
+    np.savez_compressed(os.path.join(HERE, 'recnet_tiny.npz'), **fix)
+
+    tot = sum(os.path.getsize(os.path.join(HERE, f))
+              for f in os.listdir(HERE) if f.endswith('.npz'))
+    print('golden fixtures written, %d bytes' % tot)
+
+
+if __name__ == '__main__':
+    main()
