@@ -1,0 +1,93 @@
+"""ctypes binding of libcsmri_dc.so (the C ABI of include/csmri_dc.h).
+
+There is no fallback: if the shared library has not been built, importing any
+op raises immediately with the build command.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, 'csrc')
+LIB_PATH = os.path.join(CSRC, 'libcsmri_dc.so')
+SOURCES = ['csmri_dc.cu', 'dc_core.cuh', 'fft_regs.cuh']
+NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a',
+              '-lineinfo', '-Xcompiler', '-fPIC', '-shared']
+
+_c_float_p = ctypes.c_void_p   # device pointers travel as integers
+_lib = None
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/csmri_dc.cu for sm_100a into csrc/libcsmri_dc.so."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    srcs.append(os.path.join(os.path.dirname(_HERE), 'include', 'csmri_dc.h'))
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(s) for s in srcs)
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    nvcc = os.environ.get('NVCC', 'nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH, os.path.join(CSRC, 'csmri_dc.cu')]
+    if verbose:
+        cmd += ['-Xptxas', '-v']
+        print(' '.join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB_PATH
+
+
+_SIGNATURES = {
+    'csmri_version': (ctypes.c_int, []),
+    'csmri_last_error': (ctypes.c_char_p, []),
+    'csmri_init': (ctypes.c_int, []),
+    'csmri_dc_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int] * 3),
+    'csmri_dc_prepare': (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_float, _c_float_p, _c_float_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'csmri_dc_forward_cartesian': (ctypes.c_int, [_c_float_p] * 5 + [ctypes.c_int] * 3 +
+                                   [ctypes.c_void_p]),
+    'csmri_dc_adjoint_cartesian': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 3 +
+                                   [ctypes.c_void_p]),
+    'csmri_dc_forward_general': (ctypes.c_int, [_c_float_p] * 5 + [ctypes.c_int] * 3 +
+                                 [ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    'csmri_dc_adjoint_general': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 3 +
+                                 [ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    'csmri_dc_forward': (ctypes.c_int, [_c_float_p] * 7 + [ctypes.c_int] * 3 +
+                         [ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    'csmri_dc_adjoint': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 3 +
+                         [ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    'csmri_undersample': (ctypes.c_int, [_c_float_p, ctypes.c_void_p] + [_c_float_p] * 4 +
+                          [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_void_p]),
+    'csmri_fft2': (ctypes.c_int, [_c_float_p, _c_float_p] + [ctypes.c_int] * 4 +
+                   [ctypes.c_void_p, ctypes.c_void_p]),
+    # tuning knob used by bench.py only (not declared in include/csmri_dc.h)
+    'csmri_set_variant': (ctypes.c_int, [ctypes.c_int]),
+}
+
+# every symbol include/csmri_dc.h declares
+ABI_SYMBOLS = [k for k in _SIGNATURES if k != 'csmri_set_variant']
+
+
+def lib():
+    """The loaded library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'libcsmri_dc.so is missing (%s). Build it with '
+                '`python -c "import __graft_entry__ as g; g.build()"` or '
+                '`python -m csmri_refinement_b200.build`. There is no CPU/PyTorch '
+                'fallback for the DC path.' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().csmri_last_error().decode('utf-8', 'replace')
+        raise RuntimeError('libcsmri_dc error %d: %s' % (rc, msg))

@@ -1,0 +1,782 @@
+// libcsmri_dc.so - hand-written sm_100a kernels for the k-space
+// data-consistency (DC) path of mseitzer/csmri-refinement, behind the C ABI of
+// include/csmri_dc.h.  No torch types, no CPU fallback.
+//
+// Reference arithmetic being replaced (paths relative to the reference root):
+//   data/reconstruction/deep_med_lib/my_pytorch/myfft.py:78-128   Fft2d/Ifft2d
+//   data/reconstruction/deep_med_lib/my_pytorch/myfft.py:131-142  blend
+//   data/reconstruction/deep_med_lib/my_pytorch/myfft.py:145-163  perform
+//   models/recnet.py:147-148                                      residual add
+//   data/reconstruction/deep_med_lib/utils/compressed_sensing.py:460-512 undersample
+//
+// Kernels
+//   dc_strip_row_kernel    the hot one.  Cartesian masks are constant along W
+//                          (compressed_sensing.py:115-116), so the W-axis
+//                          transforms of FFT2 / iFFT2 cancel around the blend
+//                          and DC becomes, per image column,
+//                            out = iFFT_H(D * FFT_H(x)) + addend.
+//                          A CTA owns an H x 32 column strip of one slice:
+//                          coalesced 128-byte row segments straight into
+//                          registers, two register-FFT passes per direction
+//                          with one shared-memory exchange each, blend in
+//                          registers, store.  x is read once, out written once.
+//   dc_strip_dense_kernel  same column pass for an arbitrary dense mask, on a
+//                          row-transformed (hybrid) tensor.
+//   fft_strip_kernel       single column DFT (prepare / fft2 / undersample).
+//   fft_rows_kernel        single row DFT, tile transposed through smem.
+//   mask_rows_kernel       proves row-constancy and builds the D table.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/csmri_dc.h"
+#include "dc_core.cuh"
+
+namespace csmri {
+
+cf h_twiddle[kTwN];
+
+// ---------------------------------------------------------------------------
+// global memory access helpers: everything is streamed exactly once
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// hot kernel: Cartesian DC forward / adjoint on one H x CW column strip
+// ---------------------------------------------------------------------------
+template <int H, int E, int CW, int MINB, int WT>
+__global__ void __launch_bounds__(CW*(H / E), MINB)
+    dc_strip_row_kernel(const float* __restrict__ x, const float* __restrict__ residual,
+                        const float* __restrict__ dtab, const float* __restrict__ addend,
+                        float* __restrict__ out, int W_rt, int nstrips_rt) {
+  typedef LineFFT<H, E, CW> L;
+  constexpr int T = L::T;
+  // WT != 0: the row pitch is a compile-time constant, so every row offset
+  // below folds into the immediate field of LDG/STG (no address arithmetic)
+  const int W = WT ? WT : W_rt;
+  const int nstrips = WT ? WT / CW : nstrips_rt;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf* sm = reinterpret_cast<cf*>(smem_raw);
+
+  const int lane = threadIdx.x % CW;
+  const int j = threadIdx.x / CW;
+  const int b = blockIdx.x / nstrips;
+  const int strip = blockIdx.x - b * nstrips;
+  const size_t plane = (size_t)H * W;
+  const size_t base = (size_t)b * 2 * plane + (size_t)strip * CW + lane;
+
+  cf v[E];
+  {
+    const float* pr = x + base;
+    const float* pi = pr + plane;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const size_t o = (size_t)(j + T * i) * W;
+      v[i] = mk(ld_stream(pr + o), ld_stream(pi + o));
+    }
+  }
+  if (residual != nullptr) {
+    const float* pr = residual + base;
+    const float* pi = pr + plane;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const size_t o = (size_t)(j + T * i) * W;
+      v[i] = cadd(v[i], mk(ld_stream(pr + o), ld_stream(pi + o)));
+    }
+  }
+
+  L::template a_front<false>(v, sm, j, lane);
+  __syncthreads();
+  L::template a_back<false>(v, sm, j, lane);
+
+  {
+    const float* d = dtab + (size_t)b * H;
+#pragma unroll
+    for (int r = 0; r < E; ++r) v[r] = cscale(v[r], __ldg(d + L::k_index(j, r)));
+  }
+
+  L::template b_front<true>(v, sm, j, lane);
+  __syncthreads();
+  L::template b_back<true>(v, sm, j, lane);
+
+  if (addend != nullptr) {
+    const float* pr = addend + base;
+    const float* pi = pr + plane;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const size_t o = (size_t)(j + T * i) * W;
+      v[i] = cadd(v[i], mk(ld_stream(pr + o), ld_stream(pi + o)));
+    }
+  }
+  {
+    float* pr = out + base;
+    float* pi = pr + plane;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const size_t o = (size_t)(j + T * i) * W;
+      st_stream(pr + o, v[i].x);
+      st_stream(pi + o, v[i].y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// column pass for arbitrary masks, on the row-transformed tensor (in place ok)
+//   ADJ = false: Y = blend(s*K, k0, mask)  (myfft.py:139 / :141 as written)
+//   ADJ = true : Y = D * s*K, D = (1-m) or (1-m)+m/(1+v)
+// ---------------------------------------------------------------------------
+template <int H, int E, int CW, bool NOISY, bool ADJ>
+__global__ void __launch_bounds__(CW*(H / E))
+    dc_strip_dense_kernel(const float* __restrict__ hyb, const float* __restrict__ k0,
+                          const float* __restrict__ mask, float* __restrict__ out, int W,
+                          int nstrips, float s, float nv) {
+  typedef LineFFT<H, E, CW> L;
+  constexpr int T = L::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf* sm = reinterpret_cast<cf*>(smem_raw);
+
+  const int lane = threadIdx.x % CW;
+  const int j = threadIdx.x / CW;
+  const int b = blockIdx.x / nstrips;
+  const int strip = blockIdx.x - b * nstrips;
+  const size_t plane = (size_t)H * W;
+  const size_t base = (size_t)b * 2 * plane + (size_t)strip * CW + lane;
+
+  cf v[E];
+  {
+    const float* pr = hyb + base;
+    const float* pi = pr + plane;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const size_t o = (size_t)(j + T * i) * W;
+      v[i] = mk(ld_stream(pr + o), ld_stream(pi + o));
+    }
+  }
+  L::template a_front<false>(v, sm, j, lane);
+  __syncthreads();
+  L::template a_back<false>(v, sm, j, lane);
+
+  {
+    const float inv1pv = 1.0f / (1.0f + nv);
+    const float* mr = mask + base;
+    const float* mi = mr + plane;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      const size_t o = (size_t)L::k_index(j, r) * W;
+      const float m0 = ld_stream(mr + o), m1 = ld_stream(mi + o);
+      const cf k = cscale(v[r], s);
+      if (ADJ) {
+        const float d0 = NOISY ? (1.0f - m0) + m0 * inv1pv : (1.0f - m0);
+        const float d1 = NOISY ? (1.0f - m1) + m1 * inv1pv : (1.0f - m1);
+        v[r] = mk(d0 * k.x, d1 * k.y);
+      } else {
+        const float* kr = k0 + base;
+        const float* ki = kr + plane;
+        const float a = ld_stream(kr + o), c = ld_stream(ki + o);
+        if (NOISY) {
+          v[r] = mk((1.0f - m0) * k.x + m0 * (k.x + nv * a) * inv1pv,
+                    (1.0f - m1) * k.y + m1 * (k.y + nv * c) * inv1pv);
+        } else {
+          v[r] = mk((1.0f - m0) * k.x + a, (1.0f - m1) * k.y + c);
+        }
+      }
+    }
+  }
+
+  L::template b_front<true>(v, sm, j, lane);
+  __syncthreads();
+  L::template b_back<true>(v, sm, j, lane);
+  {
+    float* pr = out + base;
+    float* pi = pr + plane;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const size_t o = (size_t)(j + T * i) * W;
+      st_stream(pr + o, v[i].x * s);
+      st_stream(pi + o, v[i].y * s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// single column DFT:  out[k, w] = scale * rowmul[k] * sum_h in[h, w] W_H^{+-hk}
+//   rows  : optional (B,H) uint8 multiplier on OUTPUT rows (undersample mask)
+//   out2  : optional second destination for the same values
+// ---------------------------------------------------------------------------
+template <int H, int E, int CW, bool INV>
+__global__ void __launch_bounds__(CW*(H / E))
+    fft_strip_kernel(const float* __restrict__ in, float* __restrict__ out, int W, int nstrips,
+                     float scale, const unsigned char* __restrict__ rows) {
+  typedef LineFFT<H, E, CW> L;
+  constexpr int T = L::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf* sm = reinterpret_cast<cf*>(smem_raw);
+
+  const int lane = threadIdx.x % CW;
+  const int j = threadIdx.x / CW;
+  const int b = blockIdx.x / nstrips;
+  const int strip = blockIdx.x - b * nstrips;
+  const size_t plane = (size_t)H * W;
+  const size_t base = (size_t)b * 2 * plane + (size_t)strip * CW + lane;
+
+  cf v[E];
+  {
+    const float* pr = in + base;
+    const float* pi = pr + plane;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const size_t o = (size_t)(j + T * i) * W;
+      v[i] = mk(ld_stream(pr + o), ld_stream(pi + o));
+    }
+  }
+  L::template a_front<INV>(v, sm, j, lane);
+  __syncthreads();
+  L::template a_back<INV>(v, sm, j, lane);
+  {
+    float* pr = out + base;
+    float* pi = pr + plane;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      const int k = L::k_index(j, r);
+      // mask * value as a product, so that masked entries are signed zeros
+      // exactly like compressed_sensing.py:510 (`mask * (x_f + nz)`)
+      const float m = (rows != nullptr) ? (rows[(size_t)b * H + k] ? 1.0f : 0.0f) : 1.0f;
+      const size_t o = (size_t)k * W;
+      st_stream(pr + o, (v[r].x * scale) * m);
+      st_stream(pi + o, (v[r].y * scale) * m);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// single row DFT along W.  A CTA owns RT = CW rows of one plane pair; the tile
+// is staged through shared memory so that global accesses stay coalesced while
+// the lanes of a warp own different rows.
+//   PRE: 0 none, 1 add `aux` (residual), 2 multiply by cmul*aux (aux = mask),
+//        3 real input (imaginary plane absent / zero)
+// ---------------------------------------------------------------------------
+template <int W, int E, int CW, bool INV, int PRE>
+__global__ void __launch_bounds__(CW*(W / E))
+    fft_rows_kernel(const float* __restrict__ in, const float* __restrict__ aux,
+                    float* __restrict__ out, int H, float scale, float cmulv) {
+  typedef LineFFT<W, E, CW> L;
+  constexpr int T = L::T;
+  constexpr int NT = CW * T;
+  constexpr int PITCH = W + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf* sm = reinterpret_cast<cf*>(smem_raw);               // exchange buffer
+  float* st = reinterpret_cast<float*>(smem_raw);          // staging (aliased)
+  float* st_re = st;
+  float* st_im = st + CW * PITCH;
+
+  const int tiles_per_slice = H / CW;
+  const int b = blockIdx.x / tiles_per_slice;
+  const int row0 = (blockIdx.x - b * tiles_per_slice) * CW;
+  const size_t plane = (size_t)H * W;
+  const size_t in_plane = plane;
+  const size_t base_in = (PRE == 3 ? (size_t)b * in_plane : (size_t)b * 2 * in_plane) +
+                         (size_t)row0 * W;
+  const size_t base = (size_t)b * 2 * plane + (size_t)row0 * W;
+
+  for (int idx = threadIdx.x; idx < CW * W; idx += NT) {
+    const int r = idx / W, w = idx - r * W;
+    float re = ld_stream(in + base_in + idx);
+    float im = (PRE == 3) ? 0.0f : ld_stream(in + base_in + in_plane + idx);
+    if (PRE == 1) {
+      re += ld_stream(aux + base + idx);
+      im += ld_stream(aux + base + plane + idx);
+    } else if (PRE == 2) {
+      re *= cmulv * ld_stream(aux + base + idx);
+      im *= cmulv * ld_stream(aux + base + plane + idx);
+    }
+    st_re[r * PITCH + w] = re;
+    st_im[r * PITCH + w] = im;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x % CW;  // row within the tile
+  const int j = threadIdx.x / CW;
+  cf v[E];
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    const int w = j + T * i;
+    v[i] = mk(st_re[lane * PITCH + w], st_im[lane * PITCH + w]);
+  }
+  __syncthreads();  // staging is dead, the exchange buffer may overwrite it
+
+  L::template a_front<INV>(v, sm, j, lane);
+  __syncthreads();
+  L::template a_back<INV>(v, sm, j, lane);
+  __syncthreads();
+
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const int k = L::k_index(j, r);
+    st_re[lane * PITCH + k] = v[r].x * scale;
+    st_im[lane * PITCH + k] = v[r].y * scale;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < CW * W; idx += NT) {
+    const int r = idx / W, w = idx - r * W;
+    st_stream(out + base + idx, st_re[r * PITCH + w]);
+    st_stream(out + base + plane + idx, st_im[r * PITCH + w]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// mask analysis: one warp per (b, h) row
+// ---------------------------------------------------------------------------
+__global__ void set_flag_kernel(int* flag, int value) { *flag = value; }
+
+__global__ void mask_rows_kernel(const float* __restrict__ mask, int B, int H, int W, float nv,
+                                 int noisy, float* __restrict__ dtab, int* __restrict__ flag) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (warp >= B * H) return;
+  const int b = warp / H, h = warp - b * H;
+  const size_t plane = (size_t)H * W;
+  const float* r0 = mask + (size_t)b * 2 * plane + (size_t)h * W;
+  const float* r1 = r0 + plane;
+  const float m = r0[0];
+  bool ok = true;
+  for (int w = lane; w < W; w += 32) ok = ok && (r0[w] == m) && (r1[w] == m);
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0) {
+    if (!ok) atomicExch(flag, 0);
+    const float d = noisy ? (1.0f - m) + m / (1.0f + nv) : (1.0f - m);
+    dtab[warp] = d / (float)H;
+  }
+}
+
+// real image + row table -> dense 2-channel mask and (img, 0) target
+__global__ void expand_mask_target_kernel(const float* __restrict__ img,
+                                          const unsigned char* __restrict__ rows,
+                                          float* __restrict__ mask, float* __restrict__ target,
+                                          int B, int H, int W) {
+  const size_t plane = (size_t)H * W;
+  const size_t n = (size_t)B * plane;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / plane, rem = i - b * plane;
+    const int h = (int)(rem / W);
+    const float m = rows[b * H + h] ? 1.0f : 0.0f;
+    mask[b * 2 * plane + rem] = m;
+    mask[b * 2 * plane + plane + rem] = m;
+    target[b * 2 * plane + rem] = img[i];
+    target[b * 2 * plane + plane + rem] = 0.0f;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(CSMRI_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CSMRI_CUDA(call)                                   \
+  do {                                                     \
+    cudaError_t e_ = (call);                               \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);    \
+  } while (0)
+
+static bool g_tw_uploaded[64] = {false};
+
+static int ensure_init() {
+  int dev = 0;
+  CSMRI_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(CSMRI_E_CUDA, "device index %d out of range", dev);
+  if (g_tw_uploaded[dev]) return CSMRI_OK;
+  static bool host_ready = false;
+  if (!host_ready) {
+    for (int m = 0; m < kTwN; ++m) {
+      const double a = -2.0 * M_PI * (double)m / (double)kTwN;
+      h_twiddle[m] = mk((float)cos(a), (float)sin(a));
+    }
+    // exact values on the axes and diagonals
+    h_twiddle[0] = mk(1.f, 0.f);
+    h_twiddle[kTwN / 4] = mk(0.f, -1.f);
+    h_twiddle[kTwN / 2] = mk(-1.f, 0.f);
+    h_twiddle[3 * kTwN / 4] = mk(0.f, 1.f);
+    host_ready = true;
+  }
+  CSMRI_CUDA(cudaMemcpyToSymbol(c_twiddle, h_twiddle, sizeof(cf) * kTwN));
+  g_tw_uploaded[dev] = true;
+  return CSMRI_OK;
+}
+
+static bool pow2_in(int n, int lo, int hi) { return n >= lo && n <= hi && (n & (n - 1)) == 0; }
+
+static int check_shape(int B, int H, int W) {
+  if (B <= 0) return fail(CSMRI_E_SHAPE, "batch must be positive, got %d", B);
+  if (!pow2_in(H, 32, 1024) || !pow2_in(W, 32, 1024))
+    return fail(CSMRI_E_SHAPE,
+                "unsupported slice size %dx%d: H and W must be powers of two in [32, 1024]", H, W);
+  if ((long long)B * H * W * 2 >= (1LL << 40)) return fail(CSMRI_E_SHAPE, "problem too large");
+  return CSMRI_OK;
+}
+static int check_ptr(const void* p, const char* name) {
+  if (p == nullptr) return fail(CSMRI_E_NULLPTR, "%s is NULL", name);
+  if (((uintptr_t)p & 3u) != 0) return fail(CSMRI_E_ALIGN, "%s is not 4-byte aligned", name);
+  return CSMRI_OK;
+}
+#define CSMRI_TRY(expr)            \
+  do {                             \
+    int rc_ = (expr);              \
+    if (rc_ != CSMRI_OK) return rc_; \
+  } while (0)
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  if (bytes > 48 * 1024)
+    CSMRI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return CSMRI_OK;
+}
+
+// ---- strip (column) launches ------------------------------------------------
+template <int H, int E, int CW, int MINB>
+static int launch_strip_row_cfg(const float* x, const float* residual, const float* dtab,
+                                const float* addend, float* out, int B, int W, cudaStream_t s) {
+  typedef LineFFT<H, E, CW> L;
+  const int nstrips = W / CW;
+  if (W == H) {  // square slices (every shipped config): compile-time row pitch
+    auto kern = dc_strip_row_kernel<H, E, CW, MINB, H>;
+    CSMRI_TRY(set_smem(kern, L::kSmemBytes));
+    kern<<<B * nstrips, CW * L::T, L::kSmemBytes, s>>>(x, residual, dtab, addend, out, W, nstrips);
+  } else {
+    auto kern = dc_strip_row_kernel<H, E, CW, MINB, 0>;
+    CSMRI_TRY(set_smem(kern, L::kSmemBytes));
+    kern<<<B * nstrips, CW * L::T, L::kSmemBytes, s>>>(x, residual, dtab, addend, out, W, nstrips);
+  }
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+static int g_strip_variant = 0;  // tuning knob, see csmri_set_variant
+
+static int launch_strip_row(const float* x, const float* residual, const float* dtab,
+                            const float* addend, float* out, int B, int H, int W,
+                            cudaStream_t s) {
+  switch (H) {
+    case 32: return launch_strip_row_cfg<32, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
+    case 64: return launch_strip_row_cfg<64, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
+    case 128: return launch_strip_row_cfg<128, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
+    case 256:
+      if (g_strip_variant == 1)
+        return launch_strip_row_cfg<256, 16, 16, 1>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 2)
+        return launch_strip_row_cfg<256, 32, 32, 1>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 3)
+        return launch_strip_row_cfg<256, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
+      return launch_strip_row_cfg<256, 16, 32, 2>(x, residual, dtab, addend, out, B, W, s);
+    case 512:
+      if (g_strip_variant == 1)
+        return launch_strip_row_cfg<512, 32, 32, 1>(x, residual, dtab, addend, out, B, W, s);
+      return launch_strip_row_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
+    case 1024: return launch_strip_row_cfg<1024, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
+  }
+  return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
+}
+
+template <int H, int E, int CW>
+static int launch_strip_dense_cfg(const float* hyb, const float* k0, const float* mask, float* out,
+                                  int B, int W, float sc, float nv, bool noisy, bool adj,
+                                  cudaStream_t s) {
+  typedef LineFFT<H, E, CW> L;
+  const int nstrips = W / CW;
+  const dim3 grid(B * nstrips), block(CW * L::T);
+#define CSMRI_DENSE(N_, A_)                                                           \
+  {                                                                                   \
+    auto kern = dc_strip_dense_kernel<H, E, CW, N_, A_>;                              \
+    CSMRI_TRY(set_smem(kern, L::kSmemBytes));                                         \
+    kern<<<grid, block, L::kSmemBytes, s>>>(hyb, k0, mask, out, W, nstrips, sc, nv); \
+  }
+  if (noisy && adj) CSMRI_DENSE(true, true)
+  else if (noisy) CSMRI_DENSE(true, false)
+  else if (adj) CSMRI_DENSE(false, true)
+  else CSMRI_DENSE(false, false)
+#undef CSMRI_DENSE
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+static int launch_strip_dense(const float* hyb, const float* k0, const float* mask, float* out,
+                              int B, int H, int W, float sc, float nv, bool noisy, bool adj,
+                              cudaStream_t s) {
+  switch (H) {
+    case 32: return launch_strip_dense_cfg<32, 8, 32>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 64: return launch_strip_dense_cfg<64, 8, 32>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 128: return launch_strip_dense_cfg<128, 16, 32>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 256: return launch_strip_dense_cfg<256, 16, 32>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 512: return launch_strip_dense_cfg<512, 32, 16>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 1024: return launch_strip_dense_cfg<1024, 32, 16>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+  }
+  return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
+}
+
+template <int H, int E, int CW>
+static int launch_fft_strip_cfg(const float* in, float* out, int B, int W, float scale, bool inv,
+                                const unsigned char* rows, cudaStream_t s) {
+  typedef LineFFT<H, E, CW> L;
+  const int nstrips = W / CW;
+  if (inv) {
+    auto kern = fft_strip_kernel<H, E, CW, true>;
+    CSMRI_TRY(set_smem(kern, L::kSmemBytes));
+    kern<<<B * nstrips, CW * L::T, L::kSmemBytes, s>>>(in, out, W, nstrips, scale, rows);
+  } else {
+    auto kern = fft_strip_kernel<H, E, CW, false>;
+    CSMRI_TRY(set_smem(kern, L::kSmemBytes));
+    kern<<<B * nstrips, CW * L::T, L::kSmemBytes, s>>>(in, out, W, nstrips, scale, rows);
+  }
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+static int launch_fft_strip(const float* in, float* out, int B, int H, int W, float scale, bool inv,
+                            const unsigned char* rows, cudaStream_t s) {
+  switch (H) {
+    case 32: return launch_fft_strip_cfg<32, 8, 32>(in, out, B, W, scale, inv, rows, s);
+    case 64: return launch_fft_strip_cfg<64, 8, 32>(in, out, B, W, scale, inv, rows, s);
+    case 128: return launch_fft_strip_cfg<128, 16, 32>(in, out, B, W, scale, inv, rows, s);
+    case 256: return launch_fft_strip_cfg<256, 16, 32>(in, out, B, W, scale, inv, rows, s);
+    case 512: return launch_fft_strip_cfg<512, 32, 16>(in, out, B, W, scale, inv, rows, s);
+    case 1024: return launch_fft_strip_cfg<1024, 32, 16>(in, out, B, W, scale, inv, rows, s);
+  }
+  return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
+}
+
+// ---- row launches -----------------------------------------------------------
+template <int W, int E, int CW>
+static int launch_fft_rows_cfg(const float* in, const float* aux, float* out, int B, int H,
+                               float scale, float cmulv, bool inv, int pre, cudaStream_t s) {
+  typedef LineFFT<W, E, CW> L;
+  constexpr int stage_bytes = 2 * CW * (W + 1) * (int)sizeof(float);
+  constexpr int smem = stage_bytes > L::kSmemBytes ? stage_bytes : L::kSmemBytes;
+  const dim3 grid(B * (H / CW)), block(CW * L::T);
+#define CSMRI_ROWS(I_, P_)                                              \
+  {                                                                     \
+    auto kern = fft_rows_kernel<W, E, CW, I_, P_>;                      \
+    CSMRI_TRY(set_smem(kern, smem));                                    \
+    kern<<<grid, block, smem, s>>>(in, aux, out, H, scale, cmulv);      \
+  }
+  if (!inv && pre == 0) CSMRI_ROWS(false, 0)
+  else if (!inv && pre == 1) CSMRI_ROWS(false, 1)
+  else if (!inv && pre == 3) CSMRI_ROWS(false, 3)
+  else if (inv && pre == 0) CSMRI_ROWS(true, 0)
+  else if (inv && pre == 2) CSMRI_ROWS(true, 2)
+  else return fail(CSMRI_E_ARG, "row kernel variant inv=%d pre=%d not instantiated", (int)inv, pre);
+#undef CSMRI_ROWS
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+static int launch_fft_rows(const float* in, const float* aux, float* out, int B, int H, int W,
+                           float scale, float cmulv, bool inv, int pre, cudaStream_t s) {
+  switch (W) {
+    case 32: return launch_fft_rows_cfg<32, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
+    case 64: return launch_fft_rows_cfg<64, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
+    case 128: return launch_fft_rows_cfg<128, 16, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
+    case 256: return launch_fft_rows_cfg<256, 16, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
+    case 512: return launch_fft_rows_cfg<512, 32, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
+    case 1024: return launch_fft_rows_cfg<1024, 32, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
+  }
+  return fail(CSMRI_E_SHAPE, "unsupported W=%d", W);
+}
+
+}  // namespace csmri
+
+using namespace csmri;
+
+extern "C" {
+
+int csmri_version(void) { return 100; }
+
+const char* csmri_last_error(void) { return g_err; }
+
+int csmri_init(void) { return ensure_init(); }
+
+// tuning knob for the benchmark harness (not part of the reference-facing ABI)
+int csmri_set_variant(int v) {
+  g_strip_variant = v;
+  return CSMRI_OK;
+}
+
+size_t csmri_dc_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)B * 2 * H * W * sizeof(float);
+}
+
+int csmri_dc_prepare(const float* k0, const float* mask, int B, int H, int W, float noise_lvl,
+                     float* dtab, float* addend, int* row_constant, void* scratch, void* stream) {
+  CSMRI_TRY(check_shape(B, H, W));
+  CSMRI_TRY(check_ptr(mask, "mask"));
+  CSMRI_TRY(check_ptr(dtab, "dtab"));
+  CSMRI_TRY(check_ptr(row_constant, "row_constant"));
+  CSMRI_TRY(ensure_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool noisy = noise_lvl != 0.0f;
+  set_flag_kernel<<<1, 1, 0, s>>>(row_constant, 1);
+  {
+    const int warps = B * H, threads = 256;
+    const int blocks = (warps * 32 + threads - 1) / threads;
+    mask_rows_kernel<<<blocks, threads, 0, s>>>(mask, B, H, W, noise_lvl, noisy ? 1 : 0, dtab,
+                                                row_constant);
+  }
+  CSMRI_CUDA(cudaGetLastError());
+  if (addend != nullptr) {
+    CSMRI_TRY(check_ptr(k0, "k0"));
+    CSMRI_TRY(check_ptr(scratch, "scratch"));
+    float* hyb = (float*)scratch;
+    const float sc = 1.0f / sqrtf((float)H * (float)W);
+    if (noisy) {
+      CSMRI_TRY(launch_fft_rows(k0, mask, hyb, B, H, W, 1.0f, noise_lvl / (1.0f + noise_lvl), true,
+                                2, s));
+    } else {
+      CSMRI_TRY(launch_fft_rows(k0, nullptr, hyb, B, H, W, 1.0f, 0.0f, true, 0, s));
+    }
+    CSMRI_TRY(launch_fft_strip(hyb, addend, B, H, W, sc, true, nullptr, s));
+  }
+  return CSMRI_OK;
+}
+
+int csmri_dc_forward_cartesian(const float* x, const float* residual, const float* dtab,
+                               const float* addend, float* out, int B, int H, int W,
+                               void* stream) {
+  CSMRI_TRY(check_shape(B, H, W));
+  if (H > 1024) return fail(CSMRI_E_SHAPE, "H too large");
+  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr(dtab, "dtab"));
+  CSMRI_TRY(check_ptr(out, "out"));
+  if (out == x || out == residual || out == addend)
+    return fail(CSMRI_E_ARG, "out must not alias an input");
+  CSMRI_TRY(ensure_init());
+  return launch_strip_row(x, residual, dtab, addend, out, B, H, W, (cudaStream_t)stream);
+}
+
+int csmri_dc_adjoint_cartesian(const float* grad_out, const float* dtab, float* grad_x, int B,
+                               int H, int W, void* stream) {
+  CSMRI_TRY(check_shape(B, H, W));
+  CSMRI_TRY(check_ptr(grad_out, "grad_out"));
+  CSMRI_TRY(check_ptr(dtab, "dtab"));
+  CSMRI_TRY(check_ptr(grad_x, "grad_x"));
+  if (grad_x == grad_out) return fail(CSMRI_E_ARG, "grad_x must not alias grad_out");
+  CSMRI_TRY(ensure_init());
+  return launch_strip_row(grad_out, nullptr, dtab, nullptr, grad_x, B, H, W,
+                          (cudaStream_t)stream);
+}
+
+int csmri_dc_forward_general(const float* x, const float* residual, const float* k0,
+                             const float* mask, float* out, int B, int H, int W, float noise_lvl,
+                             void* scratch, void* stream) {
+  CSMRI_TRY(check_shape(B, H, W));
+  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr(k0, "k0"));
+  CSMRI_TRY(check_ptr(mask, "mask"));
+  CSMRI_TRY(check_ptr(out, "out"));
+  CSMRI_TRY(check_ptr(scratch, "scratch"));
+  CSMRI_TRY(ensure_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  float* hyb = (float*)scratch;
+  const float sc = 1.0f / sqrtf((float)H * (float)W);
+  const bool noisy = noise_lvl != 0.0f;
+  CSMRI_TRY(launch_fft_rows(x, residual, hyb, B, H, W, 1.0f, 0.0f, false, residual ? 1 : 0, s));
+  CSMRI_TRY(launch_strip_dense(hyb, k0, mask, hyb, B, H, W, sc, noise_lvl, noisy, false, s));
+  CSMRI_TRY(launch_fft_rows(hyb, nullptr, out, B, H, W, 1.0f, 0.0f, true, 0, s));
+  return CSMRI_OK;
+}
+
+int csmri_dc_adjoint_general(const float* grad_out, const float* mask, float* grad_x, int B, int H,
+                             int W, float noise_lvl, void* scratch, void* stream) {
+  CSMRI_TRY(check_shape(B, H, W));
+  CSMRI_TRY(check_ptr(grad_out, "grad_out"));
+  CSMRI_TRY(check_ptr(mask, "mask"));
+  CSMRI_TRY(check_ptr(grad_x, "grad_x"));
+  CSMRI_TRY(check_ptr(scratch, "scratch"));
+  CSMRI_TRY(ensure_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  float* hyb = (float*)scratch;
+  const float sc = 1.0f / sqrtf((float)H * (float)W);
+  const bool noisy = noise_lvl != 0.0f;
+  CSMRI_TRY(launch_fft_rows(grad_out, nullptr, hyb, B, H, W, 1.0f, 0.0f, false, 0, s));
+  CSMRI_TRY(launch_strip_dense(hyb, nullptr, mask, hyb, B, H, W, sc, noise_lvl, noisy, true, s));
+  CSMRI_TRY(launch_fft_rows(hyb, nullptr, grad_x, B, H, W, 1.0f, 0.0f, true, 0, s));
+  return CSMRI_OK;
+}
+
+int csmri_dc_forward(const float* x, const float* residual, const float* k0, const float* mask,
+                     const float* dtab, const float* addend, float* out, int B, int H, int W,
+                     float noise_lvl, int mask_is_row_constant, void* scratch, void* stream) {
+  if (mask_is_row_constant) {
+    CSMRI_TRY(check_ptr(addend, "addend"));
+    return csmri_dc_forward_cartesian(x, residual, dtab, addend, out, B, H, W, stream);
+  }
+  return csmri_dc_forward_general(x, residual, k0, mask, out, B, H, W, noise_lvl, scratch, stream);
+}
+
+int csmri_dc_adjoint(const float* grad_out, const float* mask, const float* dtab, float* grad_x,
+                     int B, int H, int W, float noise_lvl, int mask_is_row_constant, void* scratch,
+                     void* stream) {
+  if (mask_is_row_constant)
+    return csmri_dc_adjoint_cartesian(grad_out, dtab, grad_x, B, H, W, stream);
+  return csmri_dc_adjoint_general(grad_out, mask, grad_x, B, H, W, noise_lvl, scratch, stream);
+}
+
+int csmri_undersample(const float* img, const unsigned char* rows, float* inp, float* kspace,
+                      float* mask, float* target, int B, int H, int W, void* scratch,
+                      void* stream) {
+  CSMRI_TRY(check_shape(B, H, W));
+  CSMRI_TRY(check_ptr(img, "img"));
+  if (rows == nullptr) return fail(CSMRI_E_NULLPTR, "rows is NULL");
+  CSMRI_TRY(check_ptr(inp, "inp"));
+  CSMRI_TRY(check_ptr(kspace, "kspace"));
+  CSMRI_TRY(check_ptr(mask, "mask"));
+  CSMRI_TRY(check_ptr(target, "target"));
+  CSMRI_TRY(check_ptr(scratch, "scratch"));
+  CSMRI_TRY(ensure_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  float* hyb = (float*)scratch;
+  const float sc = 1.0f / sqrtf((float)H * (float)W);
+  // x_f = fft2(x, ortho); x_fu = mask * x_f          (compressed_sensing.py:509-510)
+  CSMRI_TRY(launch_fft_rows(img, nullptr, hyb, B, H, W, 1.0f, 0.0f, false, 3, s));
+  CSMRI_TRY(launch_fft_strip(hyb, kspace, B, H, W, sc, false, rows, s));
+  // x_u = ifft2(x_fu, ortho)                         (compressed_sensing.py:511)
+  CSMRI_TRY(launch_fft_rows(kspace, nullptr, hyb, B, H, W, 1.0f, 0.0f, true, 0, s));
+  CSMRI_TRY(launch_fft_strip(hyb, inp, B, H, W, sc, true, nullptr, s));
+  expand_mask_target_kernel<<<148 * 8, 256, 0, s>>>(img, rows, mask, target, B, H, W);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+int csmri_fft2(const float* x, float* out, int B, int H, int W, int inverse, void* scratch,
+               void* stream) {
+  CSMRI_TRY(check_shape(B, H, W));
+  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr(out, "out"));
+  CSMRI_TRY(check_ptr(scratch, "scratch"));
+  CSMRI_TRY(ensure_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  const float sc = 1.0f / sqrtf((float)H * (float)W);
+  CSMRI_TRY(launch_fft_rows(x, nullptr, (float*)scratch, B, H, W, 1.0f, 0.0f, inverse != 0, 0, s));
+  CSMRI_TRY(launch_fft_strip((const float*)scratch, out, B, H, W, sc, inverse != 0, nullptr, s));
+  return CSMRI_OK;
+}
+
+}  // extern "C"

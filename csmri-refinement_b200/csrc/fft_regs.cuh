@@ -1,0 +1,237 @@
+// In-register complex FFT building blocks for the DC kernels (sm_100a).
+//
+// A complex number is a float2 {re, im}.  On the device every complex add,
+// subtract, +-i rotation and multiply is issued as packed FADD2 / FMUL2 /
+// FFMA2 (PTX add/mul/fma.rn.f32x2, new on sm_100): one instruction works on
+// the (re, im) pair, and the per-lane swap / negate the butterflies need are
+// free operand modifiers in SASS (.LO_HI, .NP).  The same templates compile as
+// plain scalar C++ on the host, which is how tests/test_host_emulation.py
+// checks the index logic without a GPU.
+//
+// Sizes 2, 4, 8, 16, 32 are fully unrolled radix-4/2 Cooley-Tukey with
+// compile-time twiddles, natural order in and out.  Sign convention is
+// numpy's (forward e^{-2 pi i nk/N}), the one the reference pins at
+// data/reconstruction/deep_med_lib/my_pytorch/myfft.py:225,241-242.
+#pragma once
+#include <cuda_runtime.h>
+
+#define CSMRI_HD __host__ __device__ __forceinline__
+
+namespace csmri {
+
+typedef float2 cf;
+
+#if defined(__CUDA_ARCH__) && !defined(CSMRI_SCALAR_MATH)
+#define CSMRI_PACKED 1
+#else
+#define CSMRI_PACKED 0
+#endif
+
+CSMRI_HD cf mk(float re, float im) { cf r; r.x = re; r.y = im; return r; }
+
+#if CSMRI_PACKED
+__device__ __forceinline__ cf f2add(cf a, cf b) {
+  cf r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5};"
+      " add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ cf f2sub(cf a, cf b) {
+  cf r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5};"
+      " sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ cf f2mul(cf a, cf b) {
+  cf r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5};"
+      " mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ cf f2fma(cf a, cf b, cf c) {
+  cf r;
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5};"
+      " mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+#else
+CSMRI_HD cf f2add(cf a, cf b) { return mk(a.x + b.x, a.y + b.y); }
+CSMRI_HD cf f2sub(cf a, cf b) { return mk(a.x - b.x, a.y - b.y); }
+CSMRI_HD cf f2mul(cf a, cf b) { return mk(a.x * b.x, a.y * b.y); }
+CSMRI_HD cf f2fma(cf a, cf b, cf c) {
+#ifdef __CUDA_ARCH__
+  return mk(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#else
+  return mk(__builtin_fmaf(a.x, b.x, c.x), __builtin_fmaf(a.y, b.y, c.y));
+#endif
+}
+#endif
+
+CSMRI_HD cf cadd(cf a, cf b) { return f2add(a, b); }
+CSMRI_HD cf csub(cf a, cf b) { return f2sub(a, b); }
+// a - i*b  and  a + i*b
+CSMRI_HD cf add_mi(cf a, cf b) { return f2fma(mk(b.y, -b.x), mk(1.f, 1.f), a); }
+CSMRI_HD cf add_pi(cf a, cf b) { return f2fma(mk(-b.y, b.x), mk(1.f, 1.f), a); }
+// a * w  (two packed instructions: FMUL2 + FFMA2)
+CSMRI_HD cf cmul(cf a, cf w) {
+  cf t = f2mul(mk(a.y, a.y), mk(-w.y, w.x));
+  return f2fma(mk(a.x, a.x), w, t);
+}
+// a * conj(w)
+CSMRI_HD cf cmul_conj(cf a, cf w) {
+  cf t = f2mul(mk(a.y, a.y), mk(w.y, w.x));
+  return f2fma(mk(a.x, a.x), mk(w.x, -w.y), t);
+}
+CSMRI_HD cf cscale(cf a, float s) { return f2mul(a, mk(s, s)); }
+
+// ---------------------------------------------------------------------------
+// compile-time twiddles: cos/sin(2 pi k / n) evaluated in double by Taylor
+// series after octant reduction (error < 2e-15, i.e. correctly rounded floats)
+// ---------------------------------------------------------------------------
+__host__ __device__ constexpr double ct_pi() { return 3.14159265358979323846264338327950288; }
+__host__ __device__ constexpr double ct_sin(double x) {
+  double x2 = x * x, t = x, s = x;
+  for (int i = 1; i < 14; ++i) { t *= -x2 / ((2 * i) * (2 * i + 1)); s += t; }
+  return s;
+}
+__host__ __device__ constexpr double ct_cos(double x) {
+  double x2 = x * x, t = 1, s = 1;
+  for (int i = 1; i < 14; ++i) { t *= -x2 / ((2 * i - 1) * (2 * i)); s += t; }
+  return s;
+}
+__host__ __device__ constexpr double ct_cos2pi(int k, int n) {
+  k %= n;
+  if (k < 0) k += n;
+  if ((8 * k) % n == 0) {                 // exact multiples of pi/4
+    const double h = 0.70710678118654752440084436210484903928;
+    switch ((8 * k) / n) {
+      case 0: return 1; case 1: return h; case 2: return 0; case 3: return -h;
+      case 4: return -1; case 5: return -h; case 6: return 0; default: return h;
+    }
+  }
+  int oct = (int)((8LL * k) / n);
+  double r = 2 * ct_pi() * ((double)k / n) - oct * (ct_pi() / 4);
+  switch (oct) {
+    case 0: return ct_cos(r);
+    case 1: return ct_sin(ct_pi() / 4 - r);
+    case 2: return -ct_sin(r);
+    case 3: return -ct_cos(ct_pi() / 4 - r);
+    case 4: return -ct_cos(r);
+    case 5: return -ct_sin(ct_pi() / 4 - r);
+    case 6: return ct_sin(r);
+    default: return ct_cos(ct_pi() / 4 - r);
+  }
+}
+// sin(2 pi k/n) = cos(2 pi k/n - pi/2) = cos(2 pi (4k - n)/(4n))
+__host__ __device__ constexpr double ct_sin2pi(int k, int n) { return ct_cos2pi(4 * k - n, 4 * n); }
+
+// multiply by W_N^K (forward, e^{-2 pi i K/N}) or its conjugate (INV)
+template <int K, int N, bool INV>
+CSMRI_HD cf twiddle(cf a) {
+  constexpr int KK = ((K % N) + N) % N;
+  if constexpr (KK == 0) {
+    return a;
+  } else if constexpr (4 * KK == N) {            // -i (fwd) / +i (inv)
+    return INV ? mk(-a.y, a.x) : mk(a.y, -a.x);
+  } else if constexpr (2 * KK == N) {
+    return mk(-a.x, -a.y);
+  } else if constexpr (4 * KK == 3 * N) {        // +i (fwd) / -i (inv)
+    return INV ? mk(a.y, -a.x) : mk(-a.y, a.x);
+  } else {
+    constexpr float c = (float)ct_cos2pi(KK, N);
+    constexpr float s = (float)ct_sin2pi(KK, N);
+    return cmul(a, mk(c, INV ? s : -s));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// butterflies, in place, natural order
+// ---------------------------------------------------------------------------
+template <bool INV>
+CSMRI_HD void fft2(cf& a0, cf& a1) {
+  cf t = cadd(a0, a1);
+  a1 = csub(a0, a1);
+  a0 = t;
+}
+
+template <bool INV>
+CSMRI_HD void fft4(cf& a0, cf& a1, cf& a2, cf& a3) {
+  cf t0 = cadd(a0, a2), t1 = csub(a0, a2);
+  cf t2 = cadd(a1, a3), t3 = csub(a1, a3);
+  a0 = cadd(t0, t2);
+  a2 = csub(t0, t2);
+  if (INV) { a1 = add_pi(t1, t3); a3 = add_mi(t1, t3); }
+  else     { a1 = add_mi(t1, t3); a3 = add_pi(t1, t3); }
+}
+
+template <int N, bool INV> struct RegFFT;
+
+template <bool INV> struct RegFFT<1, INV> {
+  static CSMRI_HD void run(cf*) {}
+};
+template <bool INV> struct RegFFT<2, INV> {
+  static CSMRI_HD void run(cf* v) { fft2<INV>(v[0], v[1]); }
+};
+template <bool INV> struct RegFFT<4, INV> {
+  static CSMRI_HD void run(cf* v) { fft4<INV>(v[0], v[1], v[2], v[3]); }
+};
+
+// Generic two-factor step N = A*B on a register array (all loops unroll):
+//   B sub-FFTs of size A over v[n2 + B*n1], twiddle W_N^{n2*k1},
+//   A sub-FFTs of size B over n2, then the compile-time transpose that puts
+//   X[k1 + A*k2] at v[k1 + A*k2].
+template <int N, int A, int B, bool INV>
+struct RegFFT2F {
+  template <int N2>
+  static CSMRI_HD void stage1(cf* v) {
+    if constexpr (N2 < B) {
+      cf t[A];
+#pragma unroll
+      for (int n1 = 0; n1 < A; ++n1) t[n1] = v[N2 + B * n1];
+      RegFFT<A, INV>::run(t);
+      tw_row<N2, 0>(t);
+#pragma unroll
+      for (int k1 = 0; k1 < A; ++k1) v[N2 + B * k1] = t[k1];
+      stage1<N2 + 1>(v);
+    }
+  }
+  template <int N2, int K1>
+  static CSMRI_HD void tw_row(cf* t) {
+    if constexpr (K1 < A) {
+      t[K1] = twiddle<N2 * K1, N, INV>(t[K1]);
+      tw_row<N2, K1 + 1>(t);
+    }
+  }
+  static CSMRI_HD void run(cf* v) {
+    stage1<0>(v);
+    cf w[N];
+#pragma unroll
+    for (int k1 = 0; k1 < A; ++k1) {
+      cf t[B];
+#pragma unroll
+      for (int n2 = 0; n2 < B; ++n2) t[n2] = v[n2 + B * k1];
+      RegFFT<B, INV>::run(t);
+#pragma unroll
+      for (int k2 = 0; k2 < B; ++k2) w[k1 + A * k2] = t[k2];
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = w[i];
+  }
+};
+
+template <bool INV> struct RegFFT<8, INV> {
+  static CSMRI_HD void run(cf* v) { RegFFT2F<8, 4, 2, INV>::run(v); }
+};
+template <bool INV> struct RegFFT<16, INV> {
+  static CSMRI_HD void run(cf* v) { RegFFT2F<16, 4, 4, INV>::run(v); }
+};
+template <bool INV> struct RegFFT<32, INV> {
+  static CSMRI_HD void run(cf* v) { RegFFT2F<32, 4, 8, INV>::run(v); }
+};
+
+}  // namespace csmri

@@ -1,0 +1,105 @@
+"""Drop-in for data/reconstruction/deep_med_lib/my_pytorch/myfft.py:145-163.
+
+``DataConsistencyInKspace(noise_lvl=None, norm='ortho').perform(x, k0, mask)``
+keeps the reference's name, arguments and semantics; the work is done by the
+sm_100a kernels of ``csrc/csmri_dc.cu`` through the C ABI.  Like the reference
+object it is not an ``nn.Module`` and owns no parameters or buffers, so
+``RecNet.state_dict()`` keeps its keys (models/recnet.py:128-134: ``dc_layers``
+is a plain list).
+
+``k0`` and ``mask`` are the same tensors for every DC layer of a cascade
+(models/recnet.py:139-151), so what depends only on them - the proof that the
+mask is row-constant (compressed_sensing.py:115-116), the per-row diagonal and
+``iFFT2(k0)`` - is computed once per batch and cached here.
+"""
+import collections
+
+import torch
+
+from . import ops
+
+
+class DCPlan(object):
+    """Per-batch constants of the DC operator (see csmri_dc_prepare)."""
+
+    __slots__ = ('k0', 'mask', 'noise_lvl', 'dtab', 'addend', 'row_constant', 'key')
+
+    def __init__(self, k0, mask, noise_lvl, assume_row_constant=None):
+        v = float(noise_lvl) if noise_lvl else 0.0   # `if v:` of myfft.py:137
+        self.k0, self.mask, self.noise_lvl = k0, mask, v
+        dtab, addend, flag = ops.dc_prepare(k0.detach(), mask.detach(), v)
+        self.dtab, self.addend = dtab, addend
+        if assume_row_constant is None:
+            # one 4-byte device->host read per batch
+            self.row_constant = bool(flag.item())
+        else:
+            self.row_constant = bool(assume_row_constant)
+        if not self.row_constant:
+            self.addend = None
+
+
+def _tensor_key(t):
+    return (t.data_ptr(), t.storage_offset(), tuple(t.shape), tuple(t.stride()), t._version,
+            t.device.index)
+
+
+_PLAN_CACHE = collections.OrderedDict()
+_PLAN_CACHE_SIZE = 4
+
+
+def get_plan(k0, mask, noise_lvl=None, assume_row_constant=None):
+    """Cached :class:`DCPlan` for this (k0, mask, noise_lvl).
+
+    The cache keeps the two tensors alive, so their storage cannot be handed
+    to another batch while an entry exists; in-place writes bump ``_version``
+    and miss.  Entries are evicted LRU (4 batches).
+    """
+    v = float(noise_lvl) if noise_lvl else 0.0
+    key = (_tensor_key(k0), _tensor_key(mask), v, assume_row_constant)
+    plan = _PLAN_CACHE.get(key)
+    if plan is not None:
+        _PLAN_CACHE.move_to_end(key)
+        return plan
+    plan = DCPlan(k0, mask, v, assume_row_constant)
+    plan.key = key
+    _PLAN_CACHE[key] = plan
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def clear_plan_cache():
+    _PLAN_CACHE.clear()
+
+
+def data_consistency(x, k0, mask, noise_lvl=None, residual=None, plan=None):
+    """iFFT2o(blend(FFT2o(x [+ residual]), k0, mask)) - myfft.py:131-163 in one op."""
+    if not x.is_cuda:
+        raise RuntimeError('DataConsistencyInKspace needs CUDA tensors: the B200 DC path has '
+                           'no CPU fallback (use oracle/ for CPU checks)')
+    if plan is None:
+        plan = get_plan(k0, mask, noise_lvl)
+    if plan.row_constant:
+        return ops.dc_cartesian(x, residual, plan.dtab, plan.addend)
+    return ops.dc_general(x, residual, plan.k0, plan.mask, plan.noise_lvl)
+
+
+class DataConsistencyInKspace(object):
+    """Create data consistency operator (interface of myfft.py:145-163)."""
+
+    def __init__(self, noise_lvl=None, norm='ortho'):
+        if norm != 'ortho':
+            # models/recnet.py:131 only ever builds norm='ortho'
+            raise ValueError("only norm='ortho' is supported, got %r" % (norm,))
+        self.noise_lvl = noise_lvl
+        self.norm = norm
+
+    def perform(self, x, k0, mask, residual=None):
+        """
+        x    - input in image space, (B,2,H,W)
+        k0   - initially sampled elements in k-space
+        mask - corresponding nonzero location
+        residual - optional extension: added to x before the transform
+                   (the `x + block_input` of models/recnet.py:147-148)
+        """
+        return data_consistency(x, k0, mask, self.noise_lvl, residual)

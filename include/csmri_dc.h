@@ -1,0 +1,142 @@
+/* csmri_dc.h - C ABI of libcsmri_dc.so, the B200 (sm_100a) drop-in for the
+ * k-space data-consistency (DC) hot path of mseitzer/csmri-refinement.
+ *
+ * The reference has no FFI of its own for this path (it is pure Python on top
+ * of the third-party CUDA package pytorch-fft 0.14); each entry point below
+ * names the reference interface it replaces (paths relative to the reference
+ * root).  Tensors are fp32, NCHW contiguous, C = 2 planar (channel 0 = Re,
+ * channel 1 = Im) exactly as data/reconstruction/deep_med_lib/utils/dnn_io.py:4-22
+ * produces them: element (b,c,h,w) lives at ((b*2+c)*H+h)*W+w.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching
+ *     allocator); the library allocates nothing except one immutable twiddle
+ *     table per device (constant memory, uploaded by csmri_init / first use);
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*; NULL is
+ *     the legacy default stream) and never synchronise;
+ *   - return value 0 = ok, negative = CSMRI_E_*; csmri_last_error() returns a
+ *     thread-local message.  Unsupported sizes are an error, never a fallback;
+ *   - H and W must be powers of two in [32, 1024] (H up to 512 for the strip
+ *     kernels); outputs must not alias inputs unless stated.
+ */
+#ifndef CSMRI_DC_H_
+#define CSMRI_DC_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSMRI_OK 0
+#define CSMRI_E_SHAPE (-1)    /* unsupported B/H/W                     */
+#define CSMRI_E_NULLPTR (-2)  /* required pointer is NULL              */
+#define CSMRI_E_ALIGN (-3)    /* pointer not 4-byte aligned            */
+#define CSMRI_E_CUDA (-4)     /* CUDA runtime error, see last_error    */
+#define CSMRI_E_ARG (-5)      /* bad scalar argument                   */
+
+int csmri_version(void);
+const char* csmri_last_error(void);
+
+/* Upload the twiddle table to the current device.  Optional (done lazily by
+ * every call below), but must have happened before CUDA-graph capture. */
+int csmri_init(void);
+
+/* Bytes of scratch the *_general / prepare / undersample entry points need
+ * for a (B,2,H,W) problem (one hybrid-space tensor). */
+size_t csmri_dc_workspace_bytes(int B, int H, int W);
+
+/* ---- once per batch ------------------------------------------------------
+ * Replaces nothing in the reference one-to-one: k0 and mask are constant over
+ * the cascade (models/recnet.py:139-151 passes the same kspace, mask to every
+ * dc_layers[idx].perform), so everything that depends only on them is hoisted.
+ *
+ *   dtab   (B,H)      out: D[b,h]/H with D = 1-m (noiseless) or (1-m)+m/(1+v),
+ *                          m = mask[b,0,h,0]   (autograd of myfft.py:139,141)
+ *   addend (B,2,H,W)  out: iFFT2_ortho(c*k0), c = 1 (noiseless) or m*v/(1+v)
+ *                          (the k0 term of myfft.py:139,141 after Ifft2d,
+ *                          myfft.py:110-117); may be NULL to skip
+ *   row_constant      out: device int, set to 1 iff every mask row is constant
+ *                          along W and mask[:,0]==mask[:,1] (the property of
+ *                          compressed_sensing.py:115-116 that the Cartesian
+ *                          strip kernel relies on), else 0
+ *   scratch           csmri_dc_workspace_bytes(B,H,W) bytes
+ * noise_lvl <= 0 or NaN-free 0 selects the noiseless branch (`if v:`,
+ * myfft.py:137-138).
+ */
+int csmri_dc_prepare(const float* k0, const float* mask, int B, int H, int W,
+                     float noise_lvl, float* dtab, float* addend,
+                     int* row_constant, void* scratch, void* stream);
+
+/* ---- DC forward, Cartesian (row-constant) masks ---------------------------
+ * Replaces DataConsistencyInKspace.perform (myfft.py:153-163) =
+ * Fft2d.forward (:83-90) + data_consistency (:131-142) + Ifft2d.forward
+ * (:110-117) + both torch.cat (:159,161), and optionally the residual add of
+ * models/recnet.py:147-148 (residual may be NULL).
+ *   out = iFFT_H( dtab * FFT_H(x [+ residual]) ) + addend        per column
+ * One kernel, one pass over HBM: reads x (+residual) and addend, writes out.
+ */
+int csmri_dc_forward_cartesian(const float* x, const float* residual,
+                               const float* dtab, const float* addend,
+                               float* out, int B, int H, int W, void* stream);
+
+/* ---- DC adjoint (backward), Cartesian masks -------------------------------
+ * Replaces Ifft2d.backward (myfft.py:119-128) + autograd of the blend +
+ * Fft2d.backward (myfft.py:92-102):  gx = iFFT_H( dtab * FFT_H(g) ).
+ * The operator is self-adjoint, so this is the forward without the addend.
+ */
+int csmri_dc_adjoint_cartesian(const float* grad_out, const float* dtab,
+                               float* grad_x, int B, int H, int W,
+                               void* stream);
+
+/* ---- DC forward / adjoint, arbitrary masks ---------------------------------
+ * Same reference functions as above, evaluated as written for any mask:
+ * row FFT -> (column FFT, blend with k0 under the dense mask, column iFFT)
+ * -> row iFFT; three kernels, the hybrid tensor lives in `scratch`.
+ */
+int csmri_dc_forward_general(const float* x, const float* residual,
+                             const float* k0, const float* mask, float* out,
+                             int B, int H, int W, float noise_lvl,
+                             void* scratch, void* stream);
+int csmri_dc_adjoint_general(const float* grad_out, const float* mask,
+                             float* grad_x, int B, int H, int W,
+                             float noise_lvl, void* scratch, void* stream);
+
+/* ---- unified entry point ---------------------------------------
+ * mask_is_row_constant != 0: dtab/addend from csmri_dc_prepare are used and
+ * k0/mask may be NULL; == 0: the general path is taken and dtab/addend may be
+ * NULL.  adjoint: pass k0 = addend = NULL.
+ */
+int csmri_dc_forward(const float* x, const float* residual, const float* k0,
+                     const float* mask, const float* dtab, const float* addend,
+                     float* out, int B, int H, int W, float noise_lvl,
+                     int mask_is_row_constant, void* scratch, void* stream);
+int csmri_dc_adjoint(const float* grad_out, const float* mask,
+                     const float* dtab, float* grad_x, int B, int H, int W,
+                     float noise_lvl, int mask_is_row_constant, void* scratch,
+                     void* stream);
+
+/* ---- undersampling (loader side) -------------------------------------------
+ * Replaces cs.undersample (deep_med_lib/utils/compressed_sensing.py:460-512,
+ * centred=False, norm='ortho', noise=0) + dnn_io.to_tensor_format
+ * (dnn_io.py:47-61) x4 + the channel split of scar_segmentation.py:212-218.
+ *   img   (B,H,W)  real image in [0,1]
+ *   rows  (B,H)    uint8, 1 = sampled phase-encode line (already ifftshift-ed;
+ *                  chosen on the HOST by compressed_sensing.py:82-123 because
+ *                  numpy's legacy RandomState cannot be reproduced on device)
+ *   inp, kspace, mask, target: (B,2,H,W) outputs
+ */
+int csmri_undersample(const float* img, const unsigned char* rows, float* inp,
+                      float* kspace, float* mask, float* target, int B, int H,
+                      int W, void* scratch, void* stream);
+
+/* Plain ortho FFT2 / iFFT2 of a planar complex batch (Fft2d / Ifft2d forward,
+ * myfft.py:78-128); inverse != 0 selects the inverse.  Used by the tests to
+ * check the conventions pinned at myfft.py:225,241-242. */
+int csmri_fft2(const float* x, float* out, int B, int H, int W, int inverse,
+               void* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSMRI_DC_H_ */

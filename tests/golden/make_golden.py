@@ -134,9 +134,9 @@ def main():
     for blk in net.conv_blocks:
         initialize_weights(blk, {})
     net.dc_layers = [RefBlendDC() for _ in net.dc_layers]
-    nn_ = 16
+    nn_ = 32
     img = torch.from_numpy(rs.uniform(0, 1, (2, nn_, nn_)))
-    mk = cs.cartesian_mask((2, nn_, nn_), 2, 4, centred=False,
+    mk = cs.cartesian_mask((2, nn_, nn_), 4, 4, centred=False,
                            rng=np.random.RandomState(0))
     xu, xfu = cs.undersample(img.numpy(), mk, centred=False, norm='ortho',
                              rng=np.random.RandomState(0))

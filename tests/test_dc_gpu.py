@@ -1,0 +1,312 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle
+and the reference-generated golden fixtures.
+
+Tolerance: north_star states relative L2 <= 1e-5 in fp32 for outputs and
+gradients (expected ~2e-7); mask / sampled-line selection must be bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _mods():
+    from csmri_refinement_b200 import myfft, ops, recnet, undersampling
+    return myfft, ops, recnet, undersampling
+
+
+def _problem(B, H, W, acc=4, seed=0, general=False):
+    rs = np.random.RandomState(seed)
+    if general:
+        m1 = (rs.uniform(size=(B, H, W)) < 1.0 / acc).astype(np.float64)
+    else:
+        rows = orc.cartesian_lines(B, H, acc, 8, np.random.RandomState(seed))
+        rows = np.fft.ifftshift(rows, axes=-1)
+        m1 = np.broadcast_to(rows[:, :, None], (B, H, W)).copy()
+    img = rs.uniform(0, 1, (B, H, W))
+    k0c = m1 * np.fft.fft2(img, norm='ortho')
+    x = rs.normal(size=(B, 2, H, W)).astype(np.float32)
+    k0 = orc.complex_to_planar(k0c, np.float32)
+    mask = np.stack([m1, m1], 1).astype(np.float32)
+    return x, k0, mask
+
+
+def _cuda(*arrs):
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs]
+
+
+@pytest.mark.parametrize('H,W', [(32, 32), (64, 64), (128, 128), (256, 256), (512, 512),
+                                 (64, 128), (256, 64), (1024, 32)])
+@pytest.mark.parametrize('inverse', [False, True])
+def test_fft2_conventions(H, W, inverse):
+    """myfft.py:225,241-242: equals np.fft.fft2 / ifft2 with norm='ortho'."""
+    _, ops, _, _ = _mods()
+    rs = np.random.RandomState(H + W)
+    x = rs.normal(size=(3, 2, H, W)).astype(np.float32)
+    (xd,) = _cuda(x)
+    got = ops.fft2_planar(xd, inverse=inverse).cpu().numpy()
+    f = np.fft.ifft2 if inverse else np.fft.fft2
+    ref = orc.complex_to_planar(f(orc.planar_to_complex(x.astype(np.float64)), norm='ortho'),
+                                np.float64)
+    assert orc.rel_l2(got, ref) < 2e-6
+
+
+@pytest.mark.parametrize('N', [32, 64, 128, 256, 512])
+@pytest.mark.parametrize('noise', [None, 0.1])
+def test_cartesian_forward_and_adjoint(N, noise):
+    myfft, _, _, _ = _mods()
+    B = 3
+    x, k0, mask = _problem(B, N, N, acc=4, seed=N)
+    xd, k0d, md = _cuda(x, k0, mask)
+    xd.requires_grad_(True)
+    dc = myfft.DataConsistencyInKspace(noise_lvl=noise)
+    plan = myfft.get_plan(k0d, md, noise)
+    assert plan.row_constant
+    out = dc.perform(xd, k0d, md)
+    ref = orc.dc_perform_np(x, k0, mask, noise)
+    assert orc.rel_l2(out.detach().cpu().numpy(), ref) < TOL
+    # fp32 torch arm of the oracle (what the reference computes in fp32)
+    ref32 = orc.dc_perform_torch(torch.from_numpy(x), torch.from_numpy(k0),
+                                 torch.from_numpy(mask), noise).numpy()
+    assert orc.rel_l2(out.detach().cpu().numpy(), ref32) < TOL
+    w = np.random.RandomState(1).normal(size=x.shape).astype(np.float32)
+    (wd,) = _cuda(w)
+    (out * wd).sum().backward()
+    gref = orc.dc_adjoint_np(w, mask, noise)
+    assert orc.rel_l2(xd.grad.cpu().numpy(), gref) < TOL
+
+
+@pytest.mark.parametrize('H,W', [(32, 32), (128, 64), (256, 256), (64, 512)])
+@pytest.mark.parametrize('noise', [None, 0.25])
+def test_general_mask_forward_and_adjoint(H, W, noise):
+    myfft, _, _, _ = _mods()
+    x, k0, mask = _problem(2, H, W, acc=3, seed=H * 7 + W, general=True)
+    xd, k0d, md = _cuda(x, k0, mask)
+    xd.requires_grad_(True)
+    plan = myfft.get_plan(k0d, md, noise)
+    assert not plan.row_constant
+    out = myfft.DataConsistencyInKspace(noise_lvl=noise).perform(xd, k0d, md)
+    ref = orc.dc_perform_np(x, k0, mask, noise)
+    assert orc.rel_l2(out.detach().cpu().numpy(), ref) < TOL
+    w = np.random.RandomState(2).normal(size=x.shape).astype(np.float32)
+    (wd,) = _cuda(w)
+    (out * wd).sum().backward()
+    assert orc.rel_l2(xd.grad.cpu().numpy(), orc.dc_adjoint_np(w, mask, noise)) < TOL
+
+
+def test_cartesian_equals_general_path():
+    """the 1-D column reduction is the 2-D chain for row-constant masks."""
+    myfft, ops, _, _ = _mods()
+    x, k0, mask = _problem(4, 256, 256, acc=8, seed=3)
+    xd, k0d, md = _cuda(x, k0, mask)
+    a = myfft.data_consistency(xd, k0d, md, None)
+    b = ops.dc_general(xd, None, k0d, md, 0.0)
+    assert orc.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
+    a = myfft.data_consistency(xd, k0d, md, 0.1)
+    b = ops.dc_general(xd, None, k0d, md, 0.1)
+    assert orc.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
+
+
+def test_residual_operand():
+    """models/recnet.py:147-148 folded into the kernel: DC(x + r) == perform(x, residual=r)."""
+    myfft, ops, _, _ = _mods()
+    x, k0, mask = _problem(2, 128, 128, seed=5)
+    r = np.random.RandomState(9).normal(size=x.shape).astype(np.float32)
+    xd, k0d, md, rd = _cuda(x, k0, mask, r)
+    xd.requires_grad_(True)
+    rd.requires_grad_(True)
+    out = myfft.DataConsistencyInKspace().perform(xd, k0d, md, residual=rd)
+    ref = orc.dc_perform_np(x.astype(np.float64) + r, k0, mask)
+    assert orc.rel_l2(out.detach().cpu().numpy(), ref) < TOL
+    out.square().sum().backward()
+    assert torch.equal(xd.grad, rd.grad)
+    g = orc.dc_adjoint_np(2 * ref, mask)
+    assert orc.rel_l2(xd.grad.cpu().numpy(), g) < TOL
+    # general path too
+    xg, k0g, mg = _problem(2, 64, 64, seed=6, general=True)
+    xgd, k0gd, mgd, rgd = _cuda(xg, k0g, mg, r[:, :, :64, :64].copy())
+    out = ops.dc_general(xgd, rgd, k0gd, mgd, 0.0)
+    ref = orc.dc_perform_np(xg.astype(np.float64) + r[:, :, :64, :64], k0g, mg)
+    assert orc.rel_l2(out.cpu().numpy(), ref) < TOL
+
+
+def test_golden_numpy_dc(golden_dir):
+    """Reference cs.data_consistency outputs (compressed_sensing.py:515-529)."""
+    myfft, _, _, _ = _mods()
+    g = np.load(os.path.join(golden_dir, 'undersample_dc.npz'))
+    x = orc.complex_to_planar(g['xin'], np.float32)
+    for k0c, m1, want in ((g['x_fu'], g['mask'], g['xd']), (g['gk0'], g['gmask'], g['xd_g'])):
+        k0 = orc.complex_to_planar(k0c, np.float32)
+        m = np.stack([m1, m1], 1).astype(np.float32)
+        xd, k0d, md = _cuda(x, k0, m)
+        out = myfft.DataConsistencyInKspace().perform(xd, k0d, md).cpu().numpy()
+        assert orc.rel_l2(out, orc.complex_to_planar(want, np.float64)) < TOL
+
+
+def test_golden_noisy_chain(golden_dir):
+    myfft, _, _, _ = _mods()
+    g = np.load(os.path.join(golden_dir, 'recnet_tiny.npz'))
+    inp, k0, m = _cuda(g['inp'], g['kspace'], g['mask'])
+    out = myfft.DataConsistencyInKspace(noise_lvl=0.1).perform(inp * 0.5 + 0.1, k0, m)
+    assert orc.rel_l2(out.cpu().numpy(), g['dc_noisy_0p1']) < TOL
+
+
+def test_golden_undersample_group(golden_dir):
+    """Reference Undersample.__call__ outputs: mask bit-exact, k-space support
+    bit-exact, values within tolerance."""
+    _, _, _, us = _mods()
+    g = np.load(os.path.join(golden_dir, 'undersample_group.npz'))
+    n = g['im1'].shape[0]
+    tr = us.Undersample('varden', (1, n, n), acceleration_rate=4, fixed_mask=True,
+                        num_fixed_masks=2)
+    imgs = np.stack([g['im1'][:, :, 0], g['im2'][:, :, 0]]).astype(np.float32)
+    (imd,) = _cuda(imgs)
+    batch = tr(imd)
+    for i, key in enumerate(('grp1', 'grp2')):
+        grp = g[key].transpose(2, 0, 1)            # (8,n,n): inp,kspace,mask,target
+        got = {k: v[i].cpu().numpy() for k, v in batch.items()}
+        assert np.array_equal(got['mask'], grp[4:6])                 # bit-exact
+        assert np.array_equal(got['kspace'] != 0, grp[2:4] != 0)     # support
+        assert np.array_equal(got['target'], grp[6:8])
+        assert orc.rel_l2(got['kspace'], grp[2:4]) < TOL
+        assert orc.rel_l2(got['inp'], grp[0:2]) < TOL
+
+
+@pytest.mark.parametrize('N,acc', [(128, 4), (256, 8), (512, 12)])
+def test_undersample_vs_oracle(N, acc):
+    _, _, _, us = _mods()
+    B = 3
+    rs = np.random.RandomState(N)
+    img = rs.uniform(0, 1, (B, N, N))
+    rows = us.cartesian_rows((B, N, N), acc, 8, False, np.random.RandomState(0))
+    mask = orc.cartesian_mask((B, N, N), acc, 8, False, np.random.RandomState(0))
+    assert np.array_equal(rows, mask[:, :, 0].astype(np.uint8))
+    x_u, x_fu = orc.undersample(img, mask, rng=np.random.RandomState(0))
+    (imd,) = _cuda(img.astype(np.float32))
+    batch = us.undersample(imd, rows)
+    assert np.array_equal(batch['mask'].cpu().numpy(),
+                          orc.to_tensor_format(mask, mask=True))
+    ks = batch['kspace'].cpu().numpy()
+    assert np.array_equal(ks != 0, orc.to_tensor_format(x_fu) != 0)
+    assert orc.rel_l2(ks, orc.complex_to_planar(x_fu, np.float64)) < TOL
+    assert orc.rel_l2(batch['inp'].cpu().numpy(), orc.complex_to_planar(x_u, np.float64)) < TOL
+    assert np.array_equal(batch['target'].cpu().numpy(), orc.to_tensor_format(img))
+
+
+def test_recnet_matches_reference_golden(golden_dir):
+    """The reference's own RecNet (models/recnet.py) output, loss and weight
+    gradients, reproduced by the mirror with the CUDA DC layers."""
+    _, _, recnet, _ = _mods()
+    g = np.load(os.path.join(golden_dir, 'recnet_tiny.npz'))
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        net = recnet.RecNet(num_blocks=2, num_convs=3, num_filters=4)
+        sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('w:')}
+        assert set(sd) == set(net.state_dict())
+        net.load_state_dict(sd)
+        net.cuda()
+        inp, ksp, msk, tgt = _cuda(g['inp'], g['kspace'], g['mask'], g['target'])
+        out = net(inp, ksp, msk)
+        assert orc.rel_l2(out.detach().cpu().numpy(), g['out']) < TOL
+        loss = torch.nn.functional.mse_loss(out, tgt)
+        assert abs(loss.item() - float(g['loss'])) < 1e-5 * abs(float(g['loss']))
+        loss.backward()
+        for name, p in net.named_parameters():
+            assert orc.rel_l2(p.grad.cpu().numpy(), g['g:' + name]) < 2e-5, name
+        net2 = recnet.RecNet(num_blocks=2, num_convs=3, num_filters=4, use_refinement=True,
+                             return_intermediate_recs=True, skip_final_dc=True)
+        net2.load_state_dict(sd)
+        net2.cuda()
+        o2 = net2(inp, ksp, msk)
+        assert len(o2['reconstructions']) == int(g['n_refine_recs'])
+        assert orc.rel_l2(o2['pred'].detach().cpu().numpy(), g['out_refine_pred']) < TOL
+        assert orc.rel_l2(o2['reconstructions'][0].detach().cpu().numpy(),
+                          g['out_refine_rec0']) < TOL
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (B=256, 256^2): size-independent properties."""
+    myfft, ops, _, us = _mods()
+    B, N = 256, 256
+    g = torch.Generator(device='cuda').manual_seed(0)
+    img = torch.rand(B, N, N, device='cuda', generator=g)
+    rows = us.cartesian_rows((B, N, N), 4, 8, False, np.random.RandomState(0))
+    batch = us.undersample(img, rows)
+    k0, mask, inp = batch['kspace'], batch['mask'], batch['inp']
+    dc = myfft.DataConsistencyInKspace()
+    # (ii)/(i) inp == iFFT2(k0) and DC is idempotent on it
+    out = dc.perform(inp, k0, mask)
+    assert (out - inp).norm().item() < TOL * inp.norm().item()
+    x = torch.randn(B, 2, N, N, device='cuda', generator=g)
+    y = torch.randn(B, 2, N, N, device='cuda', generator=g)
+    plan = myfft.get_plan(k0, mask)
+    A = lambda t: ops.dc_cartesian(t, None, plan.dtab, None)   # noqa: E731
+    # linearity of the k0-free operator
+    lhs = A(2.0 * x - 3.0 * y)
+    rhs = 2.0 * A(x) - 3.0 * A(y)
+    assert (lhs - rhs).norm().item() < TOL * rhs.norm().item()
+    # projection: A(A(x)) == A(x) for 0/1 masks; self-adjoint: <A x, y> == <x, A y>
+    ax = A(x)
+    assert (A(ax) - ax).norm().item() < TOL * ax.norm().item()
+    d1 = (ax.double() * y.double()).sum().item()
+    d2 = (x.double() * A(y).double()).sum().item()
+    assert abs(d1 - d2) < 1e-5 * max(abs(d1), 1.0)
+    # Parseval: ||A x||^2 == ||(1-m) F x||^2
+    kx = ops.fft2_planar(x)
+    e1 = ax.double().square().sum().item()
+    e2 = ((1 - mask.double()) * kx.double()).square().sum().item()
+    assert abs(e1 - e2) < 1e-5 * e2
+    # sampled k-space locations of the output equal k0 exactly up to rounding
+    ko = ops.fft2_planar(dc.perform(x, k0, mask))
+    diff = (mask * (ko - k0)).norm().item()
+    assert diff < TOL * k0.norm().item()
+    # spot check 2 slices against the oracle
+    ref = orc.dc_perform_np(x[:2].cpu().numpy(), k0[:2].cpu().numpy(), mask[:2].cpu().numpy())
+    assert orc.rel_l2(dc.perform(x, k0, mask)[:2].cpu().numpy(), ref) < TOL
+
+
+def test_plan_cache_and_errors():
+    myfft, ops, _, _ = _mods()
+    x, k0, mask = _problem(2, 64, 64, seed=11)
+    xd, k0d, md = _cuda(x, k0, mask)
+    myfft.clear_plan_cache()
+    p1 = myfft.get_plan(k0d, md)
+    assert myfft.get_plan(k0d, md) is p1
+    k0d.mul_(2.0)                          # in-place edit -> version bump -> new plan
+    p2 = myfft.get_plan(k0d, md)
+    assert p2 is not p1
+    out = myfft.data_consistency(xd, k0d, md)
+    assert orc.rel_l2(out.cpu().numpy(), orc.dc_perform_np(x, 2 * k0, mask)) < TOL
+    with pytest.raises(RuntimeError):
+        myfft.DataConsistencyInKspace().perform(xd.cpu(), k0d.cpu(), md.cpu())
+    bad = torch.zeros(1, 2, 48, 48, device='cuda')       # unsupported size: error, no fallback
+    with pytest.raises(RuntimeError, match='unsupported slice size'):
+        ops.fft2_planar(bad)
+    with pytest.raises(ValueError):
+        myfft.DataConsistencyInKspace(norm=None)
+    # non-contiguous input is accepted like the reference (.contiguous() inside)
+    xn = torch.randn(2, 64, 64, 2, device='cuda').permute(0, 3, 1, 2)
+    o = myfft.data_consistency(xn, k0d, md)
+    ref = orc.dc_perform_np(xn.cpu().numpy(), 2 * k0, mask)
+    assert orc.rel_l2(o.cpu().numpy(), ref) < TOL
+
+
+def test_mask_zero_and_one_edge_cases():
+    myfft, _, _, _ = _mods()
+    x, k0, mask = _problem(2, 64, 64, seed=12)
+    xd, k0d = _cuda(x, k0)
+    for fill in (0.0, 1.0):
+        m = np.full_like(mask, fill)
+        (md,) = _cuda(m)
+        out = myfft.data_consistency(xd, k0d, md)
+        assert orc.rel_l2(out.cpu().numpy(), orc.dc_perform_np(x, k0, m)) < TOL
