@@ -34,6 +34,7 @@
 
 #include "../../include/csmri_dc.h"
 #include "dc_core.cuh"
+#include "dc_pipe.cuh"
 
 namespace csmri {
 
@@ -451,6 +452,92 @@ static int set_smem(K kernel, int bytes) {
   return CSMRI_OK;
 }
 
+// ---- TMA-fed persistent strip kernel -----------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// (B,2,H,W) fp32 viewed as {W, H, 2B} (H <= 256) or {W, 256, H/256, 2B}; one
+// box = the CW-column strip of both planes of one slice.
+static int make_tile_map(CUtensorMap* m, const float* ptr, int B, int H, int W, int CW) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(CSMRI_E_CUDA, "cuTensorMapEncodeTiled is unavailable");
+  CUresult r;
+  if (H <= 256) {
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)2 * B};
+    cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+    cuuint32_t box[3] = {(cuuint32_t)CW, (cuuint32_t)H, 2};
+    cuuint32_t es[3] = {1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[4] = {(cuuint64_t)W, 256, (cuuint64_t)H / 256, (cuuint64_t)2 * B};
+    cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * 256 * 4, (cuuint64_t)W * H * 4};
+    cuuint32_t box[4] = {(cuuint32_t)CW, 256, (cuuint32_t)H / 256, 2};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) return fail(CSMRI_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return CSMRI_OK;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int H, int E, int CW, int MINB>
+static int launch_strip_pipe_cfg(const float* x, const float* residual, const float* dtab,
+                                 const float* addend, float* out, int B, int W, cudaStream_t s) {
+  typedef LineFFT<H, E, CW> L;
+  typedef PipeSmem<H, CW> S;
+  auto kern = dc_strip_pipe_kernel<H, E, CW, MINB>;
+  CSMRI_TRY(set_smem(kern, S::kBytes));
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    CSMRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, CW * L::T,
+                                                             S::kBytes));
+    if (blocks_per_sm < 1) return fail(CSMRI_E_CUDA, "pipelined strip kernel does not fit an SM");
+  }
+  alignas(64) CUtensorMap tm_x, tm_a;
+  CSMRI_TRY(make_tile_map(&tm_x, x, B, H, W, CW));
+  if (addend != nullptr) CSMRI_TRY(make_tile_map(&tm_a, addend, B, H, W, CW));
+  else tm_a = tm_x;
+  const int nstrips = W / CW;
+  const int ntiles = B * nstrips;
+  int grid = sm_count() * blocks_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<grid, CW * L::T, S::kBytes, s>>>(tm_x, tm_a, residual, dtab, out, W, nstrips, ntiles,
+                                          addend != nullptr ? 1 : 0);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+static bool tma_ok(const float* x, const float* addend, const float* dtab) {
+  return (((uintptr_t)x | (uintptr_t)addend | (uintptr_t)dtab) & 15u) == 0;
+}
+
 // ---- strip (column) launches ------------------------------------------------
 template <int H, int E, int CW, int MINB>
 static int launch_strip_row_cfg(const float* x, const float* residual, const float* dtab,
@@ -478,8 +565,17 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
   switch (H) {
     case 32: return launch_strip_row_cfg<32, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 64: return launch_strip_row_cfg<64, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
-    case 128: return launch_strip_row_cfg<128, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
+    case 128:
+      if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe_cfg<128, 16, 32, 2>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 11 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe_cfg<128, 16, 16, 4>(x, residual, dtab, addend, out, B, W, s);
+      return launch_strip_row_cfg<128, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 256:
+      if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe_cfg<256, 16, 16, 2>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 11 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe_cfg<256, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 1)
         return launch_strip_row_cfg<256, 16, 16, 1>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 2)
@@ -488,6 +584,8 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
         return launch_strip_row_cfg<256, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<256, 16, 32, 2>(x, residual, dtab, addend, out, B, W, s);
     case 512:
+      if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 1)
         return launch_strip_row_cfg<512, 32, 32, 1>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);

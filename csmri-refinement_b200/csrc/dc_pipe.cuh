@@ -1,0 +1,212 @@
+// TMA-fed, persistent version of the Cartesian DC strip kernel (sm_100a).
+//
+// The direct kernel (dc_strip_row_kernel) stalls on global-load latency: ncu
+// shows long_scoreboard as the dominant stall with HBM at ~50 %.  Here the
+// loads are taken off the instruction stream:
+//
+//   * one elected thread issues cp.async.bulk.tensor (TMA) box loads
+//     {CW columns x H rows x 2 planes} of x and of the addend into shared
+//     memory, completion signalled on an mbarrier (complete_tx::bytes);
+//   * the CTA is persistent (grid = resident CTAs) and walks tiles
+//     tile = blockIdx.x + i*gridDim.x; the load of tile i+1 is issued as soon
+//     as tile i has been pulled into registers, so HBM latency hides behind
+//     the register FFTs of tile i;
+//   * the D row of the next slice rides along as a 1-D bulk copy on the same
+//     mbarrier;
+//   * results go straight from registers to HBM (coalesced row segments).
+//
+// Shared memory per CTA: exchange H*CW*8 + x tile H*CW*8 + addend tile
+// H*CW*8 + 2 D rows.  256^2 with CW=16: 96 KiB + 2 KiB -> two CTAs per SM.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dc_core.cuh"
+
+namespace csmri {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;"
+        " selp.u32 %0, 1, 0, p; }"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes,
+                                             uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void st_stream_f32(float* p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+template <int H, int CW>
+struct PipeSmem {
+  static constexpr int kRowChunks = (H + 255) / 256;          // TMA box dims are <= 256
+  static constexpr int kTileFloats = 2 * H * CW;
+  static constexpr int kTileBytes = kTileFloats * 4;
+  static constexpr int kExchBytes = H * CW * 8;
+  static constexpr int kDBytes = 2 * H * 4;
+  static constexpr int kBytes = kExchBytes + 2 * kTileBytes + kDBytes + 64 + 128;
+};
+
+template <int H, int E, int CW, int MINB>
+__global__ void __launch_bounds__(CW*(H / E), MINB)
+    dc_strip_pipe_kernel(const __grid_constant__ CUtensorMap tm_x,
+                         const __grid_constant__ CUtensorMap tm_add,
+                         const float* __restrict__ residual, const float* __restrict__ dtab,
+                         float* __restrict__ out, int W, int nstrips, int ntiles,
+                         int has_addend) {
+  typedef LineFFT<H, E, CW> L;
+  typedef PipeSmem<H, CW> S;
+  constexpr int T = L::T;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base =
+      reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
+  cf* sm = reinterpret_cast<cf*>(base);
+  float* xbuf = reinterpret_cast<float*>(base + S::kExchBytes);
+  float* abuf = xbuf + S::kTileFloats;
+  float* dbuf = abuf + S::kTileFloats;  // [2][H]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dbuf + 2 * H);
+  const uint32_t bar_x = smem_u32(&bars[0]);
+  const uint32_t bar_a = smem_u32(&bars[1]);
+
+  const int lane = threadIdx.x % CW;
+  const int j = threadIdx.x / CW;
+  const size_t plane = (size_t)H * W;
+
+  auto issue_x = [&](int tile, int slot) {
+    const int b = tile / nstrips, strip = tile - b * nstrips;
+    mbar_expect_tx(bar_x, S::kTileBytes + H * 4);
+    if (S::kRowChunks == 1)
+      tma_load_3d(smem_u32(xbuf), &tm_x, bar_x, strip * CW, 0, b * 2);
+    else
+      tma_load_4d(smem_u32(xbuf), &tm_x, bar_x, strip * CW, 0, 0, b * 2);
+    bulk_load_1d(smem_u32(dbuf + slot * H), dtab + (size_t)b * H, H * 4, bar_x);
+  };
+  auto issue_a = [&](int tile) {
+    const int b = tile / nstrips, strip = tile - b * nstrips;
+    mbar_expect_tx(bar_a, S::kTileBytes);
+    if (S::kRowChunks == 1)
+      tma_load_3d(smem_u32(abuf), &tm_add, bar_a, strip * CW, 0, b * 2);
+    else
+      tma_load_4d(smem_u32(abuf), &tm_add, bar_a, strip * CW, 0, 0, b * 2);
+  };
+
+  int tile = blockIdx.x;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_x, 1);
+    mbar_init(bar_a, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && tile < ntiles) {
+    issue_x(tile, 0);
+    if (has_addend) issue_a(tile);
+  }
+
+  uint32_t phase = 0;
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it, phase ^= 1) {
+    const int slot = it & 1;
+    const int b = tile / nstrips, strip = tile - b * nstrips;
+    const size_t gbase = (size_t)b * 2 * plane + (size_t)strip * CW + lane;
+    const int next = tile + gridDim.x;
+
+    cf v[E];
+    mbar_wait(bar_x, phase);
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const int h = j + T * i;
+      v[i] = mk(xbuf[h * CW + lane], xbuf[(H + h) * CW + lane]);
+    }
+    if (residual != nullptr) {
+      const float* pr = residual + gbase;
+      const float* pi = pr + plane;
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const size_t o = (size_t)(j + T * i) * W;
+        v[i] = cadd(v[i], mk(ld_stream_f32(pr + o), ld_stream_f32(pi + o)));
+      }
+    }
+
+    L::template a_front<false>(v, sm, j, lane);
+    __syncthreads();  // exchange written; x tile consumed by every thread
+    if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
+
+    L::template a_back<false>(v, sm, j, lane);
+    {
+      const float* d = dbuf + slot * H;
+#pragma unroll
+      for (int r = 0; r < E; ++r) v[r] = cscale(v[r], d[L::k_index(j, r)]);
+    }
+    L::template b_front<true>(v, sm, j, lane);
+    __syncthreads();
+    L::template b_back<true>(v, sm, j, lane);
+
+    if (has_addend) {
+      mbar_wait(bar_a, phase);
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const int h = j + T * i;
+        v[i] = cadd(v[i], mk(abuf[h * CW + lane], abuf[(H + h) * CW + lane]));
+      }
+      __syncthreads();  // addend tile consumed by every thread
+      if (threadIdx.x == 0 && next < ntiles) issue_a(next);
+    }
+    {
+      float* pr = out + gbase;
+      float* pi = pr + plane;
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        const size_t o = (size_t)(j + T * i) * W;
+        st_stream_f32(pr + o, v[i].x);
+        st_stream_f32(pi + o, v[i].y);
+      }
+    }
+  }
+}
+
+}  // namespace csmri

@@ -219,8 +219,16 @@ def test_recnet_matches_reference_golden(golden_dir):
         loss = torch.nn.functional.mse_loss(out, tgt)
         assert abs(loss.item() - float(g['loss'])) < 1e-5 * abs(float(g['loss']))
         loss.backward()
+        scale = max(np.linalg.norm(g[k]) for k in g.files if k.startswith('g:'))
         for name, p in net.named_parameters():
-            assert orc.rel_l2(p.grad.cpu().numpy(), g['g:' + name]) < 2e-5, name
+            want = g['g:' + name]
+            got = p.grad.cpu().numpy()
+            if np.linalg.norm(want) < 1e-6 * scale:
+                # e.g. the bias feeding a DC layer whose mask keeps the DC line:
+                # the true gradient is 0 and both sides hold rounding noise
+                assert np.linalg.norm(got - want) < 1e-6 * scale, name
+            else:
+                assert orc.rel_l2(got, want) < 2e-5, name
         net2 = recnet.RecNet(num_blocks=2, num_convs=3, num_filters=4, use_refinement=True,
                              return_intermediate_recs=True, skip_final_dc=True)
         net2.load_state_dict(sd)

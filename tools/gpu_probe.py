@@ -29,8 +29,8 @@ def main():
     dev = torch.device('cuda:0')
     stream = torch.cuda.current_stream().cuda_stream
     res = []
-    cases = [(256, 256, [0, 1, 2, 3]), (512, 64, [0, 1]), (128, 1024, [0]), (64, 4096, [0]),
-             (1024, 16, [0])]
+    cases = [(256, 256, [0, 1, 10, 11]), (512, 64, [0, 1, 10]), (128, 1024, [0, 10, 11]),
+             (64, 4096, [0]), (1024, 16, [0])]
     extra = [int(v) for v in os.environ.get('PROBE_VARIANTS', '').split(',') if v]
     for n, B, variants in cases:
         img = torch.rand(B, n, n, device=dev)
@@ -55,8 +55,19 @@ def main():
                     xs[it[0] % 2].data_ptr(), plan.dtab.data_ptr(), out.data_ptr(), B, n, n,
                     stream))
 
+            # correctness of the variant against variant 0 on identical inputs
+            it[0] = 0
+            fwd()
+            got_f = out.clone()
+            it[0] = 0
+            adj()
+            got_a = out.clone()
+            if v == variants[0]:
+                ref_f, ref_a = got_f, got_a
+            err_f = ((got_f - ref_f).norm() / ref_f.norm()).item()
+            err_a = ((got_a - ref_a).norm() / ref_a.norm()).item()
             tf, ta = time_fn(fwd), time_fn(adj)
-            r = {'N': n, 'B': B, 'variant': v, 'fwd_ms': tf, 'adj_ms': ta,
+            r = {'N': n, 'B': B, 'variant': v, 'relerr_vs_v0': [err_f, err_a], 'fwd_ms': tf, 'adj_ms': ta,
                  'fwd_GBps': 24 * n * n * B / tf / 1e6, 'adj_GBps': 16 * n * n * B / ta / 1e6,
                  'pair_GBps': 40 * n * n * B / (tf + ta) / 1e6,
                  'pair_slices_per_s': B / (tf + ta) * 1e3}
