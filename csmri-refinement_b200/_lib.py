@@ -62,10 +62,11 @@ _SIGNATURES = {
                    [ctypes.c_void_p, ctypes.c_void_p]),
     # tuning knob used by bench.py only (not declared in include/csmri_dc.h)
     'csmri_set_variant': (ctypes.c_int, [ctypes.c_int]),
+    'csmri_set_tuning': (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
 }
 
 # every symbol include/csmri_dc.h declares
-ABI_SYMBOLS = [k for k in _SIGNATURES if k != 'csmri_set_variant']
+ABI_SYMBOLS = [k for k in _SIGNATURES if k not in ('csmri_set_variant', 'csmri_set_tuning')]
 
 
 def lib():

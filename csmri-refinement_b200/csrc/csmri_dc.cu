@@ -59,7 +59,7 @@ template <int H, int E, int CW, int MINB, int WT>
 __global__ void __launch_bounds__(CW*(H / E), MINB)
     dc_strip_row_kernel(const float* __restrict__ x, const float* __restrict__ residual,
                         const float* __restrict__ dtab, const float* __restrict__ addend,
-                        float* __restrict__ out, int W_rt, int nstrips_rt) {
+                        float* __restrict__ out, int W_rt, int nstrips_rt, int pf_dist) {
   typedef LineFFT<H, E, CW> L;
   constexpr int T = L::T;
   // WT != 0: the row pitch is a compile-time constant, so every row offset
@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
   const int nstrips = WT ? WT / CW : nstrips_rt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf* sm = reinterpret_cast<cf*>(smem_raw);
+  cf* tw_s = reinterpret_cast<cf*>(smem_raw + L::kSmemBytes);
+  L::fill_twiddles(tw_s, threadIdx.x, CW * T);
 
   const int lane = threadIdx.x % CW;
   const int j = threadIdx.x / CW;
@@ -95,8 +97,21 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
       v[i] = cadd(v[i], mk(ld_stream(pr + o), ld_stream(pi + o)));
     }
   }
+  // Software prefetch into L2 of the tile a later CTA will own (one wave
+  // ahead): its demand loads then see L2 latency instead of HBM latency.
+  if (pf_dist > 0 && (int)blockIdx.x + pf_dist < (int)gridDim.x) {
+    const int t2 = blockIdx.x + pf_dist;
+    const int b2 = t2 / nstrips, s2 = t2 - b2 * nstrips;
+    const size_t o2 = (size_t)b2 * 2 * plane + (size_t)s2 * CW;
+    for (int r = threadIdx.x; r < 2 * H; r += CW * T) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(x + o2 + (size_t)r * W));
+      if (addend != nullptr)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(addend + o2 + (size_t)r * W));
+    }
+  }
 
-  L::template a_front<false>(v, sm, j, lane);
+  __syncthreads();  // twiddle table ready (the loads above are already in flight)
+  L::template a_front<false>(v, sm, tw_s, j, lane);
   __syncthreads();
   L::template a_back<false>(v, sm, j, lane);
 
@@ -108,7 +123,7 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
 
   L::template b_front<true>(v, sm, j, lane);
   __syncthreads();
-  L::template b_back<true>(v, sm, j, lane);
+  L::template b_back<true>(v, sm, tw_s, j, lane);
 
   if (addend != nullptr) {
     const float* pr = addend + base;
@@ -145,6 +160,8 @@ __global__ void __launch_bounds__(CW*(H / E))
   constexpr int T = L::T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf* sm = reinterpret_cast<cf*>(smem_raw);
+  cf* tw_s = reinterpret_cast<cf*>(smem_raw + L::kSmemBytes);
+  L::fill_twiddles(tw_s, threadIdx.x, CW * T);
 
   const int lane = threadIdx.x % CW;
   const int j = threadIdx.x / CW;
@@ -163,7 +180,8 @@ __global__ void __launch_bounds__(CW*(H / E))
       v[i] = mk(ld_stream(pr + o), ld_stream(pi + o));
     }
   }
-  L::template a_front<false>(v, sm, j, lane);
+  __syncthreads();  // twiddle table ready (the loads above are already in flight)
+  L::template a_front<false>(v, sm, tw_s, j, lane);
   __syncthreads();
   L::template a_back<false>(v, sm, j, lane);
 
@@ -196,7 +214,7 @@ __global__ void __launch_bounds__(CW*(H / E))
 
   L::template b_front<true>(v, sm, j, lane);
   __syncthreads();
-  L::template b_back<true>(v, sm, j, lane);
+  L::template b_back<true>(v, sm, tw_s, j, lane);
   {
     float* pr = out + base;
     float* pi = pr + plane;
@@ -222,6 +240,8 @@ __global__ void __launch_bounds__(CW*(H / E))
   constexpr int T = L::T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf* sm = reinterpret_cast<cf*>(smem_raw);
+  cf* tw_s = reinterpret_cast<cf*>(smem_raw + L::kSmemBytes);
+  L::fill_twiddles(tw_s, threadIdx.x, CW * T);
 
   const int lane = threadIdx.x % CW;
   const int j = threadIdx.x / CW;
@@ -240,7 +260,8 @@ __global__ void __launch_bounds__(CW*(H / E))
       v[i] = mk(ld_stream(pr + o), ld_stream(pi + o));
     }
   }
-  L::template a_front<INV>(v, sm, j, lane);
+  __syncthreads();  // twiddle table ready
+  L::template a_front<INV>(v, sm, tw_s, j, lane);
   __syncthreads();
   L::template a_back<INV>(v, sm, j, lane);
   {
@@ -279,6 +300,10 @@ __global__ void __launch_bounds__(CW*(W / E))
   float* st = reinterpret_cast<float*>(smem_raw);          // staging (aliased)
   float* st_re = st;
   float* st_im = st + CW * PITCH;
+  constexpr int kMainBytes =
+      ((2 * CW * PITCH * 4 > L::kSmemBytes ? 2 * CW * PITCH * 4 : L::kSmemBytes) + 15) / 16 * 16;
+  cf* tw_s = reinterpret_cast<cf*>(smem_raw + kMainBytes);
+  L::fill_twiddles(tw_s, threadIdx.x, NT);
 
   const int tiles_per_slice = H / CW;
   const int b = blockIdx.x / tiles_per_slice;
@@ -313,9 +338,8 @@ __global__ void __launch_bounds__(CW*(W / E))
     const int w = j + T * i;
     v[i] = mk(st_re[lane * PITCH + w], st_im[lane * PITCH + w]);
   }
-  __syncthreads();  // staging is dead, the exchange buffer may overwrite it
-
-  L::template a_front<INV>(v, sm, j, lane);
+  __syncthreads();  // staging is dead (exchange may overwrite it); twiddle table ready
+  L::template a_front<INV>(v, sm, tw_s, j, lane);
   __syncthreads();
   L::template a_back<INV>(v, sm, j, lane);
   __syncthreads();
@@ -452,6 +476,10 @@ static int set_smem(K kernel, int bytes) {
   return CSMRI_OK;
 }
 
+static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_set_tuning
+static int g_pf_dist = 0;        // L2 software-prefetch distance in tiles (0 = off)
+static int g_dephase = 0;        // start delay (cycles) of second-wave persistent CTAs
+
 // ---- TMA-fed persistent strip kernel -----------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -507,12 +535,12 @@ static int sm_count() {
   return n;
 }
 
-template <int H, int E, int CW, int MINB>
-static int launch_strip_pipe_cfg(const float* x, const float* residual, const float* dtab,
-                                 const float* addend, float* out, int B, int W, cudaStream_t s) {
+template <int H, int E, int CW, int MINB, int WT, bool ADD>
+static int launch_strip_pipe_wt(const float* x, const float* residual, const float* dtab,
+                                const float* addend, float* out, int B, int W, cudaStream_t s) {
   typedef LineFFT<H, E, CW> L;
-  typedef PipeSmem<H, CW> S;
-  auto kern = dc_strip_pipe_kernel<H, E, CW, MINB>;
+  typedef PipeSmem<H, E, CW, ADD> S;
+  auto kern = dc_strip_pipe_kernel<H, E, CW, MINB, WT, ADD>;
   CSMRI_TRY(set_smem(kern, S::kBytes));
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
@@ -522,16 +550,31 @@ static int launch_strip_pipe_cfg(const float* x, const float* residual, const fl
   }
   alignas(64) CUtensorMap tm_x, tm_a;
   CSMRI_TRY(make_tile_map(&tm_x, x, B, H, W, CW));
-  if (addend != nullptr) CSMRI_TRY(make_tile_map(&tm_a, addend, B, H, W, CW));
+  if (ADD) CSMRI_TRY(make_tile_map(&tm_a, addend, B, H, W, CW));
   else tm_a = tm_x;
   const int nstrips = W / CW;
   const int ntiles = B * nstrips;
   int grid = sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
   kern<<<grid, CW * L::T, S::kBytes, s>>>(tm_x, tm_a, residual, dtab, out, W, nstrips, ntiles,
-                                          addend != nullptr ? 1 : 0);
+                                          blocks_per_sm > 1 ? g_dephase : 0);
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
+}
+
+// MINB_F / MINB_A: resident CTAs per SM asked of the compiler for the forward
+// (x + addend tiles in smem) and adjoint (x tile only) instantiations
+template <int H, int E, int CW, int MINB_F, int MINB_A = MINB_F>
+static int launch_strip_pipe_cfg(const float* x, const float* residual, const float* dtab,
+                                 const float* addend, float* out, int B, int W, cudaStream_t s) {
+  if (addend != nullptr) {
+    if (W == H)
+      return launch_strip_pipe_wt<H, E, CW, MINB_F, H, true>(x, residual, dtab, addend, out, B, W, s);
+    return launch_strip_pipe_wt<H, E, CW, MINB_F, 0, true>(x, residual, dtab, addend, out, B, W, s);
+  }
+  if (W == H)
+    return launch_strip_pipe_wt<H, E, CW, MINB_A, H, false>(x, residual, dtab, addend, out, B, W, s);
+  return launch_strip_pipe_wt<H, E, CW, MINB_A, 0, false>(x, residual, dtab, addend, out, B, W, s);
 }
 
 static bool tma_ok(const float* x, const float* addend, const float* dtab) {
@@ -546,18 +589,19 @@ static int launch_strip_row_cfg(const float* x, const float* residual, const flo
   const int nstrips = W / CW;
   if (W == H) {  // square slices (every shipped config): compile-time row pitch
     auto kern = dc_strip_row_kernel<H, E, CW, MINB, H>;
-    CSMRI_TRY(set_smem(kern, L::kSmemBytes));
-    kern<<<B * nstrips, CW * L::T, L::kSmemBytes, s>>>(x, residual, dtab, addend, out, W, nstrips);
+    CSMRI_TRY(set_smem(kern, L::kSmemBytes + L::kTwBytes));
+    kern<<<B * nstrips, CW * L::T, L::kSmemBytes + L::kTwBytes, s>>>(x, residual, dtab, addend, out, W, nstrips,
+                                                       g_pf_dist);
   } else {
     auto kern = dc_strip_row_kernel<H, E, CW, MINB, 0>;
-    CSMRI_TRY(set_smem(kern, L::kSmemBytes));
-    kern<<<B * nstrips, CW * L::T, L::kSmemBytes, s>>>(x, residual, dtab, addend, out, W, nstrips);
+    CSMRI_TRY(set_smem(kern, L::kSmemBytes + L::kTwBytes));
+    kern<<<B * nstrips, CW * L::T, L::kSmemBytes + L::kTwBytes, s>>>(x, residual, dtab, addend, out, W, nstrips,
+                                                       g_pf_dist);
   }
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }
 
-static int g_strip_variant = 0;  // tuning knob, see csmri_set_variant
 
 static int launch_strip_row(const float* x, const float* residual, const float* dtab,
                             const float* addend, float* out, int B, int H, int W,
@@ -566,25 +610,35 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
     case 32: return launch_strip_row_cfg<32, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 64: return launch_strip_row_cfg<64, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 128:
-      if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
+      if ((g_strip_variant == 0 || g_strip_variant == 10) && tma_ok(x, addend, dtab))
         return launch_strip_pipe_cfg<128, 16, 32, 2>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 11 && tma_ok(x, addend, dtab))
         return launch_strip_pipe_cfg<128, 16, 16, 4>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<128, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 256:
-      if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
+      if ((g_strip_variant == 0 || g_strip_variant == 10) && tma_ok(x, addend, dtab))
         return launch_strip_pipe_cfg<256, 16, 16, 2>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 11 && tma_ok(x, addend, dtab))
         return launch_strip_pipe_cfg<256, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 12 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe_cfg<256, 16, 8, 4>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 13 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe_cfg<256, 16, 16, 2, 3>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 1)
         return launch_strip_row_cfg<256, 16, 16, 1>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 4)
+        return launch_strip_row_cfg<256, 16, 16, 4>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 5)
+        return launch_strip_row_cfg<256, 16, 8, 8>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 6)
+        return launch_strip_row_cfg<256, 16, 8, 4>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 2)
         return launch_strip_row_cfg<256, 32, 32, 1>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 3)
         return launch_strip_row_cfg<256, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<256, 16, 32, 2>(x, residual, dtab, addend, out, B, W, s);
     case 512:
-      if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
+      if ((g_strip_variant == 0 || g_strip_variant == 10) && tma_ok(x, addend, dtab))
         return launch_strip_pipe_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 1)
         return launch_strip_row_cfg<512, 32, 32, 1>(x, residual, dtab, addend, out, B, W, s);
@@ -604,8 +658,8 @@ static int launch_strip_dense_cfg(const float* hyb, const float* k0, const float
 #define CSMRI_DENSE(N_, A_)                                                           \
   {                                                                                   \
     auto kern = dc_strip_dense_kernel<H, E, CW, N_, A_>;                              \
-    CSMRI_TRY(set_smem(kern, L::kSmemBytes));                                         \
-    kern<<<grid, block, L::kSmemBytes, s>>>(hyb, k0, mask, out, W, nstrips, sc, nv); \
+    CSMRI_TRY(set_smem(kern, L::kSmemBytes + L::kTwBytes));                                         \
+    kern<<<grid, block, L::kSmemBytes + L::kTwBytes, s>>>(hyb, k0, mask, out, W, nstrips, sc, nv); \
   }
   if (noisy && adj) CSMRI_DENSE(true, true)
   else if (noisy) CSMRI_DENSE(true, false)
@@ -637,12 +691,12 @@ static int launch_fft_strip_cfg(const float* in, float* out, int B, int W, float
   const int nstrips = W / CW;
   if (inv) {
     auto kern = fft_strip_kernel<H, E, CW, true>;
-    CSMRI_TRY(set_smem(kern, L::kSmemBytes));
-    kern<<<B * nstrips, CW * L::T, L::kSmemBytes, s>>>(in, out, W, nstrips, scale, rows);
+    CSMRI_TRY(set_smem(kern, L::kSmemBytes + L::kTwBytes));
+    kern<<<B * nstrips, CW * L::T, L::kSmemBytes + L::kTwBytes, s>>>(in, out, W, nstrips, scale, rows);
   } else {
     auto kern = fft_strip_kernel<H, E, CW, false>;
-    CSMRI_TRY(set_smem(kern, L::kSmemBytes));
-    kern<<<B * nstrips, CW * L::T, L::kSmemBytes, s>>>(in, out, W, nstrips, scale, rows);
+    CSMRI_TRY(set_smem(kern, L::kSmemBytes + L::kTwBytes));
+    kern<<<B * nstrips, CW * L::T, L::kSmemBytes + L::kTwBytes, s>>>(in, out, W, nstrips, scale, rows);
   }
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
@@ -667,7 +721,8 @@ static int launch_fft_rows_cfg(const float* in, const float* aux, float* out, in
                                float scale, float cmulv, bool inv, int pre, cudaStream_t s) {
   typedef LineFFT<W, E, CW> L;
   constexpr int stage_bytes = 2 * CW * (W + 1) * (int)sizeof(float);
-  constexpr int smem = stage_bytes > L::kSmemBytes ? stage_bytes : L::kSmemBytes;
+  constexpr int smem =
+      ((stage_bytes > L::kSmemBytes ? stage_bytes : L::kSmemBytes) + 15) / 16 * 16 + L::kTwBytes;
   const dim3 grid(B * (H / CW)), block(CW * L::T);
 #define CSMRI_ROWS(I_, P_)                                              \
   {                                                                     \
@@ -714,6 +769,13 @@ int csmri_init(void) { return ensure_init(); }
 // tuning knob for the benchmark harness (not part of the reference-facing ABI)
 int csmri_set_variant(int v) {
   g_strip_variant = v;
+  return CSMRI_OK;
+}
+int csmri_set_tuning(int key, int value) {
+  if (key == 0) g_strip_variant = value;
+  else if (key == 1) g_pf_dist = value;
+  else if (key == 2) g_dephase = value;
+  else return fail(CSMRI_E_ARG, "unknown tuning key %d", key);
   return CSMRI_OK;
 }
 

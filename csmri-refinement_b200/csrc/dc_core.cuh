@@ -48,20 +48,42 @@ struct LineFFT {
   static_assert(E * T == N, "N must equal E*T");
   static_assert(Q * T == E && Q >= 1, "T must divide E");
   static_assert(kTwN % N == 0, "N must divide the twiddle table size");
-  static constexpr int kSmemBytes = N * CW * (int)sizeof(cf);
+  // exchange slot of (k1, j): (k1*TP + j)*CW + lane.  With CW = 8 a warp holds
+  // four j (or t) values; one padding slot per k1 row keeps the k-layout
+  // accesses (stride TP slots between consecutive t) on disjoint banks.
+  static constexpr int TP = T + ((CW == 8 && T % 2 == 0) ? 1 : 0);
+  static constexpr int kSmemBytes = E * TP * CW * (int)sizeof(cf);
+
+  // Inter-pass twiddles W_N^{j*k1}.  Register-indexed constant loads (LDC
+  // c[3][R]) turned out to be the largest single stall source in the first
+  // ncu source pages (low-throughput, high-latency path), so each CTA keeps
+  // the N values it needs as a [T][E] table in shared memory and every thread
+  // reads its row with E/2 broadcast LDS.128.
+  static constexpr int kTwBytes = N * (int)sizeof(cf);
+  static CSMRI_HD void fill_twiddles(cf* tw_s, int tid, int nthreads) {
+    for (int idx = tid; idx < N; idx += nthreads) {
+      const int jj = idx / E, k1 = idx - jj * E;
+      tw_s[idx] = tw_lookup(jj * k1 * (kTwN / N));
+    }
+  }
+  template <bool INV>
+  static CSMRI_HD void apply_twiddles(cf* v, const cf* tw_s, int j) {
+    const float4* row = reinterpret_cast<const float4*>(tw_s + j * E);
+#pragma unroll
+    for (int p = 0; p < E / 2; ++p) {
+      const float4 q = row[p];
+      if (p > 0) v[2 * p] = INV ? cmul_conj(v[2 * p], mk(q.x, q.y)) : cmul(v[2 * p], mk(q.x, q.y));
+      v[2 * p + 1] = INV ? cmul_conj(v[2 * p + 1], mk(q.z, q.w)) : cmul(v[2 * p + 1], mk(q.z, q.w));
+    }
+  }
 
   // ---- halfA ---------------------------------------------------------------
   template <bool INV>
-  static CSMRI_HD void a_front(cf* v, cf* sm, int j, int lane) {
+  static CSMRI_HD void a_front(cf* v, cf* sm, const cf* tw_s, int j, int lane) {
     RegFFT<E, INV>::run(v);
-    const int step = j * (kTwN / N);
+    apply_twiddles<INV>(v, tw_s, j);
 #pragma unroll
-    for (int k1 = 1; k1 < E; ++k1) {
-      cf w = tw_lookup(step * k1);
-      v[k1] = INV ? cmul_conj(v[k1], w) : cmul(v[k1], w);
-    }
-#pragma unroll
-    for (int k1 = 0; k1 < E; ++k1) sm[(k1 * T + j) * CW + lane] = v[k1];
+    for (int k1 = 0; k1 < E; ++k1) sm[(k1 * TP + j) * CW + lane] = v[k1];
   }
   template <bool INV>
   static CSMRI_HD void a_back(cf* u, const cf* sm, int t, int lane) {
@@ -69,7 +91,7 @@ struct LineFFT {
     for (int q = 0; q < Q; ++q)
 #pragma unroll
       for (int j2 = 0; j2 < T; ++j2)
-        u[q * T + j2] = sm[((q * T + t) * T + j2) * CW + lane];
+        u[q * T + j2] = sm[((q * T + t) * TP + j2) * CW + lane];
 #pragma unroll
     for (int q = 0; q < Q; ++q) RegFFT<T, INV>::run(u + q * T);
   }
@@ -89,18 +111,13 @@ struct LineFFT {
     for (int q = 0; q < Q; ++q)
 #pragma unroll
       for (int j2 = 0; j2 < T; ++j2)
-        sm[((q * T + t) * T + j2) * CW + lane] = u[q * T + j2];
+        sm[((q * T + t) * TP + j2) * CW + lane] = u[q * T + j2];
   }
   template <bool INV>
-  static CSMRI_HD void b_back(cf* v, const cf* sm, int j, int lane) {
+  static CSMRI_HD void b_back(cf* v, const cf* sm, const cf* tw_s, int j, int lane) {
 #pragma unroll
-    for (int k1 = 0; k1 < E; ++k1) v[k1] = sm[(k1 * T + j) * CW + lane];
-    const int step = j * (kTwN / N);
-#pragma unroll
-    for (int k1 = 1; k1 < E; ++k1) {
-      cf w = tw_lookup(step * k1);
-      v[k1] = INV ? cmul_conj(v[k1], w) : cmul(v[k1], w);
-    }
+    for (int k1 = 0; k1 < E; ++k1) v[k1] = sm[(k1 * TP + j) * CW + lane];
+    apply_twiddles<INV>(v, tw_s, j);
     RegFFT<E, INV>::run(v);
   }
 };

@@ -83,34 +83,41 @@ __device__ __forceinline__ float ld_stream_f32(const float* p) {
   return v;
 }
 
-template <int H, int CW>
+template <int H, int E, int CW, bool ADD = true>
 struct PipeSmem {
   static constexpr int kRowChunks = (H + 255) / 256;          // TMA box dims are <= 256
   static constexpr int kTileFloats = 2 * H * CW;
   static constexpr int kTileBytes = kTileFloats * 4;
-  static constexpr int kExchBytes = H * CW * 8;
+  static constexpr int kExchBytes = (LineFFT<H, E, CW>::kSmemBytes + 127) / 128 * 128;
   static constexpr int kDBytes = 2 * H * 4;
-  static constexpr int kBytes = kExchBytes + 2 * kTileBytes + kDBytes + 64 + 128;
+  static constexpr int kTwBytes = LineFFT<H, E, CW>::kTwBytes;
+  static constexpr int kBytes = kExchBytes + (ADD ? 2 : 1) * kTileBytes + kDBytes + kTwBytes + 64;
 };
 
-template <int H, int E, int CW, int MINB>
+template <int H, int E, int CW, int MINB, int WT, bool ADD>
 __global__ void __launch_bounds__(CW*(H / E), MINB)
     dc_strip_pipe_kernel(const __grid_constant__ CUtensorMap tm_x,
                          const __grid_constant__ CUtensorMap tm_add,
                          const float* __restrict__ residual, const float* __restrict__ dtab,
-                         float* __restrict__ out, int W, int nstrips, int ntiles,
-                         int has_addend) {
+                         float* __restrict__ out, int W_rt, int nstrips_rt, int ntiles,
+                         int dephase) {
+  constexpr bool has_addend = ADD;
+  // WT != 0: compile-time row pitch (square slices) -> immediate store offsets
+  const int W = WT ? WT : W_rt;
+  const int nstrips = WT ? WT / CW : nstrips_rt;
   typedef LineFFT<H, E, CW> L;
-  typedef PipeSmem<H, CW> S;
+  typedef PipeSmem<H, E, CW, ADD> S;
   constexpr int T = L::T;
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* base =
-      reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 127) & ~(uintptr_t)127);
-  cf* sm = reinterpret_cast<cf*>(base);
-  float* xbuf = reinterpret_cast<float*>(base + S::kExchBytes);
-  float* abuf = xbuf + S::kTileFloats;
-  float* dbuf = abuf + S::kTileFloats;  // [2][H]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dbuf + 2 * H);
+  // NB: no integer arithmetic on this pointer - it would demote every access
+  // below from LDS/STS to generic LD/ST (seen in the first ncu source page).
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  cf* sm = reinterpret_cast<cf*>(smem_dyn);
+  float* xbuf = reinterpret_cast<float*>(smem_dyn + S::kExchBytes);
+  float* abuf = xbuf + S::kTileFloats;                      // absent when !ADD
+  float* dbuf = xbuf + (ADD ? 2 : 1) * S::kTileFloats;      // [2][H]
+  cf* tw_s = reinterpret_cast<cf*>(dbuf + 2 * H);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tw_s + H);
+  L::fill_twiddles(tw_s, threadIdx.x, CW * T);
   const uint32_t bar_x = smem_u32(&bars[0]);
   const uint32_t bar_a = smem_u32(&bars[1]);
 
@@ -148,6 +155,14 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
     if (has_addend) issue_a(tile);
   }
 
+  // CTAs of the second residency wave share an SM with a first-wave CTA and
+  // would otherwise run in lock-step with it (load burst / FFT / store burst
+  // at the same time); an initial delay keeps the two out of phase.
+  if (dephase > 0 && blockIdx.x >= gridDim.x / 2) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < dephase) {}
+  }
+
   uint32_t phase = 0;
   for (int it = 0; tile < ntiles; tile += gridDim.x, ++it, phase ^= 1) {
     const int slot = it & 1;
@@ -172,7 +187,7 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
       }
     }
 
-    L::template a_front<false>(v, sm, j, lane);
+    L::template a_front<false>(v, sm, tw_s, j, lane);
     __syncthreads();  // exchange written; x tile consumed by every thread
     if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
 
@@ -184,7 +199,7 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
     }
     L::template b_front<true>(v, sm, j, lane);
     __syncthreads();
-    L::template b_back<true>(v, sm, j, lane);
+    L::template b_back<true>(v, sm, tw_s, j, lane);
 
     if (has_addend) {
       mbar_wait(bar_a, phase);

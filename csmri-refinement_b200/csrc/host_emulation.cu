@@ -18,12 +18,14 @@ static void init_tw() {
   }
 }
 
-template <int N, int E>
+template <int N, int E, int CW = 2>
 static double check(bool inv_first) {
-  constexpr int CW = 2;
   typedef LineFFT<N, E, CW> L;
   constexpr int T = L::T;
-  std::vector<cf> sm(N * CW);
+  std::vector<cf> sm(L::kSmemBytes / sizeof(cf));
+  std::vector<float4> tw4(N / 2);
+  cf* tw = reinterpret_cast<cf*>(tw4.data());
+  for (int t = 0; t < T; ++t) L::fill_twiddles(tw, t, T);
   std::vector<std::vector<cf>> regs(T * CW, std::vector<cf>(E));
   std::vector<double> xr(N * CW), xi(N * CW);
   srand(N * 131 + E);
@@ -35,8 +37,8 @@ static double check(bool inv_first) {
     regs[j * CW + l][i] = mk((float)xr[n * CW + l], (float)xi[n * CW + l]);
   }
   for (int j = 0; j < T; ++j) for (int l = 0; l < CW; ++l) {
-    if (inv_first) L::template a_front<true>(regs[j * CW + l].data(), sm.data(), j, l);
-    else L::template a_front<false>(regs[j * CW + l].data(), sm.data(), j, l);
+    if (inv_first) L::template a_front<true>(regs[j * CW + l].data(), sm.data(), tw, j, l);
+    else L::template a_front<false>(regs[j * CW + l].data(), sm.data(), tw, j, l);
   }
   for (int j = 0; j < T; ++j) for (int l = 0; l < CW; ++l) {
     if (inv_first) L::template a_back<true>(regs[j * CW + l].data(), sm.data(), j, l);
@@ -65,8 +67,8 @@ static double check(bool inv_first) {
     else L::template b_front<true>(regs[j * CW + l].data(), sm.data(), j, l);
   }
   for (int j = 0; j < T; ++j) for (int l = 0; l < CW; ++l) {
-    if (inv_first) L::template b_back<false>(regs[j * CW + l].data(), sm.data(), j, l);
-    else L::template b_back<true>(regs[j * CW + l].data(), sm.data(), j, l);
+    if (inv_first) L::template b_back<false>(regs[j * CW + l].data(), sm.data(), tw, j, l);
+    else L::template b_back<true>(regs[j * CW + l].data(), sm.data(), tw, j, l);
   }
   num = den = 0;
   for (int j = 0; j < T; ++j) for (int l = 0; l < CW; ++l) for (int i = 0; i < E; ++i) {
@@ -94,6 +96,8 @@ int main() {
     upd(check<256, 32>(inv));
     upd(check<512, 32>(inv));
     upd(check<1024, 32>(inv));
+    upd(check<256, 16, 8>(inv));   // padded exchange layout (CW = 8)
+    upd(check<128, 16, 8>(inv));
   }
   printf("worst=%.3e\n", worst);
   return worst < 2e-6 ? 0 : 1;

@@ -318,3 +318,29 @@ def test_mask_zero_and_one_edge_cases():
         (md,) = _cuda(m)
         out = myfft.data_consistency(xd, k0d, md)
         assert orc.rel_l2(out.cpu().numpy(), orc.dc_perform_np(x, k0, m)) < TOL
+
+
+def test_kernel_variants_and_unaligned_pointers_agree():
+    """Every strip-kernel variant (TMA-pipelined persistent, direct) and the
+    4-byte-aligned fallback produce the same numbers."""
+    from csmri_refinement_b200 import _lib
+    myfft, ops, _, _ = _mods()
+    lib = _lib.lib()
+    x, k0, mask = _problem(5, 256, 256, acc=4, seed=21)
+    xd, k0d, md = _cuda(x, k0, mask)
+    plan = myfft.get_plan(k0d, md, 0.1)
+    ref = orc.dc_perform_np(x, k0, mask, 0.1)
+    try:
+        for v in (0, 1, 4, 5, 10, 11, 13, 20):
+            lib.csmri_set_tuning(0, v)
+            out = ops.dc_cartesian(xd, None, plan.dtab, plan.addend)
+            assert orc.rel_l2(out.cpu().numpy(), ref) < TOL, v
+    finally:
+        lib.csmri_set_tuning(0, 0)
+    # x at a 4-byte offset: not TMA-able (needs 16 B), must still be exact
+    flat = torch.empty(xd.numel() + 1, device='cuda')
+    flat[1:].copy_(xd.reshape(-1))
+    xo = flat[1:].view_as(xd)
+    assert xo.data_ptr() % 16 == 4
+    out = ops.dc_cartesian(xo, None, plan.dtab, plan.addend)
+    assert orc.rel_l2(out.cpu().numpy(), ref) < TOL
