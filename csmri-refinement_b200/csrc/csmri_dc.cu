@@ -115,11 +115,7 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
   __syncthreads();
   L::template a_back<false>(v, sm, j, lane);
 
-  {
-    const float* d = dtab + (size_t)b * H;
-#pragma unroll
-    for (int r = 0; r < E; ++r) v[r] = cscale(v[r], __ldg(d + L::k_index(j, r)));
-  }
+  L::apply_dtab(v, dtab + (size_t)b * H + j * E);
 
   L::template b_front<true>(v, sm, j, lane);
   __syncthreads();
@@ -363,8 +359,11 @@ __global__ void __launch_bounds__(CW*(W / E))
 // ---------------------------------------------------------------------------
 __global__ void set_flag_kernel(int* flag, int value) { *flag = value; }
 
+// dtab layout: D[b, k]/H stored at b*H + dtab_slot(k) for the (E, T = H/E)
+// decomposition every strip kernel of this H uses (LineFFT::dtab_slot)
 __global__ void mask_rows_kernel(const float* __restrict__ mask, int B, int H, int W, float nv,
-                                 int noisy, float* __restrict__ dtab, int* __restrict__ flag) {
+                                 int noisy, int E, float* __restrict__ dtab,
+                                 int* __restrict__ flag) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
   const int lane = threadIdx.x % 32;
   if (warp >= B * H) return;
@@ -379,7 +378,9 @@ __global__ void mask_rows_kernel(const float* __restrict__ mask, int B, int H, i
   if (lane == 0) {
     if (!ok) atomicExch(flag, 0);
     const float d = noisy ? (1.0f - m) + m / (1.0f + nv) : (1.0f - m);
-    dtab[warp] = d / (float)H;
+    const int T = H / E;
+    const int k1 = h % E, k2 = h / E;
+    dtab[(size_t)b * H + (k1 % T) * E + (k1 / T) * T + k2] = d / (float)H;
   }
 }
 
@@ -448,6 +449,10 @@ static int ensure_init() {
   return CSMRI_OK;
 }
 
+// elements per thread (E) of the two-pass column FFT for each supported H; the
+// dtab layout depends on it, so every strip-kernel variant of one H shares it
+static int strip_radix(int H) { return H <= 64 ? 8 : (H <= 256 ? 16 : 32); }
+
 static bool pow2_in(int n, int lo, int hi) { return n >= lo && n <= hi && (n & (n - 1)) == 0; }
 
 static int check_shape(int B, int H, int W) {
@@ -478,7 +483,7 @@ static int set_smem(K kernel, int bytes) {
 
 static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_set_tuning
 static int g_pf_dist = 0;        // L2 software-prefetch distance in tiles (0 = off)
-static int g_dephase = 0;        // start delay (cycles) of second-wave persistent CTAs
+static int g_probe_copy = 0;     // tuning probe: pipelined kernel moves data but skips the FFT
 
 // ---- TMA-fed persistent strip kernel -----------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -535,12 +540,12 @@ static int sm_count() {
   return n;
 }
 
-template <int H, int E, int CW, int MINB, int WT, bool ADD>
+template <int H, int E, int CW, int MINB, int WT, bool ADD, bool TWREG>
 static int launch_strip_pipe_wt(const float* x, const float* residual, const float* dtab,
                                 const float* addend, float* out, int B, int W, cudaStream_t s) {
   typedef LineFFT<H, E, CW> L;
   typedef PipeSmem<H, E, CW, ADD> S;
-  auto kern = dc_strip_pipe_kernel<H, E, CW, MINB, WT, ADD>;
+  auto kern = dc_strip_pipe_kernel<H, E, CW, MINB, WT, ADD, TWREG>;
   CSMRI_TRY(set_smem(kern, S::kBytes));
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
@@ -557,24 +562,24 @@ static int launch_strip_pipe_wt(const float* x, const float* residual, const flo
   int grid = sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
   kern<<<grid, CW * L::T, S::kBytes, s>>>(tm_x, tm_a, residual, dtab, out, W, nstrips, ntiles,
-                                          blocks_per_sm > 1 ? g_dephase : 0);
+                                          g_probe_copy);
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }
 
 // MINB_F / MINB_A: resident CTAs per SM asked of the compiler for the forward
 // (x + addend tiles in smem) and adjoint (x tile only) instantiations
-template <int H, int E, int CW, int MINB_F, int MINB_A = MINB_F>
+template <int H, int E, int CW, int MINB_F, int MINB_A = MINB_F, bool TWREG = false>
 static int launch_strip_pipe_cfg(const float* x, const float* residual, const float* dtab,
                                  const float* addend, float* out, int B, int W, cudaStream_t s) {
   if (addend != nullptr) {
     if (W == H)
-      return launch_strip_pipe_wt<H, E, CW, MINB_F, H, true>(x, residual, dtab, addend, out, B, W, s);
-    return launch_strip_pipe_wt<H, E, CW, MINB_F, 0, true>(x, residual, dtab, addend, out, B, W, s);
+      return launch_strip_pipe_wt<H, E, CW, MINB_F, H, true, TWREG>(x, residual, dtab, addend, out, B, W, s);
+    return launch_strip_pipe_wt<H, E, CW, MINB_F, 0, true, TWREG>(x, residual, dtab, addend, out, B, W, s);
   }
   if (W == H)
-    return launch_strip_pipe_wt<H, E, CW, MINB_A, H, false>(x, residual, dtab, addend, out, B, W, s);
-  return launch_strip_pipe_wt<H, E, CW, MINB_A, 0, false>(x, residual, dtab, addend, out, B, W, s);
+    return launch_strip_pipe_wt<H, E, CW, MINB_A, H, false, TWREG>(x, residual, dtab, addend, out, B, W, s);
+  return launch_strip_pipe_wt<H, E, CW, MINB_A, 0, false, TWREG>(x, residual, dtab, addend, out, B, W, s);
 }
 
 static bool tma_ok(const float* x, const float* addend, const float* dtab) {
@@ -624,6 +629,10 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
         return launch_strip_pipe_cfg<256, 16, 8, 4>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 13 && tma_ok(x, addend, dtab))
         return launch_strip_pipe_cfg<256, 16, 16, 2, 3>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 14 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe_cfg<256, 16, 16, 2, 2, true>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 15 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe_cfg<256, 16, 32, 1, 1, true>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 1)
         return launch_strip_row_cfg<256, 16, 16, 1>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 4)
@@ -632,8 +641,6 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
         return launch_strip_row_cfg<256, 16, 8, 8>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 6)
         return launch_strip_row_cfg<256, 16, 8, 4>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 2)
-        return launch_strip_row_cfg<256, 32, 32, 1>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 3)
         return launch_strip_row_cfg<256, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<256, 16, 32, 2>(x, residual, dtab, addend, out, B, W, s);
@@ -774,7 +781,7 @@ int csmri_set_variant(int v) {
 int csmri_set_tuning(int key, int value) {
   if (key == 0) g_strip_variant = value;
   else if (key == 1) g_pf_dist = value;
-  else if (key == 2) g_dephase = value;
+  else if (key == 2) g_probe_copy = value;
   else return fail(CSMRI_E_ARG, "unknown tuning key %d", key);
   return CSMRI_OK;
 }
@@ -797,8 +804,8 @@ int csmri_dc_prepare(const float* k0, const float* mask, int B, int H, int W, fl
   {
     const int warps = B * H, threads = 256;
     const int blocks = (warps * 32 + threads - 1) / threads;
-    mask_rows_kernel<<<blocks, threads, 0, s>>>(mask, B, H, W, noise_lvl, noisy ? 1 : 0, dtab,
-                                                row_constant);
+    mask_rows_kernel<<<blocks, threads, 0, s>>>(mask, B, H, W, noise_lvl, noisy ? 1 : 0,
+                                                strip_radix(H), dtab, row_constant);
   }
   CSMRI_CUDA(cudaGetLastError());
   if (addend != nullptr) {

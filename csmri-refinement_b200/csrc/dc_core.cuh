@@ -66,6 +66,28 @@ struct LineFFT {
       tw_s[idx] = tw_lookup(jj * k1 * (kTwN / N));
     }
   }
+  // register-resident twiddle row (persistent kernels keep it across tiles)
+  static CSMRI_HD void load_twiddle_row(cf* w, const cf* tw_s, int j) {
+#pragma unroll
+    for (int k1 = 0; k1 < E; ++k1) w[k1] = tw_s[j * E + k1];
+  }
+  template <bool INV>
+  static CSMRI_HD void apply_twiddles_reg(cf* v, const cf* w) {
+#pragma unroll
+    for (int k1 = 1; k1 < E; ++k1) v[k1] = INV ? cmul_conj(v[k1], w[k1]) : cmul(v[k1], w[k1]);
+  }
+  // multiply the k-layout registers of thread t by its E table entries
+  static CSMRI_HD void apply_dtab(cf* u, const float* drow_t) {
+    const float4* d4 = reinterpret_cast<const float4*>(drow_t);
+#pragma unroll
+    for (int p = 0; p < E / 4; ++p) {
+      const float4 q = d4[p];
+      u[4 * p] = cscale(u[4 * p], q.x);
+      u[4 * p + 1] = cscale(u[4 * p + 1], q.y);
+      u[4 * p + 2] = cscale(u[4 * p + 2], q.z);
+      u[4 * p + 3] = cscale(u[4 * p + 3], q.w);
+    }
+  }
   template <bool INV>
   static CSMRI_HD void apply_twiddles(cf* v, const cf* tw_s, int j) {
     const float4* row = reinterpret_cast<const float4*>(tw_s + j * E);
@@ -86,6 +108,20 @@ struct LineFFT {
     for (int k1 = 0; k1 < E; ++k1) sm[(k1 * TP + j) * CW + lane] = v[k1];
   }
   template <bool INV>
+  static CSMRI_HD void a_front_reg(cf* v, cf* sm, const cf* w, int j, int lane) {
+    RegFFT<E, INV>::run(v);
+    apply_twiddles_reg<INV>(v, w);
+#pragma unroll
+    for (int k1 = 0; k1 < E; ++k1) sm[(k1 * TP + j) * CW + lane] = v[k1];
+  }
+  template <bool INV>
+  static CSMRI_HD void b_back_reg(cf* v, const cf* sm, const cf* w, int j, int lane) {
+#pragma unroll
+    for (int k1 = 0; k1 < E; ++k1) v[k1] = sm[(k1 * TP + j) * CW + lane];
+    apply_twiddles_reg<INV>(v, w);
+    RegFFT<E, INV>::run(v);
+  }
+  template <bool INV>
   static CSMRI_HD void a_back(cf* u, const cf* sm, int t, int lane) {
 #pragma unroll
     for (int q = 0; q < Q; ++q)
@@ -98,6 +134,12 @@ struct LineFFT {
   // index held in u[r] by thread t (k-layout)
   static CSMRI_HD int k_index(int t, int r) {
     return ((r / T) * T + t) + E * (r % T);
+  }
+  // position of D[k] in the per-slice table csmri_dc_prepare writes: thread t
+  // finds the E factors of its k-layout registers contiguously at t*E + r
+  static CSMRI_HD int dtab_slot(int k) {
+    const int k1 = k % E, k2 = k / E;
+    return (k1 % T) * E + (k1 / T) * T + k2;
   }
   // index held in v[i] by thread j (n-layout)
   static CSMRI_HD int n_index(int j, int i) { return j + T * i; }

@@ -36,6 +36,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -94,20 +97,19 @@ struct PipeSmem {
   static constexpr int kBytes = kExchBytes + (ADD ? 2 : 1) * kTileBytes + kDBytes + kTwBytes + 64;
 };
 
-template <int H, int E, int CW, int MINB, int WT, bool ADD>
+template <int H, int E, int CW, int MINB, int WT, bool ADD, bool TWREG>
 __global__ void __launch_bounds__(CW*(H / E), MINB)
     dc_strip_pipe_kernel(const __grid_constant__ CUtensorMap tm_x,
                          const __grid_constant__ CUtensorMap tm_add,
                          const float* __restrict__ residual, const float* __restrict__ dtab,
-                         float* __restrict__ out, int W_rt, int nstrips_rt, int ntiles,
-                         int dephase) {
-  constexpr bool has_addend = ADD;
+                         float* __restrict__ out, int W_rt, int nstrips_rt, int ntiles, int probe_copy) {
   // WT != 0: compile-time row pitch (square slices) -> immediate store offsets
   const int W = WT ? WT : W_rt;
   const int nstrips = WT ? WT / CW : nstrips_rt;
   typedef LineFFT<H, E, CW> L;
   typedef PipeSmem<H, E, CW, ADD> S;
   constexpr int T = L::T;
+  constexpr int NT = CW * T;
   // NB: no integer arithmetic on this pointer - it would demote every access
   // below from LDS/STS to generic LD/ST (seen in the first ncu source page).
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -117,9 +119,10 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
   float* dbuf = xbuf + (ADD ? 2 : 1) * S::kTileFloats;      // [2][H]
   cf* tw_s = reinterpret_cast<cf*>(dbuf + 2 * H);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tw_s + H);
-  L::fill_twiddles(tw_s, threadIdx.x, CW * T);
-  const uint32_t bar_x = smem_u32(&bars[0]);
-  const uint32_t bar_a = smem_u32(&bars[1]);
+  L::fill_twiddles(tw_s, threadIdx.x, NT);
+  const uint32_t bar_x = smem_u32(&bars[0]);    // x tile (+ D row) landed
+  const uint32_t bar_a = smem_u32(&bars[1]);    // addend tile landed
+  const uint32_t bar_ae = smem_u32(&bars[2]);   // addend tile consumed by all NT threads
 
   const int lane = threadIdx.x % CW;
   const int j = threadIdx.x / CW;
@@ -147,21 +150,16 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
   if (threadIdx.x == 0) {
     mbar_init(bar_x, 1);
     mbar_init(bar_a, 1);
+    mbar_init(bar_ae, NT);
     fence_barrier_init();
   }
-  __syncthreads();
+  __syncthreads();   // barriers initialised, twiddle table filled
   if (threadIdx.x == 0 && tile < ntiles) {
     issue_x(tile, 0);
-    if (has_addend) issue_a(tile);
+    if (ADD) issue_a(tile);
   }
-
-  // CTAs of the second residency wave share an SM with a first-wave CTA and
-  // would otherwise run in lock-step with it (load burst / FFT / store burst
-  // at the same time); an initial delay keeps the two out of phase.
-  if (dephase > 0 && blockIdx.x >= gridDim.x / 2) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < dephase) {}
-  }
+  cf twr[TWREG ? E : 1];
+  if (TWREG) L::load_twiddle_row(twr, tw_s, j);
 
   uint32_t phase = 0;
   for (int it = 0; tile < ntiles; tile += gridDim.x, ++it, phase ^= 1) {
@@ -169,6 +167,13 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
     const int b = tile / nstrips, strip = tile - b * nstrips;
     const size_t gbase = (size_t)b * 2 * plane + (size_t)strip * CW + lane;
     const int next = tile + gridDim.x;
+
+    // the addend tile of the previous iteration has been read by everyone
+    // (bar_ae): refill it now, it is needed again only at the end of this tile
+    if (ADD && it > 0 && threadIdx.x == 0) {
+      mbar_wait(bar_ae, phase ^ 1);
+      issue_a(tile);
+    }
 
     cf v[E];
     mbar_wait(bar_x, phase);
@@ -187,29 +192,33 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
       }
     }
 
-    L::template a_front<false>(v, sm, tw_s, j, lane);
-    __syncthreads();  // exchange written; x tile consumed by every thread
-    if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
+    if (probe_copy) {
+      // tuning probe only (tools/gpu_probe.py): same loads/stores, no FFT -
+      // measures what the memory pattern alone can sustain
+      __syncthreads();
+      if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
+    } else {
+      if (TWREG) L::template a_front_reg<false>(v, sm, twr, j, lane);
+      else L::template a_front<false>(v, sm, tw_s, j, lane);
+      __syncthreads();  // exchange written; x tile consumed by every thread
+      if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
 
-    L::template a_back<false>(v, sm, j, lane);
-    {
-      const float* d = dbuf + slot * H;
-#pragma unroll
-      for (int r = 0; r < E; ++r) v[r] = cscale(v[r], d[L::k_index(j, r)]);
+      L::template a_back<false>(v, sm, j, lane);
+      L::apply_dtab(v, dbuf + slot * H + j * E);
+      L::template b_front<true>(v, sm, j, lane);
+      __syncthreads();
+      if (TWREG) L::template b_back_reg<true>(v, sm, twr, j, lane);
+      else L::template b_back<true>(v, sm, tw_s, j, lane);
     }
-    L::template b_front<true>(v, sm, j, lane);
-    __syncthreads();
-    L::template b_back<true>(v, sm, tw_s, j, lane);
 
-    if (has_addend) {
+    if (ADD) {
       mbar_wait(bar_a, phase);
 #pragma unroll
       for (int i = 0; i < E; ++i) {
         const int h = j + T * i;
         v[i] = cadd(v[i], mk(abuf[h * CW + lane], abuf[(H + h) * CW + lane]));
       }
-      __syncthreads();  // addend tile consumed by every thread
-      if (threadIdx.x == 0 && next < ntiles) issue_a(next);
+      mbar_arrive(bar_ae);
     }
     {
       float* pr = out + gbase;
