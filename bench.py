@@ -115,6 +115,51 @@ def make_batch(dev, B, n, seed):
     return x, w, batch['kspace'], batch['mask']
 
 
+def recnet_train_bench(dev, rank, world, steps=8, warmup=3, batch=32, n=256, blocks=5, convs=5,
+                       filters=32):
+    """BASELINE configs[2]: RecNet D5C5 MSE training step, batch 32 per GPU,
+    batch-sharded, one flat-bucket NCCL allreduce per step, fp32 (no TF32),
+    whole step captured in a CUDA graph.  Returns slices/s over all ranks."""
+    import torch.distributed as dist
+    from csmri_refinement_b200 import parallel, recnet, undersampling
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)                               # identical replicas on every rank
+    model = recnet.construct_model({'num_blocks': blocks, 'num_convs': convs,
+                                    'num_filters': filters}).to(dev)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    batches = []
+    for i in range(2):
+        img = torch.rand(batch, n, n, device=dev, generator=g)
+        rows = undersampling.cartesian_rows((batch, n, n), ACC, 8, False,
+                                            np.random.RandomState(100 + rank * 7 + i))
+        batches.append(undersampling.undersample(img, rows))
+    trainer = parallel.ShardedTrainer(model, lr=2e-4, cuda_graph=True, assume_row_constant=True)
+    for i in range(warmup):
+        trainer.step(batches[i % 2])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        loss = trainer.step(batches[i % 2])
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {'metric': 'recnet_train_slices_per_s', 'value': world * batch * steps / (ms * 1e-3),
+            'unit': UNIT, 'ms_per_step': ms / steps, 'steps': steps,
+            'config': 'RecNet D%dC%d nf=%d, MSE + Adam(2e-4), batch %d/GPU, %dx%d, fp32 convs '
+                      '(cuDNN, TF32 off), DC = fused strip kernel, CUDA-graph step, '
+                      'flat-bucket NCCL allreduce (%d bytes)' % (
+                          blocks, convs, filters, batch, n, n, trainer.bucket.nbytes()),
+            'loss': float(loss.item())}
+
+
 def cpu_baseline(sample_b=64, reps=6, noise=None):
     """Oracle port (torch.fft restatement of myfft.py:131-163) forward+backward
     on the host cores: the reference's DC has no CPU path of its own."""
@@ -184,6 +229,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--variant', type=int, default=None, help='kernel tuning variant (debug)')
+    ap.add_argument('--no-recnet', action='store_true', help='skip the RecNet training leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -346,6 +392,11 @@ def main():
         'roofline': roofline, 'e2e': e2e, 'gpu_launches': 2 * args.steps, 'clocks': clocks,
         'hbm_GBps_fwd_adj': value / world * 40 * N * N / 1e9,
     }
+    if not args.no_recnet:
+        try:
+            line['recnet_train'] = recnet_train_bench(dev, rank, world)
+        except Exception as e:  # secondary leg: never lose the headline line
+            line['recnet_train'] = {'error': repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline()
     elif rank == 0:

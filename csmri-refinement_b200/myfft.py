@@ -13,6 +13,7 @@ mask is row-constant (compressed_sensing.py:115-116), the per-row diagonal and
 ``iFFT2(k0)`` - is computed once per batch and cached here.
 """
 import collections
+import contextlib
 
 import torch
 
@@ -45,6 +46,23 @@ def _tensor_key(t):
 
 _PLAN_CACHE = collections.OrderedDict()
 _PLAN_CACHE_SIZE = 4
+_ASSUME_ROW_CONSTANT = None     # process-wide default, see assume_row_constant()
+
+
+@contextlib.contextmanager
+def assume_row_constant(value):
+    """Within the block, skip the per-batch device->host read that proves the
+    mask is row-constant and take ``value`` (True: Cartesian strip kernel,
+    False: general path, None: check) instead.  Needed under CUDA-graph
+    capture, where a host read is illegal."""
+    global _ASSUME_ROW_CONSTANT
+    prev = _ASSUME_ROW_CONSTANT
+    _ASSUME_ROW_CONSTANT = value
+    try:
+        yield
+    finally:
+        _ASSUME_ROW_CONSTANT = prev
+
 
 
 def get_plan(k0, mask, noise_lvl=None, assume_row_constant=None):
@@ -55,6 +73,8 @@ def get_plan(k0, mask, noise_lvl=None, assume_row_constant=None):
     and miss.  Entries are evicted LRU (4 batches).
     """
     v = float(noise_lvl) if noise_lvl else 0.0
+    if assume_row_constant is None:
+        assume_row_constant = _ASSUME_ROW_CONSTANT
     key = (_tensor_key(k0), _tensor_key(mask), v, assume_row_constant)
     plan = _PLAN_CACHE.get(key)
     if plan is not None:

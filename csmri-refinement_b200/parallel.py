@@ -1,0 +1,160 @@
+"""One process per GPU, batch sharded by rank, one flat-bucket gradient allreduce.
+
+Replaces ``utils/custom_data_parallel.py`` (a dict-aware ``nn.DataParallel``,
+:6-35) and the multi-GPU branch of ``utils/__init__.py:cudaify`` (:52-72): the
+reference replicates the model, scatters the batch and reduces gradients to
+GPU 0 inside ONE process every step.  Here every rank owns a contiguous,
+rank-major shard of the batch from the loader on (no scatter, no gather of
+outputs), the DC operator needs no communication at all, and the only
+collective of a training step is one ``all_reduce(SUM)`` over a flat fp32
+gradient buffer (0.13-2.3 MB for RecNet), followed by ``1/world``.
+
+:class:`ShardedTrainer` restates ``Runner._train_step``
+(training/runner.py:154-178): zero_grad, ``model(inp, kspace, mask)``, MSE on
+the raw 2-channel tensors (models/criteria.py:69-83), backward, optimizer step
+with ``Adam(lr, betas=(0.9, 0.999))`` (training/optimizers.py:18-21).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend=None):
+    """Join the process group described by RANK / WORLD_SIZE / LOCAL_RANK /
+    MASTER_ADDR / MASTER_PORT (torchrun).  Returns (rank, world, device)."""
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    use_cuda = torch.cuda.is_available()
+    if use_cuda:
+        torch.cuda.set_device(local_rank)
+        device = torch.device('cuda', local_rank)
+    else:
+        device = torch.device('cpu')
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29500')
+        if backend is None:
+            backend = 'nccl' if use_cuda else 'gloo'
+        kwargs = {'device_id': device} if backend == 'nccl' else {}
+        dist.init_process_group(backend, rank=rank, world_size=world, **kwargs)
+    return rank, world, device
+
+
+def shard_range(n_total, rank, world):
+    """Contiguous rank-major shard [lo, hi) of ``n_total`` items; sizes differ
+    by at most one (the first ``n_total % world`` ranks get the extra item)."""
+    base, extra = divmod(n_total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(batch, rank, world):
+    """Slice every tensor of a batch dict (scar_segmentation.py:212-218) to
+    this rank's shard along dim 0."""
+    n = next(iter(batch.values())).shape[0]
+    lo, hi = shard_range(n, rank, world)
+    return {k: v[lo:hi] for k, v in batch.items()}
+
+
+class FlatGradBucket(object):
+    """All gradients of ``params`` as views into ONE flat fp32 buffer, so the
+    gradient exchange is a single collective with no packing copies."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError('no trainable parameters')
+        dev, dt = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, device=dev, dtype=dt)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def check_views(self):
+        """Autograd accumulates in place, so the views must survive backward."""
+        off = 0
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
+                return False
+            off += p.numel()
+        return True
+
+    def allreduce_mean(self):
+        """SUM over ranks then * 1/world: the gradient of the mean loss over the
+        global batch when every rank holds the same number of slices."""
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / self.world)
+
+    def nbytes(self):
+        return self.flat.numel() * self.flat.element_size()
+
+
+class ShardedTrainer(object):
+    """RecNet MSE training step on this rank's shard (training/runner.py:154-178).
+
+    ``cuda_graph=True`` captures zero_grad + forward + loss + backward +
+    allreduce + Adam into one CUDA graph replayed per step on static input
+    buffers (the ~100 small kernels of a D5C5 step are launch-bound otherwise).
+    """
+
+    def __init__(self, model, lr=2e-4, betas=(0.9, 0.999), cuda_graph=False,
+                 assume_row_constant=None):
+        self.model = model
+        self.bucket = FlatGradBucket(model.parameters())
+        self.cuda_graph = bool(cuda_graph)
+        self.assume_row_constant = assume_row_constant
+        dev = self.bucket.flat.device
+        self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, betas=betas,
+                                          capturable=self.cuda_graph and dev.type == 'cuda')
+        self.criterion = torch.nn.MSELoss()
+        self._graph = None
+        self._static = None
+        self._loss = None
+
+    def _step_eager(self, batch):
+        from . import myfft
+        self.bucket.zero_()
+        with myfft.assume_row_constant(self.assume_row_constant):
+            out = self.model(batch['inp'], batch['kspace'], batch['mask'])
+        pred = out['pred'] if isinstance(out, dict) else out
+        loss = self.criterion(pred, batch['target'])
+        loss.backward()
+        self.bucket.allreduce_mean()
+        self.optimizer.step()
+        return loss.detach()
+
+    def _capture(self, batch):
+        self._static = {k: v.clone() for k, v in batch.items()}
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):           # warm-up off the capture stream
+            for _ in range(3):
+                self._step_eager(self._static)
+        torch.cuda.current_stream().wait_stream(s)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._loss = self._step_eager(self._static)
+
+    def step(self, batch):
+        """One optimizer step; returns the (local-shard) loss as a 0-dim tensor."""
+        if not self.cuda_graph:
+            return self._step_eager(batch)
+        if self.assume_row_constant is None:
+            raise ValueError('cuda_graph=True needs assume_row_constant=True/False: the mask '
+                             'check is a device->host read, which a graph cannot contain')
+        if self._graph is None:
+            self._capture(batch)
+        for k, v in batch.items():
+            self._static[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        return self._loss

@@ -344,3 +344,36 @@ def test_kernel_variants_and_unaligned_pointers_agree():
     assert xo.data_ptr() % 16 == 4
     out = ops.dc_cartesian(xo, None, plan.dtab, plan.addend)
     assert orc.rel_l2(out.cpu().numpy(), ref) < TOL
+
+
+def test_sharded_trainer_cuda_graph_matches_eager():
+    """The CUDA-graph-captured training step (parallel.ShardedTrainer) takes
+    the same optimizer steps as the eager one."""
+    from csmri_refinement_b200 import parallel
+    _, _, recnet, us = _mods()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = torch.Generator(device='cuda').manual_seed(5)
+        batches = []
+        for i in range(2):
+            img = torch.rand(4, 64, 64, device='cuda', generator=g)
+            rows = us.cartesian_rows((4, 64, 64), 4, 8, False, np.random.RandomState(i))
+            batches.append(us.undersample(img, rows))
+        nets = []
+        for graph in (False, True):
+            torch.manual_seed(0)
+            net = recnet.construct_model({'num_blocks': 2, 'num_convs': 3, 'num_filters': 8}).cuda()
+            tr = parallel.ShardedTrainer(net, lr=1e-3, cuda_graph=graph, assume_row_constant=True)
+            losses = [float(tr.step(batches[i % 2]).item()) for i in range(4)]
+            nets.append((net, losses, tr))
+        (n0, l0, t0), (n1, l1, t1) = nets
+        assert all(abs(a - b) < 1e-4 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
+        assert l0[2] < l0[0]                       # it actually trains
+        gmax = float(t0.bucket.flat.abs().max())
+        for (k, a), b, p in zip(n0.named_parameters(), n1.parameters(), t0.bucket.params):
+            noise_only = float(p.grad.abs().max()) < 1e-5 * gmax
+            tol = 5e-3 if noise_only else 5e-5
+            assert (a - b).abs().max().item() < tol, k
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev

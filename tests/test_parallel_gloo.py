@@ -1,0 +1,120 @@
+"""world_size-2 gloo tests (CPU) of the multi-rank host logic: rank-major batch
+sharding, the flat gradient bucket and its single allreduce, and that a
+2-rank sharded RecNet step equals the 1-rank step on the whole batch.
+The DC layers are the CPU oracle here (the product DC op is CUDA-only)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import dc_oracle as orc
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _make_batch(B, n, seed=0):
+    rs = np.random.RandomState(seed)
+    img = rs.uniform(0, 1, (B, n, n))
+    m1 = orc.cartesian_mask((B, n, n), 4, 8, False, np.random.RandomState(seed))
+    xu, xfu = orc.undersample(img, m1, rng=np.random.RandomState(seed))
+    return {'inp': torch.from_numpy(orc.to_tensor_format(xu)),
+            'kspace': torch.from_numpy(orc.to_tensor_format(xfu)),
+            'mask': torch.from_numpy(orc.to_tensor_format(m1, mask=True)),
+            'target': torch.from_numpy(orc.to_tensor_format(img))}
+
+
+def _build(seed=0):
+    from csmri_refinement_b200 import recnet
+    torch.manual_seed(seed)
+    return recnet.construct_model({'num_blocks': 2, 'num_convs': 2, 'num_filters': 4},
+                                  dc_factory=orc.OracleDataConsistencyInKspace)
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    from csmri_refinement_b200 import parallel
+    r, w, dev = parallel.init_distributed('gloo')
+    assert (r, w) == (rank, world) and dev.type == 'cpu'
+    model = _build()
+    trainer = parallel.ShardedTrainer(model, lr=1e-3)
+    assert trainer.bucket.world == world
+    full = _make_batch(4, 32)
+    shard = parallel.shard_batch(full, rank, world)
+    assert shard['inp'].shape[0] == 2
+    losses = [trainer.step(shard).item()]
+    grad1 = trainer.bucket.flat.clone()          # allreduced gradient of step 1
+    losses.append(trainer.step(shard).item())
+    assert trainer.bucket.check_views()
+    torch.save({'sd': model.state_dict(), 'losses': losses, 'grad1': grad1,
+                'grad': trainer.bucket.flat.clone()}, os.path.join(out_dir, 'r%d.pt' % rank))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_shard_range_is_contiguous_rank_major():
+    from csmri_refinement_b200 import parallel
+    for n, world in ((256, 8), (10, 4), (3, 8), (7, 2)):
+        spans = [parallel.shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for a, b in zip(spans, spans[1:]):
+            assert a[1] == b[0]
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_flat_bucket_views_survive_backward():
+    from csmri_refinement_b200 import parallel
+    model = _build()
+    bucket = parallel.FlatGradBucket(model.parameters())
+    assert bucket.flat.numel() == sum(p.numel() for p in model.parameters())
+    b = _make_batch(2, 32)
+    out = model(b['inp'], b['kspace'], b['mask'])
+    torch.nn.functional.mse_loss(out, b['target']).backward()
+    assert bucket.check_views()
+    ref = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert torch.equal(ref, bucket.flat) and bucket.flat.abs().sum() > 0
+    bucket.zero_()
+    assert all(float(p.grad.abs().sum()) == 0.0 for p in model.parameters())
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_step_equals_single_rank_full_batch(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(os.path.join(str(tmp_path), 'r0.pt'))
+    r1 = torch.load(os.path.join(str(tmp_path), 'r1.pt'))
+    # identical replicas after the allreduce'd updates
+    for k in r0['sd']:
+        assert torch.equal(r0['sd'][k], r1['sd'][k]), k
+    assert torch.equal(r0['grad'], r1['grad'])
+    # and equal to one process stepping on the whole batch
+    from csmri_refinement_b200 import parallel
+    model = _build()
+    trainer = parallel.ShardedTrainer(model, lr=1e-3)
+    full = _make_batch(4, 32)
+    losses = [trainer.step(full).item()]
+    # the allreduced mean of the shard gradients IS the full-batch gradient
+    assert orc.rel_l2(r0['grad1'].numpy(), trainer.bucket.flat.numpy()) < 1e-5
+    losses.append(trainer.step(full).item())
+    # Adam divides by sqrt(v): parameters whose true gradient is ~0 (the bias in
+    # front of a DC layer) move by O(lr) in a rounding-noise direction, so the
+    # weights are compared with an absolute tolerance well below lr = 1e-3
+    gmax = max(float(p.grad.abs().max()) for p in trainer.bucket.params)
+    for (k, v), p in zip(model.named_parameters(), trainer.bucket.params):
+        noise_only = float(p.grad.abs().max()) < 1e-5 * gmax
+        tol = 2.5e-3 if noise_only else 2e-5          # 2 steps * lr for noise-driven ones
+        assert (r0['sd'][k] - v.detach()).abs().max().item() < tol, k
+    # mean of the two shard losses == full-batch loss (equal shard sizes)
+    for i in range(2):
+        assert abs(0.5 * (r0['losses'][i] + r1['losses'][i]) - losses[i]) < 1e-6
