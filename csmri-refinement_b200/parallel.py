@@ -134,16 +134,38 @@ class ShardedTrainer(object):
         return loss.detach()
 
     def _capture(self, batch):
+        from . import myfft
         self._static = {k: v.clone() for k, v in batch.items()}
+        params = self.bucket.params
+        # warm-up and capture must not advance training: snapshot weights and
+        # optimizer state, restore them (in place - the graph holds the
+        # addresses) once the graph exists
+        saved_p = [p.detach().clone() for p in params]
+        saved_s = {i: {k: v.clone() for k, v in self.optimizer.state[p].items()
+                       if torch.is_tensor(v)}
+                   for i, p in enumerate(params) if p in self.optimizer.state}
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):           # warm-up off the capture stream
             for _ in range(3):
                 self._step_eager(self._static)
         torch.cuda.current_stream().wait_stream(s)
+        # the per-batch DC plan (D table, addend) must be recomputed INSIDE the
+        # graph on every replay: drop the entry the warm-up left in the cache
+        myfft.clear_plan_cache()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._loss = self._step_eager(self._static)
+        myfft.clear_plan_cache()
+        with torch.no_grad():
+            for i, p in enumerate(params):
+                p.copy_(saved_p[i])
+                for k, v in self.optimizer.state[p].items():
+                    if torch.is_tensor(v):
+                        if i in saved_s and k in saved_s[i]:
+                            v.copy_(saved_s[i][k])
+                        else:
+                            v.zero_()
 
     def step(self, batch):
         """One optimizer step; returns the (local-shard) loss as a 0-dim tensor."""
