@@ -63,10 +63,11 @@ _SIGNATURES = {
     # tuning knob used by bench.py only (not declared in include/csmri_dc.h)
     'csmri_set_variant': (ctypes.c_int, [ctypes.c_int]),
     'csmri_set_tuning': (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    'csmri_set_trace': (ctypes.c_int, [ctypes.c_void_p]),
 }
 
 # every symbol include/csmri_dc.h declares
-ABI_SYMBOLS = [k for k in _SIGNATURES if k not in ('csmri_set_variant', 'csmri_set_tuning')]
+ABI_SYMBOLS = [k for k in _SIGNATURES if k not in ('csmri_set_variant', 'csmri_set_tuning', 'csmri_set_trace')]
 
 
 def lib():

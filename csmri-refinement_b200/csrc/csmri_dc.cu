@@ -35,6 +35,8 @@
 #include "../../include/csmri_dc.h"
 #include "dc_core.cuh"
 #include "dc_pipe.cuh"
+#include "dc_pipe2.cuh"
+#include "dc_pipev.cuh"
 
 namespace csmri {
 
@@ -445,6 +447,18 @@ static int ensure_init() {
     host_ready = true;
   }
   CSMRI_CUDA(cudaMemcpyToSymbol(c_twiddle, h_twiddle, sizeof(cf) * kTwN));
+  {
+    // [T][E] inter-pass tables for every supported line length (dc_core.cuh)
+    static cf lines[kTwLinesTotal];
+    for (int n = 32; n <= 1024; n *= 2) {
+      const int e = n <= 64 ? 8 : (n <= 256 ? 16 : 32);
+      for (int idx = 0; idx < n; ++idx) {
+        const int jj = idx / e, k1 = idx % e;
+        lines[(n - 32) + idx] = h_twiddle[(jj * k1) * (kTwN / n)];
+      }
+    }
+    CSMRI_CUDA(cudaMemcpyToSymbol(g_tw_lines, lines, sizeof(lines)));
+  }
   g_tw_uploaded[dev] = true;
   return CSMRI_OK;
 }
@@ -474,15 +488,36 @@ static int check_ptr(const void* p, const char* name) {
     if (rc_ != CSMRI_OK) return rc_; \
   } while (0)
 
+// cudaFuncSetAttribute is issued once per (kernel, device), never on the hot
+// path: per-launch calls showed up as a ~9 us bubble between back-to-back
+// launches in the per-CTA timeline (tools/gpu_trace.py).
+struct SmemOptIn {
+  const void* fn;
+  int dev;
+  int bytes;
+};
+static SmemOptIn g_smem_optin[512];
+static int g_smem_optin_n = 0;
+
 template <typename K>
 static int set_smem(K kernel, int bytes) {
-  if (bytes > 48 * 1024)
-    CSMRI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (bytes <= 48 * 1024) return CSMRI_OK;
+  int dev = 0;
+  CSMRI_CUDA(cudaGetDevice(&dev));
+  const void* fn = (const void*)kernel;
+  for (int i = 0; i < g_smem_optin_n; ++i)
+    if (g_smem_optin[i].fn == fn && g_smem_optin[i].dev == dev && g_smem_optin[i].bytes >= bytes)
+      return CSMRI_OK;
+  CSMRI_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (g_smem_optin_n < 512) g_smem_optin[g_smem_optin_n++] = SmemOptIn{fn, dev, bytes};
   return CSMRI_OK;
 }
 
 static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_set_tuning
 static int g_pf_dist = 0;        // L2 software-prefetch distance in tiles (0 = off)
+static int g_dephase = 0;        // tuning probe: random CTA start delay (cycles)
+static long long* g_trace = nullptr;  // tuning probe: per-CTA timeline buffers (2 x 1024 x 40)
+static int g_trace_launch = 0;
 static int g_probe_copy = 0;     // tuning probe: pipelined kernel moves data but skips the FFT
 
 // ---- TMA-fed persistent strip kernel -----------------------------------------
@@ -562,7 +597,7 @@ static int launch_strip_pipe_wt(const float* x, const float* residual, const flo
   int grid = sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
   kern<<<grid, CW * L::T, S::kBytes, s>>>(tm_x, tm_a, residual, dtab, out, W, nstrips, ntiles,
-                                          g_probe_copy);
+                                          g_probe_copy, g_dephase);
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }
@@ -580,6 +615,84 @@ static int launch_strip_pipe_cfg(const float* x, const float* residual, const fl
   if (W == H)
     return launch_strip_pipe_wt<H, E, CW, MINB_A, H, false, TWREG>(x, residual, dtab, addend, out, B, W, s);
   return launch_strip_pipe_wt<H, E, CW, MINB_A, 0, false, TWREG>(x, residual, dtab, addend, out, B, W, s);
+}
+
+template <int H, int E, int CW, int MINB, int WT, bool ADD, int XS>
+static int launch_strip_pipe2_wt(const float* x, const float* residual, const float* dtab,
+                                 const float* addend, float* out, int B, int W, cudaStream_t s) {
+  typedef LineFFT<H, E, CW> L;
+  typedef Pipe2Smem<H, E, CW, XS> S;
+  auto kern = dc_strip_pipe2_kernel<H, E, CW, MINB, WT, ADD, XS>;
+  CSMRI_TRY(set_smem(kern, S::kBytes));
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    CSMRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, CW * L::T,
+                                                             S::kBytes));
+    if (blocks_per_sm < 1) return fail(CSMRI_E_CUDA, "pipelined strip kernel does not fit an SM");
+  }
+  alignas(64) CUtensorMap tm_x;
+  CSMRI_TRY(make_tile_map(&tm_x, x, B, H, W, CW));
+  const int nstrips = W / CW;
+  const int ntiles = B * nstrips;
+  int grid = sm_count() * blocks_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<grid, CW * L::T, S::kBytes, s>>>(tm_x, addend, residual, dtab, out, W, nstrips, ntiles);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+template <int H, int E, int CW, int MINB_F, int XS_F, int MINB_A, int XS_A>
+static int launch_strip_pipe2_cfg(const float* x, const float* residual, const float* dtab,
+                                  const float* addend, float* out, int B, int W, cudaStream_t s) {
+  if (addend != nullptr) {
+    if (W == H)
+      return launch_strip_pipe2_wt<H, E, CW, MINB_F, H, true, XS_F>(x, residual, dtab, addend, out, B, W, s);
+    return launch_strip_pipe2_wt<H, E, CW, MINB_F, 0, true, XS_F>(x, residual, dtab, addend, out, B, W, s);
+  }
+  if (W == H)
+    return launch_strip_pipe2_wt<H, E, CW, MINB_A, H, false, XS_A>(x, residual, dtab, addend, out, B, W, s);
+  return launch_strip_pipe2_wt<H, E, CW, MINB_A, 0, false, XS_A>(x, residual, dtab, addend, out, B, W, s);
+}
+
+template <int H, int E, int CW, int MINB, int WT, bool ADD>
+static int launch_strip_pipev_wt(const float* x, const float* residual, const float* dtab,
+                                 const float* addend, float* out, int B, int W, cudaStream_t s) {
+  typedef PipeVSmem<H, E, CW, ADD> S;
+  constexpr int threads = (CW / 2) * (H / E);
+  auto kern = dc_strip_pipev_kernel<H, E, CW, MINB, WT, ADD>;
+  CSMRI_TRY(set_smem(kern, S::kBytes));
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    CSMRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads,
+                                                             S::kBytes));
+    if (blocks_per_sm < 1) return fail(CSMRI_E_CUDA, "two-column strip kernel does not fit an SM");
+  }
+  alignas(64) CUtensorMap tm_x, tm_a;
+  CSMRI_TRY(make_tile_map(&tm_x, x, B, H, W, CW));
+  if (ADD) CSMRI_TRY(make_tile_map(&tm_a, addend, B, H, W, CW));
+  else tm_a = tm_x;
+  const int nstrips = W / CW;
+  const int ntiles = B * nstrips;
+  int grid = sm_count() * blocks_per_sm;
+  if (grid > ntiles) grid = ntiles;
+  kern<<<grid, threads, S::kBytes, s>>>(tm_x, tm_a, residual, dtab, out, W, nstrips, ntiles,
+                                        g_dephase,
+                                        g_trace ? g_trace + (size_t)((g_trace_launch++) & 1) * 1024 * 40 : nullptr);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+template <int H, int E, int CW, int MINB_F, int MINB_A>
+static int launch_strip_pipev_cfg(const float* x, const float* residual, const float* dtab,
+                                  const float* addend, float* out, int B, int W, cudaStream_t s) {
+  if (addend != nullptr) {
+    if (W == H)
+      return launch_strip_pipev_wt<H, E, CW, MINB_F, H, true>(x, residual, dtab, addend, out, B, W, s);
+    return launch_strip_pipev_wt<H, E, CW, MINB_F, 0, true>(x, residual, dtab, addend, out, B, W, s);
+  }
+  if (W == H)
+    return launch_strip_pipev_wt<H, E, CW, MINB_A, H, false>(x, residual, dtab, addend, out, B, W, s);
+  return launch_strip_pipev_wt<H, E, CW, MINB_A, 0, false>(x, residual, dtab, addend, out, B, W, s);
 }
 
 static bool tma_ok(const float* x, const float* addend, const float* dtab) {
@@ -615,14 +728,51 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
     case 32: return launch_strip_row_cfg<32, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 64: return launch_strip_row_cfg<64, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 128:
-      if ((g_strip_variant == 0 || g_strip_variant == 10) && tma_ok(x, addend, dtab))
+      if (g_strip_variant == 0 && tma_ok(x, addend, dtab)) {
+        if (addend != nullptr)
+          return launch_strip_pipe_cfg<128, 16, 32, 2>(x, residual, dtab, addend, out, B, W, s);
+        return launch_strip_pipev_cfg<128, 16, 32, 2, 3>(x, residual, dtab, addend, out, B, W, s);
+      }
+      if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
         return launch_strip_pipe_cfg<128, 16, 32, 2>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 30 && tma_ok(x, addend, dtab))
+        return launch_strip_pipev_cfg<128, 16, 32, 2, 3>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 31 && tma_ok(x, addend, dtab))
+        return launch_strip_pipev_cfg<128, 16, 16, 4, 6>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 20 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe2_cfg<128, 16, 32, 2, 2, 2, 2>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 21 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe2_cfg<128, 16, 32, 3, 2, 3, 2>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 11 && tma_ok(x, addend, dtab))
         return launch_strip_pipe_cfg<128, 16, 16, 4>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<128, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 256:
-      if ((g_strip_variant == 0 || g_strip_variant == 10) && tma_ok(x, addend, dtab))
+      if (g_strip_variant == 0 && tma_ok(x, addend, dtab)) {
+        // measured best per direction (profiles/): forward = two columns per
+        // thread, 32-column tiles, one 256-thread CTA per SM; adjoint = two
+        // columns per thread, 16-column tiles, three 128-thread CTAs per SM
+        if (addend != nullptr)
+          return launch_strip_pipev_cfg<256, 16, 32, 1, 1>(x, residual, dtab, addend, out, B, W, s);
+        return launch_strip_pipev_cfg<256, 16, 16, 2, 3>(x, residual, dtab, addend, out, B, W, s);
+      }
+      if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
         return launch_strip_pipe_cfg<256, 16, 16, 2>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 30 && tma_ok(x, addend, dtab))
+        return launch_strip_pipev_cfg<256, 16, 16, 2, 3>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 31 && tma_ok(x, addend, dtab))
+        return launch_strip_pipev_cfg<256, 16, 32, 1, 1>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 32 && tma_ok(x, addend, dtab))
+        return launch_strip_pipev_cfg<256, 16, 16, 2, 2>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 20 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe2_cfg<256, 16, 16, 2, 2, 2, 2>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 21 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe2_cfg<256, 16, 16, 2, 2, 3, 1>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 22 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe2_cfg<256, 16, 16, 3, 1, 3, 1>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 23 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe2_cfg<256, 16, 32, 1, 2, 1, 2>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 24 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe2_cfg<256, 16, 16, 2, 3, 2, 3>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 11 && tma_ok(x, addend, dtab))
         return launch_strip_pipe_cfg<256, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 12 && tma_ok(x, addend, dtab))
@@ -647,6 +797,8 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
     case 512:
       if ((g_strip_variant == 0 || g_strip_variant == 10) && tma_ok(x, addend, dtab))
         return launch_strip_pipe_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
+      if (g_strip_variant == 20 && tma_ok(x, addend, dtab))
+        return launch_strip_pipe2_cfg<512, 32, 16, 1, 2, 1, 2>(x, residual, dtab, addend, out, B, W, s);
       if (g_strip_variant == 1)
         return launch_strip_row_cfg<512, 32, 32, 1>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
@@ -778,10 +930,16 @@ int csmri_set_variant(int v) {
   g_strip_variant = v;
   return CSMRI_OK;
 }
+int csmri_set_trace(void* device_buffer) {
+  g_trace = (long long*)device_buffer;
+  g_trace_launch = 0;
+  return CSMRI_OK;
+}
 int csmri_set_tuning(int key, int value) {
   if (key == 0) g_strip_variant = value;
   else if (key == 1) g_pf_dist = value;
   else if (key == 2) g_probe_copy = value;
+  else if (key == 3) g_dephase = value;
   else return fail(CSMRI_E_ARG, "unknown tuning key %d", key);
   return CSMRI_OK;
 }

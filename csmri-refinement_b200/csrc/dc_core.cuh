@@ -26,8 +26,16 @@ namespace csmri {
 
 constexpr int kTwN = 1024;  // twiddle table: W_1024^m = exp(-2 pi i m/1024)
 
+// Per-size inter-pass twiddle tables W_N^{j*k1} in [T][E] order, for N = 32 ..
+// 1024 back to back (N entries each, offset N - 32).  They live in global
+// memory (L2-resident, 16 KiB) and each CTA copies its table into shared memory
+// with coalesced 8-byte loads.  (The first version gathered them from constant
+// memory with per-thread indices: divergent, cold LDC cost ~7 us per CTA -
+// found with the per-CTA timeline probe, tools/gpu_trace.py.)
+constexpr int kTwLinesTotal = 2048 - 32;
 #ifdef __CUDACC__
 __constant__ cf c_twiddle[kTwN];
+__device__ cf g_tw_lines[kTwLinesTotal];
 #endif
 #ifndef __CUDA_ARCH__
 extern cf h_twiddle[kTwN];  // host mirror (emulation + upload source)
@@ -61,10 +69,15 @@ struct LineFFT {
   // reads its row with E/2 broadcast LDS.128.
   static constexpr int kTwBytes = N * (int)sizeof(cf);
   static CSMRI_HD void fill_twiddles(cf* tw_s, int tid, int nthreads) {
+#ifdef __CUDA_ARCH__
+    const cf* src = g_tw_lines + (N - 32);
+    for (int idx = tid; idx < N; idx += nthreads) tw_s[idx] = __ldg(src + idx);
+#else
     for (int idx = tid; idx < N; idx += nthreads) {
       const int jj = idx / E, k1 = idx - jj * E;
       tw_s[idx] = tw_lookup(jj * k1 * (kTwN / N));
     }
+#endif
   }
   // register-resident twiddle row (persistent kernels keep it across tiles)
   static CSMRI_HD void load_twiddle_row(cf* w, const cf* tw_s, int j) {
@@ -159,6 +172,82 @@ struct LineFFT {
   static CSMRI_HD void b_back(cf* v, const cf* sm, const cf* tw_s, int j, int lane) {
 #pragma unroll
     for (int k1 = 0; k1 < E; ++k1) v[k1] = sm[(k1 * TP + j) * CW + lane];
+    apply_twiddles<INV>(v, tw_s, j);
+    RegFFT<E, INV>::run(v);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// LineFFTV: the same two-pass transform with TWO lines per thread (cf2, SoA).
+// LW lanes own 2*LW adjacent lines; exchange slots are float4
+// {re.x, re.y, im.x, im.y} moved with STS.128 / LDS.128 (a quarter-warp covers a
+// contiguous 128 bytes in both layouts, so no padding is needed).
+// ---------------------------------------------------------------------------
+template <int N, int E, int LW>
+struct LineFFTV {
+  typedef LineFFT<N, E, LW> Base;           // index helpers + twiddle table
+  static constexpr int T = N / E;
+  static constexpr int Q = E / T;
+  static constexpr int kSmemBytes = N * LW * (int)sizeof(float4);
+  static constexpr int kTwBytes = Base::kTwBytes;
+
+  static CSMRI_HD float4 pack(cf2 a) {
+    float4 r; r.x = a.re.x; r.y = a.re.y; r.z = a.im.x; r.w = a.im.y; return r;
+  }
+  static CSMRI_HD cf2 unpack(float4 a) { return mk2(mk(a.x, a.y), mk(a.z, a.w)); }
+
+  template <bool INV>
+  static CSMRI_HD void apply_twiddles(cf2* v, const cf* tw_s, int j) {
+    const float4* row = reinterpret_cast<const float4*>(tw_s + j * E);
+#pragma unroll
+    for (int p = 0; p < E / 2; ++p) {
+      const float4 q = row[p];
+      if (p > 0) v[2 * p] = INV ? cmul_conj(v[2 * p], mk(q.x, q.y)) : cmul(v[2 * p], mk(q.x, q.y));
+      v[2 * p + 1] = INV ? cmul_conj(v[2 * p + 1], mk(q.z, q.w)) : cmul(v[2 * p + 1], mk(q.z, q.w));
+    }
+  }
+  static CSMRI_HD void apply_dtab(cf2* u, const float* drow_t) {
+    const float4* d4 = reinterpret_cast<const float4*>(drow_t);
+#pragma unroll
+    for (int p = 0; p < E / 4; ++p) {
+      const float4 q = d4[p];
+      u[4 * p] = cscale(u[4 * p], q.x);
+      u[4 * p + 1] = cscale(u[4 * p + 1], q.y);
+      u[4 * p + 2] = cscale(u[4 * p + 2], q.z);
+      u[4 * p + 3] = cscale(u[4 * p + 3], q.w);
+    }
+  }
+  template <bool INV>
+  static CSMRI_HD void a_front(cf2* v, float4* sm, const cf* tw_s, int j, int lane) {
+    RegFFT<E, INV>::run(v);
+    apply_twiddles<INV>(v, tw_s, j);
+#pragma unroll
+    for (int k1 = 0; k1 < E; ++k1) sm[(k1 * T + j) * LW + lane] = pack(v[k1]);
+  }
+  template <bool INV>
+  static CSMRI_HD void a_back(cf2* u, const float4* sm, int t, int lane) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+      for (int j2 = 0; j2 < T; ++j2)
+        u[q * T + j2] = unpack(sm[((q * T + t) * T + j2) * LW + lane]);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) RegFFT<T, INV>::run(u + q * T);
+  }
+  template <bool INV>
+  static CSMRI_HD void b_front(cf2* u, float4* sm, int t, int lane) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) RegFFT<T, INV>::run(u + q * T);
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+      for (int j2 = 0; j2 < T; ++j2)
+        sm[((q * T + t) * T + j2) * LW + lane] = pack(u[q * T + j2]);
+  }
+  template <bool INV>
+  static CSMRI_HD void b_back(cf2* v, const float4* sm, const cf* tw_s, int j, int lane) {
+#pragma unroll
+    for (int k1 = 0; k1 < E; ++k1) v[k1] = unpack(sm[(k1 * T + j) * LW + lane]);
     apply_twiddles<INV>(v, tw_s, j);
     RegFFT<E, INV>::run(v);
   }

@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
     dc_strip_pipe_kernel(const __grid_constant__ CUtensorMap tm_x,
                          const __grid_constant__ CUtensorMap tm_add,
                          const float* __restrict__ residual, const float* __restrict__ dtab,
-                         float* __restrict__ out, int W_rt, int nstrips_rt, int ntiles, int probe_copy) {
+                         float* __restrict__ out, int W_rt, int nstrips_rt, int ntiles, int probe_copy,
+                         int dephase) {
   // WT != 0: compile-time row pitch (square slices) -> immediate store offsets
   const int W = WT ? WT : W_rt;
   const int nstrips = WT ? WT / CW : nstrips_rt;
@@ -119,7 +120,6 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
   float* dbuf = xbuf + (ADD ? 2 : 1) * S::kTileFloats;      // [2][H]
   cf* tw_s = reinterpret_cast<cf*>(dbuf + 2 * H);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tw_s + H);
-  L::fill_twiddles(tw_s, threadIdx.x, NT);
   const uint32_t bar_x = smem_u32(&bars[0]);    // x tile (+ D row) landed
   const uint32_t bar_a = smem_u32(&bars[1]);    // addend tile landed
   const uint32_t bar_ae = smem_u32(&bars[2]);   // addend tile consumed by all NT threads
@@ -146,20 +146,31 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
       tma_load_4d(smem_u32(abuf), &tm_add, bar_a, strip * CW, 0, 0, b * 2);
   };
 
+  // thread 0 gets the first tile moving before anything else; the twiddle
+  // table fill and the barrier-visibility sync overlap its HBM latency
   int tile = blockIdx.x;
   if (threadIdx.x == 0) {
     mbar_init(bar_x, 1);
     mbar_init(bar_a, 1);
     mbar_init(bar_ae, NT);
     fence_barrier_init();
+    if (tile < ntiles) {
+      issue_x(tile, 0);
+      if (ADD) issue_a(tile);
+    }
   }
+  L::fill_twiddles(tw_s, threadIdx.x, NT);
   __syncthreads();   // barriers initialised, twiddle table filled
-  if (threadIdx.x == 0 && tile < ntiles) {
-    issue_x(tile, 0);
-    if (ADD) issue_a(tile);
-  }
   cf twr[TWREG ? E : 1];
   if (TWREG) L::load_twiddle_row(twr, tw_s, j);
+
+  // tuning probe: a pseudo-random start delay de-synchronises the CTAs, which
+  // otherwise all load / compute / store in lock-step across the whole chip
+  if (dephase > 0) {
+    const unsigned r = (blockIdx.x * 2654435761u) >> 22;          // 0..1023
+    const long long t0 = clock64(), d = ((long long)dephase * r) >> 10;
+    while (clock64() - t0 < d) {}
+  }
 
   uint32_t phase = 0;
   for (int it = 0; tile < ntiles; tile += gridDim.x, ++it, phase ^= 1) {

@@ -90,6 +90,39 @@ CSMRI_HD cf cmul_conj(cf a, cf w) {
 CSMRI_HD cf cscale(cf a, float s) { return f2mul(a, mk(s, s)); }
 
 // ---------------------------------------------------------------------------
+// cf2: the same complex arithmetic on TWO independent lines at once, stored
+// structure-of-arrays {re.x, re.y} / {im.x, im.y}.  Every operation is still one
+// packed instruction per register pair, multiplications by a (shared) twiddle
+// broadcast the scalar, and +-i rotations are pure register renaming.  A thread
+// that owns two adjacent image columns moves them with 64-bit global / 128-bit
+// shared accesses, halving the memory-instruction count per element.
+// ---------------------------------------------------------------------------
+struct cf2 {
+  float2 re, im;
+};
+CSMRI_HD cf2 mk2(float2 re, float2 im) { cf2 r; r.re = re; r.im = im; return r; }
+CSMRI_HD float2 f2neg(float2 a) { return mk(-a.x, -a.y); }
+CSMRI_HD cf2 cadd(cf2 a, cf2 b) { return mk2(f2add(a.re, b.re), f2add(a.im, b.im)); }
+CSMRI_HD cf2 csub(cf2 a, cf2 b) { return mk2(f2sub(a.re, b.re), f2sub(a.im, b.im)); }
+CSMRI_HD cf2 add_mi(cf2 a, cf2 b) { return mk2(f2add(a.re, b.im), f2sub(a.im, b.re)); }
+CSMRI_HD cf2 add_pi(cf2 a, cf2 b) { return mk2(f2sub(a.re, b.im), f2add(a.im, b.re)); }
+CSMRI_HD cf2 cmul(cf2 a, cf w) {
+  const float2 c = mk(w.x, w.x), s = mk(w.y, w.y);
+  return mk2(f2fma(a.re, c, f2neg(f2mul(a.im, s))), f2fma(a.im, c, f2mul(a.re, s)));
+}
+CSMRI_HD cf2 cmul_conj(cf2 a, cf w) {
+  const float2 c = mk(w.x, w.x), s = mk(w.y, w.y);
+  return mk2(f2fma(a.re, c, f2mul(a.im, s)), f2fma(a.im, c, f2neg(f2mul(a.re, s))));
+}
+CSMRI_HD cf2 cscale(cf2 a, float s) { return mk2(f2mul(a.re, mk(s, s)), f2mul(a.im, mk(s, s))); }
+CSMRI_HD cf2 rot_mi(cf2 a) { return mk2(a.im, f2neg(a.re)); }   // a * (-i)
+CSMRI_HD cf2 rot_pi(cf2 a) { return mk2(f2neg(a.im), a.re); }   // a * (+i)
+CSMRI_HD cf2 cneg(cf2 a) { return mk2(f2neg(a.re), f2neg(a.im)); }
+CSMRI_HD cf rot_mi(cf a) { return mk(a.y, -a.x); }
+CSMRI_HD cf rot_pi(cf a) { return mk(-a.y, a.x); }
+CSMRI_HD cf cneg(cf a) { return mk(-a.x, -a.y); }
+
+// ---------------------------------------------------------------------------
 // compile-time twiddles: cos/sin(2 pi k / n) evaluated in double by Taylor
 // series after octant reduction (error < 2e-15, i.e. correctly rounded floats)
 // ---------------------------------------------------------------------------
@@ -131,17 +164,17 @@ __host__ __device__ constexpr double ct_cos2pi(int k, int n) {
 __host__ __device__ constexpr double ct_sin2pi(int k, int n) { return ct_cos2pi(4 * k - n, 4 * n); }
 
 // multiply by W_N^K (forward, e^{-2 pi i K/N}) or its conjugate (INV)
-template <int K, int N, bool INV>
-CSMRI_HD cf twiddle(cf a) {
+template <int K, int N, bool INV, typename C>
+CSMRI_HD C twiddle(C a) {
   constexpr int KK = ((K % N) + N) % N;
   if constexpr (KK == 0) {
     return a;
   } else if constexpr (4 * KK == N) {            // -i (fwd) / +i (inv)
-    return INV ? mk(-a.y, a.x) : mk(a.y, -a.x);
+    return INV ? rot_pi(a) : rot_mi(a);
   } else if constexpr (2 * KK == N) {
-    return mk(-a.x, -a.y);
+    return cneg(a);
   } else if constexpr (4 * KK == 3 * N) {        // +i (fwd) / -i (inv)
-    return INV ? mk(a.y, -a.x) : mk(-a.y, a.x);
+    return INV ? rot_mi(a) : rot_pi(a);
   } else {
     constexpr float c = (float)ct_cos2pi(KK, N);
     constexpr float s = (float)ct_sin2pi(KK, N);
@@ -152,17 +185,17 @@ CSMRI_HD cf twiddle(cf a) {
 // ---------------------------------------------------------------------------
 // butterflies, in place, natural order
 // ---------------------------------------------------------------------------
-template <bool INV>
-CSMRI_HD void fft2(cf& a0, cf& a1) {
-  cf t = cadd(a0, a1);
+template <bool INV, typename C>
+CSMRI_HD void fft2(C& a0, C& a1) {
+  C t = cadd(a0, a1);
   a1 = csub(a0, a1);
   a0 = t;
 }
 
-template <bool INV>
-CSMRI_HD void fft4(cf& a0, cf& a1, cf& a2, cf& a3) {
-  cf t0 = cadd(a0, a2), t1 = csub(a0, a2);
-  cf t2 = cadd(a1, a3), t3 = csub(a1, a3);
+template <bool INV, typename C>
+CSMRI_HD void fft4(C& a0, C& a1, C& a2, C& a3) {
+  C t0 = cadd(a0, a2), t1 = csub(a0, a2);
+  C t2 = cadd(a1, a3), t3 = csub(a1, a3);
   a0 = cadd(t0, t2);
   a2 = csub(t0, t2);
   if (INV) { a1 = add_pi(t1, t3); a3 = add_mi(t1, t3); }
@@ -172,13 +205,13 @@ CSMRI_HD void fft4(cf& a0, cf& a1, cf& a2, cf& a3) {
 template <int N, bool INV> struct RegFFT;
 
 template <bool INV> struct RegFFT<1, INV> {
-  static CSMRI_HD void run(cf*) {}
+  template <typename C> static CSMRI_HD void run(C*) {}
 };
 template <bool INV> struct RegFFT<2, INV> {
-  static CSMRI_HD void run(cf* v) { fft2<INV>(v[0], v[1]); }
+  template <typename C> static CSMRI_HD void run(C* v) { fft2<INV>(v[0], v[1]); }
 };
 template <bool INV> struct RegFFT<4, INV> {
-  static CSMRI_HD void run(cf* v) { fft4<INV>(v[0], v[1], v[2], v[3]); }
+  template <typename C> static CSMRI_HD void run(C* v) { fft4<INV>(v[0], v[1], v[2], v[3]); }
 };
 
 // Generic two-factor step N = A*B on a register array (all loops unroll):
@@ -187,10 +220,10 @@ template <bool INV> struct RegFFT<4, INV> {
 //   X[k1 + A*k2] at v[k1 + A*k2].
 template <int N, int A, int B, bool INV>
 struct RegFFT2F {
-  template <int N2>
-  static CSMRI_HD void stage1(cf* v) {
+  template <int N2, typename C>
+  static CSMRI_HD void stage1(C* v) {
     if constexpr (N2 < B) {
-      cf t[A];
+      C t[A];
 #pragma unroll
       for (int n1 = 0; n1 < A; ++n1) t[n1] = v[N2 + B * n1];
       RegFFT<A, INV>::run(t);
@@ -200,19 +233,20 @@ struct RegFFT2F {
       stage1<N2 + 1>(v);
     }
   }
-  template <int N2, int K1>
-  static CSMRI_HD void tw_row(cf* t) {
+  template <int N2, int K1, typename C>
+  static CSMRI_HD void tw_row(C* t) {
     if constexpr (K1 < A) {
       t[K1] = twiddle<N2 * K1, N, INV>(t[K1]);
       tw_row<N2, K1 + 1>(t);
     }
   }
-  static CSMRI_HD void run(cf* v) {
+  template <typename C>
+  static CSMRI_HD void run(C* v) {
     stage1<0>(v);
-    cf w[N];
+    C w[N];
 #pragma unroll
     for (int k1 = 0; k1 < A; ++k1) {
-      cf t[B];
+      C t[B];
 #pragma unroll
       for (int n2 = 0; n2 < B; ++n2) t[n2] = v[n2 + B * k1];
       RegFFT<B, INV>::run(t);
@@ -225,13 +259,13 @@ struct RegFFT2F {
 };
 
 template <bool INV> struct RegFFT<8, INV> {
-  static CSMRI_HD void run(cf* v) { RegFFT2F<8, 4, 2, INV>::run(v); }
+  template <typename C> static CSMRI_HD void run(C* v) { RegFFT2F<8, 4, 2, INV>::run(v); }
 };
 template <bool INV> struct RegFFT<16, INV> {
-  static CSMRI_HD void run(cf* v) { RegFFT2F<16, 4, 4, INV>::run(v); }
+  template <typename C> static CSMRI_HD void run(C* v) { RegFFT2F<16, 4, 4, INV>::run(v); }
 };
 template <bool INV> struct RegFFT<32, INV> {
-  static CSMRI_HD void run(cf* v) { RegFFT2F<32, 4, 8, INV>::run(v); }
+  template <typename C> static CSMRI_HD void run(C* v) { RegFFT2F<32, 4, 8, INV>::run(v); }
 };
 
 }  // namespace csmri

@@ -83,6 +83,67 @@ static double check(bool inv_first) {
   return e1 > e2 ? e1 : e2;
 }
 
+// two lines per thread (cf2 / LineFFTV): forward DFT vs naive, then round trip
+template <int N, int E>
+static double check_v2() {
+  constexpr int LW = 2;
+  typedef LineFFTV<N, E, LW> L;
+  typedef LineFFT<N, E, LW> B;
+  constexpr int T = L::T;
+  std::vector<float4> sm(N * LW);
+  std::vector<float4> tw4(N / 2);
+  cf* tw = reinterpret_cast<cf*>(tw4.data());
+  for (int t = 0; t < T; ++t) B::fill_twiddles(tw, t, T);
+  std::vector<std::vector<cf2>> regs(T * LW, std::vector<cf2>(E));
+  const int NL = 2 * LW;   // lines
+  std::vector<double> xr(N * NL), xi(N * NL);
+  srand(N * 7 + E);
+  for (auto& a : xr) a = rand() / (double)RAND_MAX - 0.5;
+  for (auto& a : xi) a = rand() / (double)RAND_MAX - 0.5;
+  for (int j = 0; j < T; ++j) for (int l = 0; l < LW; ++l) for (int i = 0; i < E; ++i) {
+    int n = B::n_index(j, i);
+    regs[j * LW + l][i] = mk2(mk((float)xr[n * NL + 2 * l], (float)xr[n * NL + 2 * l + 1]),
+                              mk((float)xi[n * NL + 2 * l], (float)xi[n * NL + 2 * l + 1]));
+  }
+  for (int j = 0; j < T; ++j) for (int l = 0; l < LW; ++l)
+    L::template a_front<false>(regs[j * LW + l].data(), sm.data(), tw, j, l);
+  for (int j = 0; j < T; ++j) for (int l = 0; l < LW; ++l)
+    L::template a_back<false>(regs[j * LW + l].data(), sm.data(), j, l);
+  double num = 0, den = 0;
+  for (int l = 0; l < LW; ++l) for (int c = 0; c < 2; ++c) for (int t = 0; t < T; ++t)
+    for (int r = 0; r < E; ++r) {
+      int k = B::k_index(t, r), line = 2 * l + c;
+      double sr = 0, si = 0;
+      for (int n = 0; n < N; ++n) {
+        double a = -2.0 * M_PI * ((long long)n * k % N) / N;
+        sr += xr[n * NL + line] * cos(a) - xi[n * NL + line] * sin(a);
+        si += xr[n * NL + line] * sin(a) + xi[n * NL + line] * cos(a);
+      }
+      cf2 g = regs[t * LW + l][r];
+      double gr = c ? g.re.y : g.re.x, gi = c ? g.im.y : g.im.x;
+      num += (gr - sr) * (gr - sr) + (gi - si) * (gi - si);
+      den += sr * sr + si * si;
+    }
+  double e1 = sqrt(num / den);
+  for (int j = 0; j < T; ++j) for (int l = 0; l < LW; ++l)
+    L::template b_front<true>(regs[j * LW + l].data(), sm.data(), j, l);
+  for (int j = 0; j < T; ++j) for (int l = 0; l < LW; ++l)
+    L::template b_back<true>(regs[j * LW + l].data(), sm.data(), tw, j, l);
+  num = den = 0;
+  for (int j = 0; j < T; ++j) for (int l = 0; l < LW; ++l) for (int i = 0; i < E; ++i)
+    for (int c = 0; c < 2; ++c) {
+      int n = B::n_index(j, i), line = 2 * l + c;
+      cf2 g = regs[j * LW + l][i];
+      double dr = (c ? g.re.y : g.re.x) / N - xr[n * NL + line];
+      double di = (c ? g.im.y : g.im.x) / N - xi[n * NL + line];
+      num += dr * dr + di * di;
+      den += xr[n * NL + line] * xr[n * NL + line] + xi[n * NL + line] * xi[n * NL + line];
+    }
+  double e2 = sqrt(num / den);
+  printf("V2 N=%d E=%d dft_rel_l2=%.3e roundtrip_rel_l2=%.3e\n", N, E, e1, e2);
+  return e1 > e2 ? e1 : e2;
+}
+
 int main() {
   init_tw();
   double worst = 0;
@@ -99,6 +160,10 @@ int main() {
     upd(check<256, 16, 8>(inv));   // padded exchange layout (CW = 8)
     upd(check<128, 16, 8>(inv));
   }
+  upd(check_v2<256, 16>());
+  upd(check_v2<128, 16>());
+  upd(check_v2<512, 32>());
+  upd(check_v2<64, 8>());
   printf("worst=%.3e\n", worst);
   return worst < 2e-6 ? 0 : 1;
 }
