@@ -224,7 +224,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -276,7 +276,7 @@ def main():
     for i in range(args.warmup):
         step(i)
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period=0.002)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -285,7 +285,6 @@ def main():
         step(i)
     ev1.record()
     barrier()
-    clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -325,15 +324,22 @@ def main():
     reps = max(args.steps, 20)
     ms_fwd = time_kernel(raw_fwd, reps)
     ms_adj = time_kernel(raw_adj, reps)
+    clocks = sampler.stop()   # sampled over the timed region and the per-kernel timing loops
     peak, peak_src = measured_peak()
     bytes_fwd, bytes_adj = 24 * N * N * B, 16 * N * N * B
     gbs_fwd = bytes_fwd / (ms_fwd * 1e-3) / 1e9
     gbs_adj = bytes_adj / (ms_adj * 1e-3) / 1e9
     gbs_pair = (bytes_fwd + bytes_adj) / ((ms_fwd + ms_adj) * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_dram_traffic.json')) as f:
+            traffic = json.load(f).get('bytes_per_fwd_adj_pair')
+    except Exception:
+        pass
     roofline = {
-        'bound': 'hbm', 'kernel': 'dc_strip_row_kernel<256,...> (forward+adjoint launches)',
+        'bound': 'hbm', 'kernel': 'dc_strip_pipev_kernel<256,16,16,...> (forward + adjoint launches)',
         'achieved': gbs_pair, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_pair / peak,
-        'traffic': None, 'peak_source': peak_src,
+        'traffic': traffic, 'peak_source': peak_src,
         'bytes_per_launch': {'forward': bytes_fwd, 'adjoint': bytes_adj},
         'forward': {'ms': ms_fwd, 'GBps': gbs_fwd, 'frac': gbs_fwd / peak},
         'adjoint': {'ms': ms_adj, 'GBps': gbs_adj, 'frac': gbs_adj / peak},

@@ -513,6 +513,9 @@ static int set_smem(K kernel, int bytes) {
   return CSMRI_OK;
 }
 
+__device__ unsigned g_sched[128];     // 64 x (tiles handed out, retired CTAs), zero = armed
+static unsigned g_sched_next = 0;
+static int g_use_pdl = 1;             // programmatic dependent launch for the strip kernels
 static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_set_tuning
 static int g_pf_dist = 0;        // L2 software-prefetch distance in tiles (0 = off)
 static int g_dephase = 0;        // tuning probe: random CTA start delay (cycles)
@@ -596,8 +599,21 @@ static int launch_strip_pipe_wt(const float* x, const float* residual, const flo
   const int ntiles = B * nstrips;
   int grid = sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
-  kern<<<grid, CW * L::T, S::kBytes, s>>>(tm_x, tm_a, residual, dtab, out, W, nstrips, ntiles,
-                                          g_probe_copy, g_dephase);
+  unsigned* sched = nullptr;
+  CSMRI_CUDA(cudaGetSymbolAddress((void**)&sched, g_sched));
+  sched += 2 * ((g_sched_next++) & 63);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(CW * L::T);
+  cfg.dynamicSmemBytes = S::kBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CSMRI_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_x, tm_a, residual, dtab, out, W, nstrips, ntiles,
+                                g_probe_copy, g_dephase, sched));
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }
@@ -675,9 +691,25 @@ static int launch_strip_pipev_wt(const float* x, const float* residual, const fl
   const int ntiles = B * nstrips;
   int grid = sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
-  kern<<<grid, threads, S::kBytes, s>>>(tm_x, tm_a, residual, dtab, out, W, nstrips, ntiles,
-                                        g_dephase,
-                                        g_trace ? g_trace + (size_t)((g_trace_launch++) & 1) * 1024 * 40 : nullptr);
+  // scheduler slot: a ring of 64 (tile counter, retired counter) pairs, so up
+  // to 64 launches may be in flight on different streams at once
+  unsigned* sched = nullptr;
+  CSMRI_CUDA(cudaGetSymbolAddress((void**)&sched, g_sched));
+  sched += 2 * ((g_sched_next++) & 63);
+  long long* trace =
+      g_trace ? g_trace + (size_t)((g_trace_launch++) & 1) * 1024 * 40 : nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = S::kBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CSMRI_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_x, tm_a, residual, dtab, out, W, nstrips, ntiles,
+                                g_dephase, trace, sched));
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }
@@ -729,8 +761,6 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
     case 64: return launch_strip_row_cfg<64, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 128:
       if (g_strip_variant == 0 && tma_ok(x, addend, dtab)) {
-        if (addend != nullptr)
-          return launch_strip_pipe_cfg<128, 16, 32, 2>(x, residual, dtab, addend, out, B, W, s);
         return launch_strip_pipev_cfg<128, 16, 32, 2, 3>(x, residual, dtab, addend, out, B, W, s);
       }
       if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
@@ -748,11 +778,8 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
       return launch_strip_row_cfg<128, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 256:
       if (g_strip_variant == 0 && tma_ok(x, addend, dtab)) {
-        // measured best per direction (profiles/): forward = two columns per
-        // thread, 32-column tiles, one 256-thread CTA per SM; adjoint = two
-        // columns per thread, 16-column tiles, three 128-thread CTAs per SM
-        if (addend != nullptr)
-          return launch_strip_pipev_cfg<256, 16, 32, 1, 1>(x, residual, dtab, addend, out, B, W, s);
+        // measured best (profiles/): two columns per thread, 16-column tiles,
+        // 128-thread persistent CTAs, two (forward) / three (adjoint) per SM
         return launch_strip_pipev_cfg<256, 16, 16, 2, 3>(x, residual, dtab, addend, out, B, W, s);
       }
       if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
@@ -940,6 +967,7 @@ int csmri_set_tuning(int key, int value) {
   else if (key == 1) g_pf_dist = value;
   else if (key == 2) g_probe_copy = value;
   else if (key == 3) g_dephase = value;
+  else if (key == 4) g_use_pdl = value;
   else return fail(CSMRI_E_ARG, "unknown tuning key %d", key);
   return CSMRI_OK;
 }

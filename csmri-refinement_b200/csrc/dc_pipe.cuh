@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
                          const __grid_constant__ CUtensorMap tm_add,
                          const float* __restrict__ residual, const float* __restrict__ dtab,
                          float* __restrict__ out, int W_rt, int nstrips_rt, int ntiles, int probe_copy,
-                         int dephase) {
+                         int dephase, unsigned* __restrict__ sched) {
   // WT != 0: compile-time row pitch (square slices) -> immediate store offsets
   const int W = WT ? WT : W_rt;
   const int nstrips = WT ? WT / CW : nstrips_rt;
@@ -149,15 +149,20 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
   // thread 0 gets the first tile moving before anything else; the twiddle
   // table fill and the barrier-visibility sync overlap its HBM latency
   int tile = blockIdx.x;
+  int* next_tile = reinterpret_cast<int*>(&bars[4]);   // [2], written by thread 0
   if (threadIdx.x == 0) {
     mbar_init(bar_x, 1);
     mbar_init(bar_a, 1);
     mbar_init(bar_ae, NT);
     fence_barrier_init();
-    if (tile < ntiles) {
-      issue_x(tile, 0);
-      if (ADD) issue_a(tile);
-    }
+  }
+  // programmatic dependent launch (see dc_pipev.cuh): the prologue above overlaps
+  // the previous kernel's tail, its results are visible after the wait
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0 && tile < ntiles) {
+    issue_x(tile, 0);
+    if (ADD) issue_a(tile);
   }
   L::fill_twiddles(tw_s, threadIdx.x, NT);
   __syncthreads();   // barriers initialised, twiddle table filled
@@ -173,11 +178,11 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
   }
 
   uint32_t phase = 0;
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it, phase ^= 1) {
+  // dynamic tile scheduler, see dc_pipev.cuh
+  for (int it = 0; tile < ntiles; ++it, phase ^= 1) {
     const int slot = it & 1;
     const int b = tile / nstrips, strip = tile - b * nstrips;
     const size_t gbase = (size_t)b * 2 * plane + (size_t)strip * CW + lane;
-    const int next = tile + gridDim.x;
 
     // the addend tile of the previous iteration has been read by everyone
     // (bar_ae): refill it now, it is needed again only at the end of this tile
@@ -203,15 +208,20 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
       }
     }
 
+    if (threadIdx.x == 0)
+      next_tile[slot ^ 1] = (int)atomicAdd(&sched[0], 1u) + (int)gridDim.x;
+    int next;
     if (probe_copy) {
       // tuning probe only (tools/gpu_probe.py): same loads/stores, no FFT -
       // measures what the memory pattern alone can sustain
       __syncthreads();
+      next = next_tile[slot ^ 1];
       if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
     } else {
       if (TWREG) L::template a_front_reg<false>(v, sm, twr, j, lane);
       else L::template a_front<false>(v, sm, tw_s, j, lane);
-      __syncthreads();  // exchange written; x tile consumed by every thread
+      __syncthreads();  // exchange written; x tile consumed by everyone; next_tile visible
+      next = next_tile[slot ^ 1];
       if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
 
       L::template a_back<false>(v, sm, j, lane);
@@ -240,6 +250,14 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
         st_stream_f32(pr + o, v[i].x);
         st_stream_f32(pi + o, v[i].y);
       }
+    }
+    tile = next;
+  }
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {   // last CTA out re-arms the slot
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
     }
   }
 }

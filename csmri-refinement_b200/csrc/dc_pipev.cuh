@@ -43,7 +43,7 @@ __global__ void __launch_bounds__((CW / 2) * (H / E), MINB)
                           const __grid_constant__ CUtensorMap tm_add,
                           const float* __restrict__ residual, const float* __restrict__ dtab,
                           float* __restrict__ out, int W_rt, int nstrips_rt, int ntiles, int dephase,
-                          long long* __restrict__ trace) {
+                          long long* __restrict__ trace, unsigned* __restrict__ sched) {
   const int W = WT ? WT : W_rt;
   const int nstrips = WT ? WT / CW : nstrips_rt;
   constexpr int LW = CW / 2;
@@ -92,15 +92,21 @@ __global__ void __launch_bounds__((CW / 2) * (H / E), MINB)
   // thread 0 gets the first tile moving before anything else; the twiddle
   // table fill and the barrier-visibility sync overlap its HBM latency
   int tile = blockIdx.x;
+  int* next_tile = reinterpret_cast<int*>(&bars[4]);   // [2], written by thread 0
   if (threadIdx.x == 0) {
     mbar_init(bar_x, 1);
     mbar_init(bar_a, 1);
     mbar_init(bar_ae, NT);
     fence_barrier_init();
-    if (tile < ntiles) {
-      issue_x(tile, 0);
-      if (ADD) issue_a(tile);
-    }
+  }
+  // Programmatic dependent launch: everything above overlapped the tail of the
+  // previous kernel in the stream; its results are visible after this wait, and
+  // the kernel after us may start its own prologue as our CTAs retire.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0 && tile < ntiles) {
+    issue_x(tile, 0);
+    if (ADD) issue_a(tile);
   }
   L::Base::fill_twiddles(tw_s, threadIdx.x, NT);
   __syncthreads();
@@ -128,12 +134,16 @@ __global__ void __launch_bounds__((CW / 2) * (H / E), MINB)
   };
   stamp(0);
 
+  // Tiles are handed out dynamically (one atomic per tile, taken by thread 0
+  // one tile ahead, when it issues that tile's TMA load): CTAs drift by several
+  // microseconds over a launch, and a static round-robin leaves the fast ones
+  // idle at the end.  sched[0] = tiles handed out beyond the first wave,
+  // sched[1] = retired CTAs; the last CTA to retire re-arms both.
   uint32_t phase = 0;
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it, phase ^= 1) {
+  for (int it = 0; tile < ntiles; ++it, phase ^= 1) {
     const int slot = it & 1;
     const int b = tile / nstrips, strip = tile - b * nstrips;
     const size_t gbase = (size_t)b * 2 * plane + (size_t)strip * CW + 2 * lane;
-    const int next = tile + gridDim.x;
 
     if (ADD && it > 0 && threadIdx.x == 0) {
       mbar_wait(bar_ae, phase ^ 1);
@@ -158,7 +168,10 @@ __global__ void __launch_bounds__((CW / 2) * (H / E), MINB)
     }
 
     L::template a_front<false>(v, sm, tw_s, j, lane);
-    __syncthreads();  // exchange written; x tile consumed by every thread
+    if (threadIdx.x == 0)
+      next_tile[slot ^ 1] = (int)atomicAdd(&sched[0], 1u) + (int)gridDim.x;
+    __syncthreads();  // exchange written; x tile consumed by everyone; next_tile visible
+    const int next = next_tile[slot ^ 1];
     if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
 
     L::template a_back<false>(v, sm, j, lane);
@@ -187,6 +200,14 @@ __global__ void __launch_bounds__((CW / 2) * (H / E), MINB)
       }
     }
     stamp(1 + it);
+    tile = next;
+  }
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {   // last CTA out re-arms the slot
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
+    }
   }
 }
 

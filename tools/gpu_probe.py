@@ -45,6 +45,7 @@ def time_fn(fn, reps=30):
 
 def main():
     lib = _lib.lib()
+    lib.csmri_set_tuning(4, int(os.environ.get('PROBE_PDL', '1')))
     dev = torch.device('cuda:0')
     stream = torch.cuda.current_stream().cuda_stream
     cases = [tuple(int(v) for v in c.split(':')) for c in
