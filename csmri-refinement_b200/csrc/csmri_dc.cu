@@ -426,6 +426,11 @@ static int cuda_fail(cudaError_t e, const char* what) {
     if (e_ != cudaSuccess) return cuda_fail(e_, #call);    \
   } while (0)
 
+// elements per thread (E) of the two-pass column FFT for each supported line
+// length; the dtab layout depends on it, so every strip-kernel variant of one H
+// shares it
+static int strip_radix(int H) { return H == 320 ? 40 : (H <= 64 ? 8 : (H <= 256 ? 16 : 32)); }
+
 static bool g_tw_uploaded[64] = {false};
 
 static int ensure_init() {
@@ -450,11 +455,22 @@ static int ensure_init() {
   {
     // [T][E] inter-pass tables for every supported line length (dc_core.cuh)
     static cf lines[kTwLinesTotal];
-    for (int n = 32; n <= 1024; n *= 2) {
-      const int e = n <= 64 ? 8 : (n <= 256 ? 16 : 32);
+    const int sizes[7] = {32, 64, 128, 256, 512, 1024, 320};
+    for (int si = 0; si < 7; ++si) {
+      const int n = sizes[si], e = strip_radix(n);
       for (int idx = 0; idx < n; ++idx) {
         const int jj = idx / e, k1 = idx % e;
-        lines[(n - 32) + idx] = h_twiddle[(jj * k1) * (kTwN / n)];
+        const int m = (jj * k1) % n;
+        cf w;
+        if (4 * m == n) w = mk(0.f, -1.f);
+        else if (2 * m == n) w = mk(-1.f, 0.f);
+        else if (4 * m == 3 * n) w = mk(0.f, 1.f);
+        else if (m == 0) w = mk(1.f, 0.f);
+        else {
+          const double a = -2.0 * M_PI * (double)m / (double)n;
+          w = mk((float)cos(a), (float)sin(a));
+        }
+        lines[tw_lines_offset(n) + idx] = w;
       }
     }
     CSMRI_CUDA(cudaMemcpyToSymbol(g_tw_lines, lines, sizeof(lines)));
@@ -463,17 +479,14 @@ static int ensure_init() {
   return CSMRI_OK;
 }
 
-// elements per thread (E) of the two-pass column FFT for each supported H; the
-// dtab layout depends on it, so every strip-kernel variant of one H shares it
-static int strip_radix(int H) { return H <= 64 ? 8 : (H <= 256 ? 16 : 32); }
-
 static bool pow2_in(int n, int lo, int hi) { return n >= lo && n <= hi && (n & (n - 1)) == 0; }
 
 static int check_shape(int B, int H, int W) {
   if (B <= 0) return fail(CSMRI_E_SHAPE, "batch must be positive, got %d", B);
-  if (!pow2_in(H, 32, 1024) || !pow2_in(W, 32, 1024))
+  if (!(pow2_in(H, 32, 1024) || H == 320) || !(pow2_in(W, 32, 1024) || W == 320))
     return fail(CSMRI_E_SHAPE,
-                "unsupported slice size %dx%d: H and W must be powers of two in [32, 1024]", H, W);
+                "unsupported slice size %dx%d: H and W must be powers of two in [32, 1024] or 320",
+                H, W);
   if ((long long)B * H * W * 2 >= (1LL << 40)) return fail(CSMRI_E_SHAPE, "problem too large");
   return CSMRI_OK;
 }
@@ -830,6 +843,7 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
         return launch_strip_row_cfg<512, 32, 32, 1>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
     case 1024: return launch_strip_row_cfg<1024, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
+    case 320: return launch_strip_row_cfg<320, 40, 32, 1>(x, residual, dtab, addend, out, B, W, s);
   }
   return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
 }
@@ -866,6 +880,7 @@ static int launch_strip_dense(const float* hyb, const float* k0, const float* ma
     case 256: return launch_strip_dense_cfg<256, 16, 32>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
     case 512: return launch_strip_dense_cfg<512, 32, 16>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
     case 1024: return launch_strip_dense_cfg<1024, 32, 16>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 320: return launch_strip_dense_cfg<320, 40, 32>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
   }
   return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
 }
@@ -897,6 +912,7 @@ static int launch_fft_strip(const float* in, float* out, int B, int H, int W, fl
     case 256: return launch_fft_strip_cfg<256, 16, 32>(in, out, B, W, scale, inv, rows, s);
     case 512: return launch_fft_strip_cfg<512, 32, 16>(in, out, B, W, scale, inv, rows, s);
     case 1024: return launch_fft_strip_cfg<1024, 32, 16>(in, out, B, W, scale, inv, rows, s);
+    case 320: return launch_fft_strip_cfg<320, 40, 32>(in, out, B, W, scale, inv, rows, s);
   }
   return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
 }
@@ -936,6 +952,7 @@ static int launch_fft_rows(const float* in, const float* aux, float* out, int B,
     case 256: return launch_fft_rows_cfg<256, 16, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
     case 512: return launch_fft_rows_cfg<512, 32, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
     case 1024: return launch_fft_rows_cfg<1024, 32, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
+    case 320: return launch_fft_rows_cfg<320, 40, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
   }
   return fail(CSMRI_E_SHAPE, "unsupported W=%d", W);
 }

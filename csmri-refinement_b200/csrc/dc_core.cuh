@@ -32,7 +32,8 @@ constexpr int kTwN = 1024;  // twiddle table: W_1024^m = exp(-2 pi i m/1024)
 // with coalesced 8-byte loads.  (The first version gathered them from constant
 // memory with per-thread indices: divergent, cold LDC cost ~7 us per CTA -
 // found with the per-CTA timeline probe, tools/gpu_trace.py.)
-constexpr int kTwLinesTotal = 2048 - 32;
+constexpr int kTwLinesTotal = 2048 - 32 + 320;   // ... followed by the table for N = 320
+CSMRI_HD constexpr int tw_lines_offset(int n) { return n == 320 ? 2048 - 32 : n - 32; }
 #ifdef __CUDACC__
 __constant__ cf c_twiddle[kTwN];
 __device__ cf g_tw_lines[kTwLinesTotal];
@@ -55,7 +56,6 @@ struct LineFFT {
   static constexpr int Q = E / T;  // T-point sub-FFTs per thread in pass 2
   static_assert(E * T == N, "N must equal E*T");
   static_assert(Q * T == E && Q >= 1, "T must divide E");
-  static_assert(kTwN % N == 0, "N must divide the twiddle table size");
   // exchange slot of (k1, j): (k1*TP + j)*CW + lane.  With CW = 8 a warp holds
   // four j (or t) values; one padding slot per k1 row keeps the k-layout
   // accesses (stride TP slots between consecutive t) on disjoint banks.
@@ -70,12 +70,13 @@ struct LineFFT {
   static constexpr int kTwBytes = N * (int)sizeof(cf);
   static CSMRI_HD void fill_twiddles(cf* tw_s, int tid, int nthreads) {
 #ifdef __CUDA_ARCH__
-    const cf* src = g_tw_lines + (N - 32);
+    const cf* src = g_tw_lines + tw_lines_offset(N);
     for (int idx = tid; idx < N; idx += nthreads) tw_s[idx] = __ldg(src + idx);
 #else
     for (int idx = tid; idx < N; idx += nthreads) {
       const int jj = idx / E, k1 = idx - jj * E;
-      tw_s[idx] = tw_lookup(jj * k1 * (kTwN / N));
+      const double a = -2.0 * 3.14159265358979323846 * (double)((jj * k1) % N) / (double)N;
+      tw_s[idx] = mk((float)__builtin_cos(a), (float)__builtin_sin(a));
     }
 #endif
   }

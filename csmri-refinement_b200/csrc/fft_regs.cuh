@@ -118,6 +118,10 @@ CSMRI_HD cf2 cscale(cf2 a, float s) { return mk2(f2mul(a.re, mk(s, s)), f2mul(a.
 CSMRI_HD cf2 rot_mi(cf2 a) { return mk2(a.im, f2neg(a.re)); }   // a * (-i)
 CSMRI_HD cf2 rot_pi(cf2 a) { return mk2(f2neg(a.im), a.re); }   // a * (+i)
 CSMRI_HD cf2 cneg(cf2 a) { return mk2(f2neg(a.re), f2neg(a.im)); }
+CSMRI_HD cf cmadd(cf acc, cf a, float s) { return f2fma(a, mk(s, s), acc); }
+CSMRI_HD cf2 cmadd(cf2 acc, cf2 a, float s) {
+  return mk2(f2fma(a.re, mk(s, s), acc.re), f2fma(a.im, mk(s, s), acc.im));
+}
 CSMRI_HD cf rot_mi(cf a) { return mk(a.y, -a.x); }
 CSMRI_HD cf rot_pi(cf a) { return mk(-a.y, a.x); }
 CSMRI_HD cf cneg(cf a) { return mk(-a.x, -a.y); }
@@ -202,6 +206,21 @@ CSMRI_HD void fft4(C& a0, C& a1, C& a2, C& a3) {
   else     { a1 = add_mi(t1, t3); a3 = add_pi(t1, t3); }
 }
 
+// radix-5 (320 = 2^6 * 5): 4 real constants, natural order in place
+template <bool INV, typename C>
+CSMRI_HD void fft5(C& a0, C& a1, C& a2, C& a3, C& a4) {
+  constexpr float c1 = (float)ct_cos2pi(1, 5), c2 = (float)ct_cos2pi(2, 5);
+  constexpr float s1 = (float)ct_sin2pi(1, 5), s2 = (float)ct_sin2pi(2, 5);
+  const C t1 = cadd(a1, a4), t2 = cadd(a2, a3), t3 = csub(a1, a4), t4 = csub(a2, a3);
+  const C m1 = cmadd(cmadd(a0, t1, c1), t2, c2);
+  const C m2 = cmadd(cmadd(a0, t1, c2), t2, c1);
+  const C n1 = cmadd(cscale(t3, s1), t4, s2);
+  const C n2 = cmadd(cscale(t3, s2), t4, -s1);
+  a0 = cadd(a0, cadd(t1, t2));
+  if (INV) { a1 = add_pi(m1, n1); a4 = add_mi(m1, n1); a2 = add_pi(m2, n2); a3 = add_mi(m2, n2); }
+  else     { a1 = add_mi(m1, n1); a4 = add_pi(m1, n1); a2 = add_mi(m2, n2); a3 = add_pi(m2, n2); }
+}
+
 template <int N, bool INV> struct RegFFT;
 
 template <bool INV> struct RegFFT<1, INV> {
@@ -209,6 +228,9 @@ template <bool INV> struct RegFFT<1, INV> {
 };
 template <bool INV> struct RegFFT<2, INV> {
   template <typename C> static CSMRI_HD void run(C* v) { fft2<INV>(v[0], v[1]); }
+};
+template <bool INV> struct RegFFT<5, INV> {
+  template <typename C> static CSMRI_HD void run(C* v) { fft5<INV>(v[0], v[1], v[2], v[3], v[4]); }
 };
 template <bool INV> struct RegFFT<4, INV> {
   template <typename C> static CSMRI_HD void run(C* v) { fft4<INV>(v[0], v[1], v[2], v[3]); }
@@ -263,6 +285,9 @@ template <bool INV> struct RegFFT<8, INV> {
 };
 template <bool INV> struct RegFFT<16, INV> {
   template <typename C> static CSMRI_HD void run(C* v) { RegFFT2F<16, 4, 4, INV>::run(v); }
+};
+template <bool INV> struct RegFFT<40, INV> {
+  template <typename C> static CSMRI_HD void run(C* v) { RegFFT2F<40, 8, 5, INV>::run(v); }
 };
 template <bool INV> struct RegFFT<32, INV> {
   template <typename C> static CSMRI_HD void run(C* v) { RegFFT2F<32, 4, 8, INV>::run(v); }

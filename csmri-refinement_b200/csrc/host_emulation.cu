@@ -157,6 +157,8 @@ int main() {
     upd(check<256, 32>(inv));
     upd(check<512, 32>(inv));
     upd(check<1024, 32>(inv));
+    upd(check<320, 40>(inv));      // radix-5 path
+    upd(check<320, 40, 8>(inv));
     upd(check<256, 16, 8>(inv));   // padded exchange layout (CW = 8)
     upd(check<128, 16, 8>(inv));
   }
@@ -164,6 +166,7 @@ int main() {
   upd(check_v2<128, 16>());
   upd(check_v2<512, 32>());
   upd(check_v2<64, 8>());
+  upd(check_v2<320, 40>());
   printf("worst=%.3e\n", worst);
   return worst < 2e-6 ? 0 : 1;
 }

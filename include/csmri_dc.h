@@ -16,8 +16,8 @@
  *     the legacy default stream) and never synchronise;
  *   - return value 0 = ok, negative = CSMRI_E_*; csmri_last_error() returns a
  *     thread-local message.  Unsupported sizes are an error, never a fallback;
- *   - H and W must be powers of two in [32, 1024] (H up to 512 for the strip
- *     kernels); outputs must not alias inputs unless stated.
+ *   - H and W must each be a power of two in [32, 1024] or 320 (= 2^6 * 5, radix-5
+ *     path); outputs must not alias inputs unless stated.
  */
 #ifndef CSMRI_DC_H_
 #define CSMRI_DC_H_

@@ -41,7 +41,7 @@ def test_abi_rejects_bad_arguments_without_touching_the_gpu(built_lib):
     assert lib.csmri_dc_workspace_bytes(4, 256, 256) == 4 * 2 * 256 * 256 * 4
     assert lib.csmri_dc_workspace_bytes(0, 256, 256) == 0
     # unsupported size -> CSMRI_E_SHAPE (-1), never a fallback
-    rc = lib.csmri_fft2(8, 8, 1, 320, 320, 0, 8, None)
+    rc = lib.csmri_fft2(8, 8, 1, 96, 96, 0, 8, None)
     assert rc == -1
     assert b'unsupported slice size' in lib.csmri_last_error()
     rc = lib.csmri_dc_forward_cartesian(None, None, None, None, None, 1, 256, 256, None)
