@@ -569,9 +569,11 @@ static int make_tile_map(CUtensorMap* m, const float* ptr, int B, int H, int W, 
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
-    cuuint64_t dims[4] = {(cuuint64_t)W, 256, (cuuint64_t)H / 256, (cuuint64_t)2 * B};
-    cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * 256 * 4, (cuuint64_t)W * H * 4};
-    cuuint32_t box[4] = {(cuuint32_t)CW, 256, (cuuint32_t)H / 256, 2};
+    // box dimensions are limited to 256: split the rows into equal chunks
+    const int nch = (H + 255) / 256, rows = H / nch;
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)rows, (cuuint64_t)nch, (cuuint64_t)2 * B};
+    cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * rows * 4, (cuuint64_t)W * H * 4};
+    cuuint32_t box[4] = {(cuuint32_t)CW, (cuuint32_t)rows, (cuuint32_t)nch, 2};
     cuuint32_t es[4] = {1, 1, 1, 1};
     r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -771,7 +773,10 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
                             cudaStream_t s) {
   switch (H) {
     case 32: return launch_strip_row_cfg<32, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
-    case 64: return launch_strip_row_cfg<64, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
+    case 64:
+      if (g_strip_variant == 0 && tma_ok(x, addend, dtab))
+        return launch_strip_pipev_cfg<64, 8, 32, 4, 6>(x, residual, dtab, addend, out, B, W, s);
+      return launch_strip_row_cfg<64, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 128:
       if (g_strip_variant == 0 && tma_ok(x, addend, dtab)) {
         return launch_strip_pipev_cfg<128, 16, 32, 2, 3>(x, residual, dtab, addend, out, B, W, s);
@@ -843,7 +848,10 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
         return launch_strip_row_cfg<512, 32, 32, 1>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
     case 1024: return launch_strip_row_cfg<1024, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
-    case 320: return launch_strip_row_cfg<320, 40, 32, 1>(x, residual, dtab, addend, out, B, W, s);
+    case 320:
+      if ((g_strip_variant == 0 || g_strip_variant == 10) && tma_ok(x, addend, dtab))
+        return launch_strip_pipe_cfg<320, 40, 16, 1, 2>(x, residual, dtab, addend, out, B, W, s);
+      return launch_strip_row_cfg<320, 40, 32, 1>(x, residual, dtab, addend, out, B, W, s);
   }
   return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
 }
