@@ -35,7 +35,6 @@
 #include "../../include/csmri_dc.h"
 #include "dc_core.cuh"
 #include "dc_pipe.cuh"
-#include "dc_pipe2.cuh"
 #include "dc_pipev.cuh"
 
 namespace csmri {
@@ -61,7 +60,7 @@ template <int H, int E, int CW, int MINB, int WT>
 __global__ void __launch_bounds__(CW*(H / E), MINB)
     dc_strip_row_kernel(const float* __restrict__ x, const float* __restrict__ residual,
                         const float* __restrict__ dtab, const float* __restrict__ addend,
-                        float* __restrict__ out, int W_rt, int nstrips_rt, int pf_dist) {
+                        float* __restrict__ out, int W_rt, int nstrips_rt) {
   typedef LineFFT<H, E, CW> L;
   constexpr int T = L::T;
   // WT != 0: the row pitch is a compile-time constant, so every row offset
@@ -99,19 +98,6 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
       v[i] = cadd(v[i], mk(ld_stream(pr + o), ld_stream(pi + o)));
     }
   }
-  // Software prefetch into L2 of the tile a later CTA will own (one wave
-  // ahead): its demand loads then see L2 latency instead of HBM latency.
-  if (pf_dist > 0 && (int)blockIdx.x + pf_dist < (int)gridDim.x) {
-    const int t2 = blockIdx.x + pf_dist;
-    const int b2 = t2 / nstrips, s2 = t2 - b2 * nstrips;
-    const size_t o2 = (size_t)b2 * 2 * plane + (size_t)s2 * CW;
-    for (int r = threadIdx.x; r < 2 * H; r += CW * T) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(x + o2 + (size_t)r * W));
-      if (addend != nullptr)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(addend + o2 + (size_t)r * W));
-    }
-  }
-
   __syncthreads();  // twiddle table ready (the loads above are already in flight)
   L::template a_front<false>(v, sm, tw_s, j, lane);
   __syncthreads();
@@ -530,11 +516,8 @@ __device__ unsigned g_sched[128];     // 64 x (tiles handed out, retired CTAs), 
 static unsigned g_sched_next = 0;
 static int g_use_pdl = 1;             // programmatic dependent launch for the strip kernels
 static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_set_tuning
-static int g_pf_dist = 0;        // L2 software-prefetch distance in tiles (0 = off)
-static int g_dephase = 0;        // tuning probe: random CTA start delay (cycles)
 static long long* g_trace = nullptr;  // tuning probe: per-CTA timeline buffers (2 x 1024 x 40)
 static int g_trace_launch = 0;
-static int g_probe_copy = 0;     // tuning probe: pipelined kernel moves data but skips the FFT
 
 // ---- TMA-fed persistent strip kernel -----------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -593,12 +576,12 @@ static int sm_count() {
   return n;
 }
 
-template <int H, int E, int CW, int MINB, int WT, bool ADD, bool TWREG>
+template <int H, int E, int CW, int MINB, int WT, bool ADD>
 static int launch_strip_pipe_wt(const float* x, const float* residual, const float* dtab,
                                 const float* addend, float* out, int B, int W, cudaStream_t s) {
   typedef LineFFT<H, E, CW> L;
   typedef PipeSmem<H, E, CW, ADD> S;
-  auto kern = dc_strip_pipe_kernel<H, E, CW, MINB, WT, ADD, TWREG>;
+  auto kern = dc_strip_pipe_kernel<H, E, CW, MINB, WT, ADD>;
   CSMRI_TRY(set_smem(kern, S::kBytes));
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
@@ -628,61 +611,24 @@ static int launch_strip_pipe_wt(const float* x, const float* residual, const flo
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   CSMRI_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_x, tm_a, residual, dtab, out, W, nstrips, ntiles,
-                                g_probe_copy, g_dephase, sched));
+                                sched));
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }
 
 // MINB_F / MINB_A: resident CTAs per SM asked of the compiler for the forward
 // (x + addend tiles in smem) and adjoint (x tile only) instantiations
-template <int H, int E, int CW, int MINB_F, int MINB_A = MINB_F, bool TWREG = false>
+template <int H, int E, int CW, int MINB_F, int MINB_A = MINB_F>
 static int launch_strip_pipe_cfg(const float* x, const float* residual, const float* dtab,
                                  const float* addend, float* out, int B, int W, cudaStream_t s) {
   if (addend != nullptr) {
     if (W == H)
-      return launch_strip_pipe_wt<H, E, CW, MINB_F, H, true, TWREG>(x, residual, dtab, addend, out, B, W, s);
-    return launch_strip_pipe_wt<H, E, CW, MINB_F, 0, true, TWREG>(x, residual, dtab, addend, out, B, W, s);
+      return launch_strip_pipe_wt<H, E, CW, MINB_F, H, true>(x, residual, dtab, addend, out, B, W, s);
+    return launch_strip_pipe_wt<H, E, CW, MINB_F, 0, true>(x, residual, dtab, addend, out, B, W, s);
   }
   if (W == H)
-    return launch_strip_pipe_wt<H, E, CW, MINB_A, H, false, TWREG>(x, residual, dtab, addend, out, B, W, s);
-  return launch_strip_pipe_wt<H, E, CW, MINB_A, 0, false, TWREG>(x, residual, dtab, addend, out, B, W, s);
-}
-
-template <int H, int E, int CW, int MINB, int WT, bool ADD, int XS>
-static int launch_strip_pipe2_wt(const float* x, const float* residual, const float* dtab,
-                                 const float* addend, float* out, int B, int W, cudaStream_t s) {
-  typedef LineFFT<H, E, CW> L;
-  typedef Pipe2Smem<H, E, CW, XS> S;
-  auto kern = dc_strip_pipe2_kernel<H, E, CW, MINB, WT, ADD, XS>;
-  CSMRI_TRY(set_smem(kern, S::kBytes));
-  static int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    CSMRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, CW * L::T,
-                                                             S::kBytes));
-    if (blocks_per_sm < 1) return fail(CSMRI_E_CUDA, "pipelined strip kernel does not fit an SM");
-  }
-  alignas(64) CUtensorMap tm_x;
-  CSMRI_TRY(make_tile_map(&tm_x, x, B, H, W, CW));
-  const int nstrips = W / CW;
-  const int ntiles = B * nstrips;
-  int grid = sm_count() * blocks_per_sm;
-  if (grid > ntiles) grid = ntiles;
-  kern<<<grid, CW * L::T, S::kBytes, s>>>(tm_x, addend, residual, dtab, out, W, nstrips, ntiles);
-  CSMRI_CUDA(cudaGetLastError());
-  return CSMRI_OK;
-}
-
-template <int H, int E, int CW, int MINB_F, int XS_F, int MINB_A, int XS_A>
-static int launch_strip_pipe2_cfg(const float* x, const float* residual, const float* dtab,
-                                  const float* addend, float* out, int B, int W, cudaStream_t s) {
-  if (addend != nullptr) {
-    if (W == H)
-      return launch_strip_pipe2_wt<H, E, CW, MINB_F, H, true, XS_F>(x, residual, dtab, addend, out, B, W, s);
-    return launch_strip_pipe2_wt<H, E, CW, MINB_F, 0, true, XS_F>(x, residual, dtab, addend, out, B, W, s);
-  }
-  if (W == H)
-    return launch_strip_pipe2_wt<H, E, CW, MINB_A, H, false, XS_A>(x, residual, dtab, addend, out, B, W, s);
-  return launch_strip_pipe2_wt<H, E, CW, MINB_A, 0, false, XS_A>(x, residual, dtab, addend, out, B, W, s);
+    return launch_strip_pipe_wt<H, E, CW, MINB_A, H, false>(x, residual, dtab, addend, out, B, W, s);
+  return launch_strip_pipe_wt<H, E, CW, MINB_A, 0, false>(x, residual, dtab, addend, out, B, W, s);
 }
 
 template <int H, int E, int CW, int MINB, int WT, bool ADD>
@@ -724,7 +670,7 @@ static int launch_strip_pipev_wt(const float* x, const float* residual, const fl
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   CSMRI_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_x, tm_a, residual, dtab, out, W, nstrips, ntiles,
-                                g_dephase, trace, sched));
+                                trace, sched));
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }
@@ -755,103 +701,50 @@ static int launch_strip_row_cfg(const float* x, const float* residual, const flo
   if (W == H) {  // square slices (every shipped config): compile-time row pitch
     auto kern = dc_strip_row_kernel<H, E, CW, MINB, H>;
     CSMRI_TRY(set_smem(kern, L::kSmemBytes + L::kTwBytes));
-    kern<<<B * nstrips, CW * L::T, L::kSmemBytes + L::kTwBytes, s>>>(x, residual, dtab, addend, out, W, nstrips,
-                                                       g_pf_dist);
+    kern<<<B * nstrips, CW * L::T, L::kSmemBytes + L::kTwBytes, s>>>(x, residual, dtab, addend, out, W, nstrips);
   } else {
     auto kern = dc_strip_row_kernel<H, E, CW, MINB, 0>;
     CSMRI_TRY(set_smem(kern, L::kSmemBytes + L::kTwBytes));
-    kern<<<B * nstrips, CW * L::T, L::kSmemBytes + L::kTwBytes, s>>>(x, residual, dtab, addend, out, W, nstrips,
-                                                       g_pf_dist);
+    kern<<<B * nstrips, CW * L::T, L::kSmemBytes + L::kTwBytes, s>>>(x, residual, dtab, addend, out, W, nstrips);
   }
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }
 
 
+// Kernel choice per column length H (measured, profiles/README.md):
+//   variant 0 (default)  best TMA-pipelined kernel for the size
+//   variant 1            one-column pipelined kernel (128 / 256; A/B comparison)
+//   variant 2            direct kernel (also taken whenever a pointer is not
+//                        16-byte aligned, which TMA requires)
 static int launch_strip_row(const float* x, const float* residual, const float* dtab,
                             const float* addend, float* out, int B, int H, int W,
                             cudaStream_t s) {
+  const bool tma = g_strip_variant != 2 && tma_ok(x, addend, dtab);
   switch (H) {
     case 32: return launch_strip_row_cfg<32, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 64:
-      if (g_strip_variant == 0 && tma_ok(x, addend, dtab))
-        return launch_strip_pipev_cfg<64, 8, 32, 4, 6>(x, residual, dtab, addend, out, B, W, s);
+      if (tma) return launch_strip_pipev_cfg<64, 8, 32, 4, 6>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<64, 8, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 128:
-      if (g_strip_variant == 0 && tma_ok(x, addend, dtab)) {
-        return launch_strip_pipev_cfg<128, 16, 32, 2, 3>(x, residual, dtab, addend, out, B, W, s);
-      }
-      if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
+      if (tma && g_strip_variant == 1)
         return launch_strip_pipe_cfg<128, 16, 32, 2>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 30 && tma_ok(x, addend, dtab))
-        return launch_strip_pipev_cfg<128, 16, 32, 2, 3>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 31 && tma_ok(x, addend, dtab))
-        return launch_strip_pipev_cfg<128, 16, 16, 4, 6>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 20 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe2_cfg<128, 16, 32, 2, 2, 2, 2>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 21 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe2_cfg<128, 16, 32, 3, 2, 3, 2>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 11 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe_cfg<128, 16, 16, 4>(x, residual, dtab, addend, out, B, W, s);
+      if (tma) return launch_strip_pipev_cfg<128, 16, 32, 2, 3>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<128, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 256:
-      if (g_strip_variant == 0 && tma_ok(x, addend, dtab)) {
-        // measured best (profiles/): two columns per thread, 16-column tiles,
-        // 128-thread persistent CTAs, two (forward) / three (adjoint) per SM
-        return launch_strip_pipev_cfg<256, 16, 16, 2, 3>(x, residual, dtab, addend, out, B, W, s);
-      }
-      if (g_strip_variant == 10 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe_cfg<256, 16, 16, 2>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 30 && tma_ok(x, addend, dtab))
-        return launch_strip_pipev_cfg<256, 16, 16, 2, 3>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 31 && tma_ok(x, addend, dtab))
-        return launch_strip_pipev_cfg<256, 16, 32, 1, 1>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 32 && tma_ok(x, addend, dtab))
-        return launch_strip_pipev_cfg<256, 16, 16, 2, 2>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 20 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe2_cfg<256, 16, 16, 2, 2, 2, 2>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 21 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe2_cfg<256, 16, 16, 2, 2, 3, 1>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 22 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe2_cfg<256, 16, 16, 3, 1, 3, 1>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 23 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe2_cfg<256, 16, 32, 1, 2, 1, 2>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 24 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe2_cfg<256, 16, 16, 2, 3, 2, 3>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 11 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe_cfg<256, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 12 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe_cfg<256, 16, 8, 4>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 13 && tma_ok(x, addend, dtab))
+      if (tma && g_strip_variant == 1)
         return launch_strip_pipe_cfg<256, 16, 16, 2, 3>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 14 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe_cfg<256, 16, 16, 2, 2, true>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 15 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe_cfg<256, 16, 32, 1, 1, true>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 1)
-        return launch_strip_row_cfg<256, 16, 16, 1>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 4)
-        return launch_strip_row_cfg<256, 16, 16, 4>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 5)
-        return launch_strip_row_cfg<256, 16, 8, 8>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 6)
-        return launch_strip_row_cfg<256, 16, 8, 4>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 3)
-        return launch_strip_row_cfg<256, 16, 32, 1>(x, residual, dtab, addend, out, B, W, s);
-      return launch_strip_row_cfg<256, 16, 32, 2>(x, residual, dtab, addend, out, B, W, s);
+      // two columns per thread, 16-column tiles, 128-thread persistent CTAs,
+      // two (forward) / three (adjoint) per SM
+      if (tma) return launch_strip_pipev_cfg<256, 16, 16, 2, 3>(x, residual, dtab, addend, out, B, W, s);
+      return launch_strip_row_cfg<256, 16, 16, 4>(x, residual, dtab, addend, out, B, W, s);
+    case 320:
+      if (tma) return launch_strip_pipe_cfg<320, 40, 16, 1, 2>(x, residual, dtab, addend, out, B, W, s);
+      return launch_strip_row_cfg<320, 40, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 512:
-      if ((g_strip_variant == 0 || g_strip_variant == 10) && tma_ok(x, addend, dtab))
-        return launch_strip_pipe_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 20 && tma_ok(x, addend, dtab))
-        return launch_strip_pipe2_cfg<512, 32, 16, 1, 2, 1, 2>(x, residual, dtab, addend, out, B, W, s);
-      if (g_strip_variant == 1)
-        return launch_strip_row_cfg<512, 32, 32, 1>(x, residual, dtab, addend, out, B, W, s);
+      if (tma) return launch_strip_pipe_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
     case 1024: return launch_strip_row_cfg<1024, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
-    case 320:
-      if ((g_strip_variant == 0 || g_strip_variant == 10) && tma_ok(x, addend, dtab))
-        return launch_strip_pipe_cfg<320, 40, 16, 1, 2>(x, residual, dtab, addend, out, B, W, s);
-      return launch_strip_row_cfg<320, 40, 32, 1>(x, residual, dtab, addend, out, B, W, s);
   }
   return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
 }
@@ -989,9 +882,6 @@ int csmri_set_trace(void* device_buffer) {
 }
 int csmri_set_tuning(int key, int value) {
   if (key == 0) g_strip_variant = value;
-  else if (key == 1) g_pf_dist = value;
-  else if (key == 2) g_probe_copy = value;
-  else if (key == 3) g_dephase = value;
   else if (key == 4) g_use_pdl = value;
   else return fail(CSMRI_E_ARG, "unknown tuning key %d", key);
   return CSMRI_OK;

@@ -80,16 +80,6 @@ struct LineFFT {
     }
 #endif
   }
-  // register-resident twiddle row (persistent kernels keep it across tiles)
-  static CSMRI_HD void load_twiddle_row(cf* w, const cf* tw_s, int j) {
-#pragma unroll
-    for (int k1 = 0; k1 < E; ++k1) w[k1] = tw_s[j * E + k1];
-  }
-  template <bool INV>
-  static CSMRI_HD void apply_twiddles_reg(cf* v, const cf* w) {
-#pragma unroll
-    for (int k1 = 1; k1 < E; ++k1) v[k1] = INV ? cmul_conj(v[k1], w[k1]) : cmul(v[k1], w[k1]);
-  }
   // multiply the k-layout registers of thread t by its E table entries
   static CSMRI_HD void apply_dtab(cf* u, const float* drow_t) {
     const float4* d4 = reinterpret_cast<const float4*>(drow_t);
@@ -120,20 +110,6 @@ struct LineFFT {
     apply_twiddles<INV>(v, tw_s, j);
 #pragma unroll
     for (int k1 = 0; k1 < E; ++k1) sm[(k1 * TP + j) * CW + lane] = v[k1];
-  }
-  template <bool INV>
-  static CSMRI_HD void a_front_reg(cf* v, cf* sm, const cf* w, int j, int lane) {
-    RegFFT<E, INV>::run(v);
-    apply_twiddles_reg<INV>(v, w);
-#pragma unroll
-    for (int k1 = 0; k1 < E; ++k1) sm[(k1 * TP + j) * CW + lane] = v[k1];
-  }
-  template <bool INV>
-  static CSMRI_HD void b_back_reg(cf* v, const cf* sm, const cf* w, int j, int lane) {
-#pragma unroll
-    for (int k1 = 0; k1 < E; ++k1) v[k1] = sm[(k1 * TP + j) * CW + lane];
-    apply_twiddles_reg<INV>(v, w);
-    RegFFT<E, INV>::run(v);
   }
   template <bool INV>
   static CSMRI_HD void a_back(cf* u, const cf* sm, int t, int lane) {

@@ -97,13 +97,13 @@ struct PipeSmem {
   static constexpr int kBytes = kExchBytes + (ADD ? 2 : 1) * kTileBytes + kDBytes + kTwBytes + 64;
 };
 
-template <int H, int E, int CW, int MINB, int WT, bool ADD, bool TWREG>
+template <int H, int E, int CW, int MINB, int WT, bool ADD>
 __global__ void __launch_bounds__(CW*(H / E), MINB)
     dc_strip_pipe_kernel(const __grid_constant__ CUtensorMap tm_x,
                          const __grid_constant__ CUtensorMap tm_add,
                          const float* __restrict__ residual, const float* __restrict__ dtab,
-                         float* __restrict__ out, int W_rt, int nstrips_rt, int ntiles, int probe_copy,
-                         int dephase, unsigned* __restrict__ sched) {
+                         float* __restrict__ out, int W_rt, int nstrips_rt, int ntiles,
+                         unsigned* __restrict__ sched) {
   // WT != 0: compile-time row pitch (square slices) -> immediate store offsets
   const int W = WT ? WT : W_rt;
   const int nstrips = WT ? WT / CW : nstrips_rt;
@@ -166,16 +166,6 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
   }
   L::fill_twiddles(tw_s, threadIdx.x, NT);
   __syncthreads();   // barriers initialised, twiddle table filled
-  cf twr[TWREG ? E : 1];
-  if (TWREG) L::load_twiddle_row(twr, tw_s, j);
-
-  // tuning probe: a pseudo-random start delay de-synchronises the CTAs, which
-  // otherwise all load / compute / store in lock-step across the whole chip
-  if (dephase > 0) {
-    const unsigned r = (blockIdx.x * 2654435761u) >> 22;          // 0..1023
-    const long long t0 = clock64(), d = ((long long)dephase * r) >> 10;
-    while (clock64() - t0 < d) {}
-  }
 
   uint32_t phase = 0;
   // dynamic tile scheduler, see dc_pipev.cuh
@@ -210,27 +200,16 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
 
     if (threadIdx.x == 0)
       next_tile[slot ^ 1] = (int)atomicAdd(&sched[0], 1u) + (int)gridDim.x;
-    int next;
-    if (probe_copy) {
-      // tuning probe only (tools/gpu_probe.py): same loads/stores, no FFT -
-      // measures what the memory pattern alone can sustain
-      __syncthreads();
-      next = next_tile[slot ^ 1];
-      if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
-    } else {
-      if (TWREG) L::template a_front_reg<false>(v, sm, twr, j, lane);
-      else L::template a_front<false>(v, sm, tw_s, j, lane);
-      __syncthreads();  // exchange written; x tile consumed by everyone; next_tile visible
-      next = next_tile[slot ^ 1];
-      if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
+    L::template a_front<false>(v, sm, tw_s, j, lane);
+    __syncthreads();  // exchange written; x tile consumed by everyone; next_tile visible
+    const int next = next_tile[slot ^ 1];
+    if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
 
-      L::template a_back<false>(v, sm, j, lane);
-      L::apply_dtab(v, dbuf + slot * H + j * E);
-      L::template b_front<true>(v, sm, j, lane);
-      __syncthreads();
-      if (TWREG) L::template b_back_reg<true>(v, sm, twr, j, lane);
-      else L::template b_back<true>(v, sm, tw_s, j, lane);
-    }
+    L::template a_back<false>(v, sm, j, lane);
+    L::apply_dtab(v, dbuf + slot * H + j * E);
+    L::template b_front<true>(v, sm, j, lane);
+    __syncthreads();
+    L::template b_back<true>(v, sm, tw_s, j, lane);
 
     if (ADD) {
       mbar_wait(bar_a, phase);

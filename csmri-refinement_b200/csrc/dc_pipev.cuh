@@ -42,7 +42,7 @@ __global__ void __launch_bounds__((CW / 2) * (H / E), MINB)
     dc_strip_pipev_kernel(const __grid_constant__ CUtensorMap tm_x,
                           const __grid_constant__ CUtensorMap tm_add,
                           const float* __restrict__ residual, const float* __restrict__ dtab,
-                          float* __restrict__ out, int W_rt, int nstrips_rt, int ntiles, int dephase,
+                          float* __restrict__ out, int W_rt, int nstrips_rt, int ntiles,
                           long long* __restrict__ trace, unsigned* __restrict__ sched) {
   const int W = WT ? WT : W_rt;
   const int nstrips = WT ? WT / CW : nstrips_rt;
@@ -115,14 +115,6 @@ __global__ void __launch_bounds__((CW / 2) * (H / E), MINB)
   const float2* xs_im = reinterpret_cast<const float2*>(xbuf + H * CW);
   const float2* as_re = reinterpret_cast<const float2*>(abuf);
   const float2* as_im = reinterpret_cast<const float2*>(abuf + H * CW);
-
-  // tuning probe: a pseudo-random start delay de-synchronises the CTAs, which
-  // otherwise all load / compute / store in lock-step across the whole chip
-  if (dephase > 0) {
-    const unsigned r = (blockIdx.x * 2654435761u) >> 22;          // 0..1023
-    const long long t0 = clock64(), d = ((long long)dephase * r) >> 10;
-    while (clock64() - t0 < d) {}
-  }
 
   // tuning probe: per-CTA timeline (globaltimer ns) - [0] start, [1+it] end of tile it
   auto stamp = [&](int slot_) {

@@ -341,7 +341,7 @@ def test_kernel_variants_and_unaligned_pointers_agree():
     plan = myfft.get_plan(k0d, md, 0.1)
     ref = orc.dc_perform_np(x, k0, mask, 0.1)
     try:
-        for v in (0, 1, 4, 5, 10, 11, 13, 14, 20, 21, 30, 31, 32, 99):
+        for v in (0, 1, 2):
             lib.csmri_set_tuning(0, v)
             out = ops.dc_cartesian(xd, None, plan.dtab, plan.addend)
             assert orc.rel_l2(out.cpu().numpy(), ref) < TOL, v

@@ -1,7 +1,7 @@
 """Time the strip-kernel tuning variants on the GPU box (writes gpurun_out/probe.json).
 
 PROBE_CASES="N:B,N:B"       sizes (default 256:256,512:64,128:1024)
-PROBE_LIST="v:pf,v:pf"      variant:prefetch-distance pairs for every case
+PROBE_LIST="v,v"            kernel variants (0 default, 1 one-column pipeline, 2 direct)
 PROBE_CONTEXT=0             skip the general-path / torch.fft context timings
 """
 import json
@@ -65,8 +65,6 @@ def main():
         ref_f = ref_a = None
         for v, pf, dph in [(0, 0, 0)] + plist:
             lib.csmri_set_tuning(0, v)
-            lib.csmri_set_tuning(1, pf)
-            lib.csmri_set_tuning(3, dph)
             it = [0]
 
             def fwd():
@@ -101,8 +99,6 @@ def main():
             print(json.dumps(r), flush=True)
             res.append(r)
         lib.csmri_set_tuning(0, 0)
-        lib.csmri_set_tuning(1, 0)
-        lib.csmri_set_tuning(3, 0)
         if context:
             k0, mask = batch['kspace'], batch['mask']
             tg = time_fn(lambda: ops.dc_general(xs[0], None, k0, mask, 0.0), 10)
