@@ -124,6 +124,7 @@ def recnet_train_bench(dev, rank, world, steps=8, warmup=3, batch=32, n=256, blo
     from csmri_refinement_b200 import parallel, recnet, undersampling
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True              # let cuDNN pick its fastest fp32 algorithms
     torch.manual_seed(0)                               # identical replicas on every rank
     model = recnet.construct_model({'num_blocks': blocks, 'num_convs': convs,
                                     'num_filters': filters}).to(dev)

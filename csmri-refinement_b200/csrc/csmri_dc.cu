@@ -14,7 +14,8 @@
 //                          (compressed_sensing.py:115-116), so the W-axis
 //                          transforms of FFT2 / iFFT2 cancel around the blend
 //                          and DC becomes, per image column,
-//                            out = iFFT_H(D * FFT_H(x)) + addend.
+//                            out = iFFT_H(D * FFT_H(x) + addend)
+//                          with addend = iFFT_W(c*k0) prepared once per batch.
 //                          A CTA owns an H x 32 column strip of one slice:
 //                          coalesced 128-byte row segments straight into
 //                          registers, two register-FFT passes per direction
@@ -104,20 +105,19 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
   L::template a_back<false>(v, sm, j, lane);
 
   L::apply_dtab(v, dtab + (size_t)b * H + j * E);
+  if (addend != nullptr) {   // hybrid-space k0 term, rows in k-layout order
+    const float* pr = addend + base;
+    const float* pi = pr + plane;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      const size_t o = (size_t)j * W + (size_t)L::k_index(0, r) * W;
+      v[r] = cadd(v[r], mk(ld_stream(pr + o), ld_stream(pi + o)));
+    }
+  }
 
   L::template b_front<true>(v, sm, j, lane);
   __syncthreads();
   L::template b_back<true>(v, sm, tw_s, j, lane);
-
-  if (addend != nullptr) {
-    const float* pr = addend + base;
-    const float* pi = pr + plane;
-#pragma unroll
-    for (int i = 0; i < E; ++i) {
-      const size_t o = (size_t)(j + T * i) * W;
-      v[i] = cadd(v[i], mk(ld_stream(pr + o), ld_stream(pi + o)));
-    }
-  }
   {
     float* pr = out + base;
     float* pi = pr + plane;
@@ -910,18 +910,19 @@ int csmri_dc_prepare(const float* k0, const float* mask, int B, int H, int W, fl
   }
   CSMRI_CUDA(cudaGetLastError());
   if (addend != nullptr) {
+    // addend = iFFT_W(c*k0) / sqrt(H*W): the k0 term in hybrid (k_H, w) space.  The
+    // strip kernels add it between their forward and inverse column passes, so
+    // only the row transform is left to do here.
     CSMRI_TRY(check_ptr(k0, "k0"));
-    CSMRI_TRY(check_ptr(scratch, "scratch"));
-    float* hyb = (float*)scratch;
     const float sc = 1.0f / sqrtf((float)H * (float)W);
     if (noisy) {
-      CSMRI_TRY(launch_fft_rows(k0, mask, hyb, B, H, W, 1.0f, noise_lvl / (1.0f + noise_lvl), true,
-                                2, s));
+      CSMRI_TRY(launch_fft_rows(k0, mask, addend, B, H, W, sc, noise_lvl / (1.0f + noise_lvl),
+                                true, 2, s));
     } else {
-      CSMRI_TRY(launch_fft_rows(k0, nullptr, hyb, B, H, W, 1.0f, 0.0f, true, 0, s));
+      CSMRI_TRY(launch_fft_rows(k0, nullptr, addend, B, H, W, sc, 0.0f, true, 0, s));
     }
-    CSMRI_TRY(launch_fft_strip(hyb, addend, B, H, W, sc, true, nullptr, s));
   }
+  (void)scratch;
   return CSMRI_OK;
 }
 

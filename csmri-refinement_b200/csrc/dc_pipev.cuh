@@ -168,19 +168,18 @@ __global__ void __launch_bounds__((CW / 2) * (H / E), MINB)
 
     L::template a_back<false>(v, sm, j, lane);
     L::apply_dtab(v, dbuf + slot * H + j * E);
-    L::template b_front<true>(v, sm, j, lane);
-    __syncthreads();
-    L::template b_back<true>(v, sm, tw_s, j, lane);
-
-    if (ADD) {
+    if (ADD) {   // + hybrid-space k0 term (rows of the tile in k-layout order)
       mbar_wait(bar_a, phase);
 #pragma unroll
-      for (int i = 0; i < E; ++i) {
-        const int h = j + T * i;
-        v[i] = cadd(v[i], mk2(as_re[h * LW + lane], as_im[h * LW + lane]));
+      for (int r = 0; r < E; ++r) {
+        const int k = L::Base::k_index(j, r);
+        v[r] = cadd(v[r], mk2(as_re[k * LW + lane], as_im[k * LW + lane]));
       }
       mbar_arrive(bar_ae);
     }
+    L::template b_front<true>(v, sm, j, lane);
+    __syncthreads();
+    L::template b_back<true>(v, sm, tw_s, j, lane);
     {
       float* pr = out + gbase;
       float* pi = pr + plane;

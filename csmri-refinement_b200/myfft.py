@@ -10,7 +10,8 @@ is a plain list).
 ``k0`` and ``mask`` are the same tensors for every DC layer of a cascade
 (models/recnet.py:139-151), so what depends only on them - the proof that the
 mask is row-constant (compressed_sensing.py:115-116), the per-row diagonal and
-``iFFT2(k0)`` - is computed once per batch and cached here.
+the k0 term in hybrid space ``iFFT_W(k0)`` - is computed once per batch and
+cached here.
 """
 import collections
 import contextlib

@@ -52,10 +52,9 @@ def dc_prepare(k0: torch.Tensor, mask: torch.Tensor,
         dtab = torch.empty((B, H), dtype=torch.float32, device=k0.device)
         addend = torch.empty_like(k0)
         flag = torch.empty((1,), dtype=torch.int32, device=k0.device)
-        scratch = torch.empty_like(k0)
         _lib.check(_lib.lib().csmri_dc_prepare(
             _ptr(k0), _ptr(mask), B, H, W, float(noise_lvl), _ptr(dtab), _ptr(addend),
-            _ptr(flag), _ptr(scratch), _stream()))
+            _ptr(flag), None, _stream()))
     return dtab, addend, flag
 
 
@@ -67,7 +66,7 @@ def _(k0, mask, noise_lvl):
 
 
 # ---------------------------------------------------------------------------
-# csmri::dc_cartesian - out = iFFT_H(dtab * FFT_H(x [+ residual])) [+ addend]
+# csmri::dc_cartesian - out = iFFT_H(dtab * FFT_H(x [+ residual]) [+ addend])
 # ---------------------------------------------------------------------------
 @torch.library.custom_op('csmri::dc_cartesian', mutates_args=(), device_types='cuda')
 def dc_cartesian(x: torch.Tensor, residual: Optional[torch.Tensor], dtab: torch.Tensor,
@@ -109,8 +108,11 @@ def _dc_cartesian_backward(ctx, grad):
     gx = dc_cartesian(grad, None, dtab, None) if ctx.needs_input_grad[0] or (
         ctx.has_residual and ctx.needs_input_grad[1]) else None
     g_res = gx if ctx.has_residual and ctx.needs_input_grad[1] else None
-    g_add = grad if ctx.has_addend and ctx.needs_input_grad[3] else None
-    return (gx if ctx.needs_input_grad[0] else None), g_res, None, g_add
+    if ctx.has_addend and ctx.needs_input_grad[3]:
+        # the reference never differentiates w.r.t. k0 (loader output,
+        # requires_grad=False: utils/__init__.py:75-83)
+        raise RuntimeError('gradient w.r.t. the prepared k0 term is not supported')
+    return (gx if ctx.needs_input_grad[0] else None), g_res, None, None
 
 
 dc_cartesian.register_autograd(_dc_cartesian_backward, setup_context=_dc_cartesian_setup)

@@ -53,14 +53,15 @@ size_t csmri_dc_workspace_bytes(int B, int H, int W);
  *
  *   dtab   (B,H)      out: D[b,h]/H with D = 1-m (noiseless) or (1-m)+m/(1+v),
  *                          m = mask[b,0,h,0]   (autograd of myfft.py:139,141)
- *   addend (B,2,H,W)  out: iFFT2_ortho(c*k0), c = 1 (noiseless) or m*v/(1+v)
- *                          (the k0 term of myfft.py:139,141 after Ifft2d,
- *                          myfft.py:110-117); may be NULL to skip
+ *   addend (B,2,H,W)  out: iFFT_W(c*k0)/sqrt(H*W), c = 1 (noiseless) or m*v/(1+v):
+ *                          the k0 term of myfft.py:139,141 in hybrid (k_H, w)
+ *                          space, which the strip kernel adds between its
+ *                          forward and inverse column passes; may be NULL to skip
  *   row_constant      out: device int, set to 1 iff every mask row is constant
  *                          along W and mask[:,0]==mask[:,1] (the property of
  *                          compressed_sensing.py:115-116 that the Cartesian
  *                          strip kernel relies on), else 0
- *   scratch           csmri_dc_workspace_bytes(B,H,W) bytes
+ *   scratch           unused by prepare (kept for ABI symmetry), may be NULL
  * noise_lvl <= 0 or NaN-free 0 selects the noiseless branch (`if v:`,
  * myfft.py:137-138).
  */
@@ -73,7 +74,7 @@ int csmri_dc_prepare(const float* k0, const float* mask, int B, int H, int W,
  * Fft2d.forward (:83-90) + data_consistency (:131-142) + Ifft2d.forward
  * (:110-117) + both torch.cat (:159,161), and optionally the residual add of
  * models/recnet.py:147-148 (residual may be NULL).
- *   out = iFFT_H( dtab * FFT_H(x [+ residual]) ) + addend        per column
+ *   out = iFFT_H( dtab * FFT_H(x [+ residual]) + addend )        per column
  * One kernel, one pass over HBM: reads x (+residual) and addend, writes out.
  */
 int csmri_dc_forward_cartesian(const float* x, const float* residual,
