@@ -24,7 +24,9 @@
 //   dc_strip_dense_kernel  same column pass for an arbitrary dense mask, on a
 //                          row-transformed (hybrid) tensor.
 //   fft_strip_kernel       single column DFT (prepare / fft2 / undersample).
-//   fft_rows_kernel        single row DFT, tile transposed through smem.
+//   fft_rows_kernel        single row DFT; the threads of a row sit in adjacent
+//                          lanes, so HBM <-> register traffic is coalesced without
+//                          a staging transpose.
 //   mask_rows_kernel       proves row-constancy and builds the D table.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -271,74 +273,79 @@ __global__ void __launch_bounds__(CW*(H / E))
 //   PRE: 0 none, 1 add `aux` (residual), 2 multiply by cmul*aux (aux = mask),
 //        3 real input (imaginary plane absent / zero)
 // ---------------------------------------------------------------------------
-template <int W, int E, int CW, bool INV, int PRE>
-__global__ void __launch_bounds__(CW*(W / E))
+template <int W, int E, int R, bool INV, int PRE>
+__global__ void __launch_bounds__(R*(W / E))
     fft_rows_kernel(const float* __restrict__ in, const float* __restrict__ aux,
                     float* __restrict__ out, int H, float scale, float cmulv) {
-  typedef LineFFT<W, E, CW> L;
-  constexpr int T = L::T;
-  constexpr int NT = CW * T;
-  constexpr int PITCH = W + 1;
+  // The T = W/E threads of one row sit in adjacent lanes (thread j holds
+  // x[j + T*i]), so for every i the lanes read / write consecutive floats:
+  // global traffic goes straight between HBM and registers in T*4-byte
+  // segments, no staging transpose.  R rows per CTA.  The exchange buffer is
+  // private to a row; its k1-rows are padded by one slot so that both the
+  // n-layout (consecutive j) and the k-layout (consecutive t, stride T+1
+  // slots) accesses are bank-conflict free.
+  constexpr int T = W / E;
+  constexpr int Q = E / T;
+  constexpr int TP = T + 1;
+  constexpr int NT = R * T;
+  static_assert(Q * T == E, "T must divide E");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cf* sm = reinterpret_cast<cf*>(smem_raw);               // exchange buffer
-  float* st = reinterpret_cast<float*>(smem_raw);          // staging (aliased)
-  float* st_re = st;
-  float* st_im = st + CW * PITCH;
-  constexpr int kMainBytes =
-      ((2 * CW * PITCH * 4 > L::kSmemBytes ? 2 * CW * PITCH * 4 : L::kSmemBytes) + 15) / 16 * 16;
-  cf* tw_s = reinterpret_cast<cf*>(smem_raw + kMainBytes);
-  L::fill_twiddles(tw_s, threadIdx.x, NT);
-
-  const int tiles_per_slice = H / CW;
-  const int b = blockIdx.x / tiles_per_slice;
-  const int row0 = (blockIdx.x - b * tiles_per_slice) * CW;
-  const size_t plane = (size_t)H * W;
-  const size_t in_plane = plane;
-  const size_t base_in = (PRE == 3 ? (size_t)b * in_plane : (size_t)b * 2 * in_plane) +
-                         (size_t)row0 * W;
-  const size_t base = (size_t)b * 2 * plane + (size_t)row0 * W;
-
-  for (int idx = threadIdx.x; idx < CW * W; idx += NT) {
-    const int r = idx / W, w = idx - r * W;
-    float re = ld_stream(in + base_in + idx);
-    float im = (PRE == 3) ? 0.0f : ld_stream(in + base_in + in_plane + idx);
-    if (PRE == 1) {
-      re += ld_stream(aux + base + idx);
-      im += ld_stream(aux + base + plane + idx);
-    } else if (PRE == 2) {
-      re *= cmulv * ld_stream(aux + base + idx);
-      im *= cmulv * ld_stream(aux + base + plane + idx);
+  cf* sm_all = reinterpret_cast<cf*>(smem_raw);          // [R][E*TP]
+  cf* tw_t = sm_all + R * E * TP;                        // [E][T]: W_W^{j*k1} at k1*T + j
+  {
+    const cf* src = g_tw_lines + tw_lines_offset(W);     // global table is [T][E]
+    for (int idx = threadIdx.x; idx < W; idx += NT) {
+      const int jj = idx / E, k1 = idx - jj * E;
+      tw_t[k1 * T + jj] = __ldg(src + idx);
     }
-    st_re[r * PITCH + w] = re;
-    st_im[r * PITCH + w] = im;
   }
-  __syncthreads();
+  const int j = threadIdx.x % T;
+  const int r = threadIdx.x / T;
+  cf* sm = sm_all + r * (E * TP);
 
-  const int lane = threadIdx.x % CW;  // row within the tile
-  const int j = threadIdx.x / CW;
+  const int tiles_per_slice = H / R;
+  const int b = blockIdx.x / tiles_per_slice;
+  const int row = (blockIdx.x - b * tiles_per_slice) * R + r;
+  const size_t plane = (size_t)H * W;
+  const size_t off_in = (PRE == 3 ? (size_t)b * plane : (size_t)b * 2 * plane) + (size_t)row * W + j;
+  const size_t off = (size_t)b * 2 * plane + (size_t)row * W + j;
+
   cf v[E];
 #pragma unroll
   for (int i = 0; i < E; ++i) {
-    const int w = j + T * i;
-    v[i] = mk(st_re[lane * PITCH + w], st_im[lane * PITCH + w]);
+    float re = ld_stream(in + off_in + T * i);
+    float im = (PRE == 3) ? 0.0f : ld_stream(in + off_in + plane + T * i);
+    if (PRE == 1) {
+      re += ld_stream(aux + off + T * i);
+      im += ld_stream(aux + off + plane + T * i);
+    } else if (PRE == 2) {
+      re *= cmulv * ld_stream(aux + off + T * i);
+      im *= cmulv * ld_stream(aux + off + plane + T * i);
+    }
+    v[i] = mk(re, im);
   }
-  __syncthreads();  // staging is dead (exchange may overwrite it); twiddle table ready
-  L::template a_front<INV>(v, sm, tw_s, j, lane);
-  __syncthreads();
-  L::template a_back<INV>(v, sm, j, lane);
-  __syncthreads();
-
+  RegFFT<E, INV>::run(v);
+  __syncthreads();   // twiddle table ready
 #pragma unroll
-  for (int r = 0; r < E; ++r) {
-    const int k = L::k_index(j, r);
-    st_re[lane * PITCH + k] = v[r].x * scale;
-    st_im[lane * PITCH + k] = v[r].y * scale;
+  for (int k1 = 1; k1 < E; ++k1) {
+    const cf w = tw_t[k1 * T + j];
+    v[k1] = INV ? cmul_conj(v[k1], w) : cmul(v[k1], w);
   }
+#pragma unroll
+  for (int k1 = 0; k1 < E; ++k1) sm[k1 * TP + j] = v[k1];
   __syncthreads();
-  for (int idx = threadIdx.x; idx < CW * W; idx += NT) {
-    const int r = idx / W, w = idx - r * W;
-    st_stream(out + base + idx, st_re[r * PITCH + w]);
-    st_stream(out + base + plane + idx, st_im[r * PITCH + w]);
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+#pragma unroll
+    for (int j2 = 0; j2 < T; ++j2) v[q * T + j2] = sm[(q * T + j) * TP + j2];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) RegFFT<T, INV>::run(v + q * T);
+  // thread t = j holds X[(q*T + t) + E*k2] in v[q*T + k2]: consecutive t -> consecutive k
+#pragma unroll
+  for (int rr = 0; rr < E; ++rr) {
+    const int k0i = (rr / T) * T + E * (rr % T);          // + j
+    st_stream(out + off + k0i, v[rr].x * scale);
+    st_stream(out + off + plane + k0i, v[rr].y * scale);
   }
 }
 
@@ -361,7 +368,17 @@ __global__ void mask_rows_kernel(const float* __restrict__ mask, int B, int H, i
   const float* r1 = r0 + plane;
   const float m = r0[0];
   bool ok = true;
-  for (int w = lane; w < W; w += 32) ok = ok && (r0[w] == m) && (r1[w] == m);
+  if ((((uintptr_t)r0 | (uintptr_t)r1) & 15u) == 0) {     // 128-bit loads (W % 4 == 0 always)
+    const float4* q0 = reinterpret_cast<const float4*>(r0);
+    const float4* q1 = reinterpret_cast<const float4*>(r1);
+    for (int w = lane; w < W / 4; w += 32) {
+      const float4 a = __ldcs(q0 + w), c = __ldcs(q1 + w);
+      ok = ok && a.x == m && a.y == m && a.z == m && a.w == m && c.x == m && c.y == m &&
+           c.z == m && c.w == m;
+    }
+  } else {
+    for (int w = lane; w < W; w += 32) ok = ok && (r0[w] == m) && (r1[w] == m);
+  }
   ok = __all_sync(0xffffffffu, ok);
   if (lane == 0) {
     if (!ok) atomicExch(flag, 0);
@@ -819,17 +836,16 @@ static int launch_fft_strip(const float* in, float* out, int B, int H, int W, fl
 }
 
 // ---- row launches -----------------------------------------------------------
-template <int W, int E, int CW>
+template <int W, int E, int R>
 static int launch_fft_rows_cfg(const float* in, const float* aux, float* out, int B, int H,
                                float scale, float cmulv, bool inv, int pre, cudaStream_t s) {
-  typedef LineFFT<W, E, CW> L;
-  constexpr int stage_bytes = 2 * CW * (W + 1) * (int)sizeof(float);
-  constexpr int smem =
-      ((stage_bytes > L::kSmemBytes ? stage_bytes : L::kSmemBytes) + 15) / 16 * 16 + L::kTwBytes;
-  const dim3 grid(B * (H / CW)), block(CW * L::T);
+  constexpr int T = W / E;
+  constexpr int smem = (R * E * (T + 1) + W) * (int)sizeof(cf);
+  if (H % R != 0) return fail(CSMRI_E_SHAPE, "H=%d is not a multiple of %d", H, R);
+  const dim3 grid(B * (H / R)), block(R * T);
 #define CSMRI_ROWS(I_, P_)                                              \
   {                                                                     \
-    auto kern = fft_rows_kernel<W, E, CW, I_, P_>;                      \
+    auto kern = fft_rows_kernel<W, E, R, I_, P_>;                       \
     CSMRI_TRY(set_smem(kern, smem));                                    \
     kern<<<grid, block, smem, s>>>(in, aux, out, H, scale, cmulv);      \
   }
@@ -847,13 +863,13 @@ static int launch_fft_rows_cfg(const float* in, const float* aux, float* out, in
 static int launch_fft_rows(const float* in, const float* aux, float* out, int B, int H, int W,
                            float scale, float cmulv, bool inv, int pre, cudaStream_t s) {
   switch (W) {
-    case 32: return launch_fft_rows_cfg<32, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
-    case 64: return launch_fft_rows_cfg<64, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
-    case 128: return launch_fft_rows_cfg<128, 16, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
-    case 256: return launch_fft_rows_cfg<256, 16, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
-    case 512: return launch_fft_rows_cfg<512, 32, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
-    case 1024: return launch_fft_rows_cfg<1024, 32, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
-    case 320: return launch_fft_rows_cfg<320, 40, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);
+    case 32: return launch_fft_rows_cfg<32, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);   // T=4
+    case 64: return launch_fft_rows_cfg<64, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);   // T=8
+    case 128: return launch_fft_rows_cfg<128, 16, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);  // T=8
+    case 256: return launch_fft_rows_cfg<256, 16, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s);  // T=16
+    case 512: return launch_fft_rows_cfg<512, 32, 8>(in, aux, out, B, H, scale, cmulv, inv, pre, s);   // T=16
+    case 1024: return launch_fft_rows_cfg<1024, 32, 8>(in, aux, out, B, H, scale, cmulv, inv, pre, s);  // T=32
+    case 320: return launch_fft_rows_cfg<320, 40, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s);  // T=8
   }
   return fail(CSMRI_E_SHAPE, "unsupported W=%d", W);
 }
