@@ -60,6 +60,10 @@ _SIGNATURES = {
                           [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_void_p]),
     'csmri_fft2': (ctypes.c_int, [_c_float_p, _c_float_p] + [ctypes.c_int] * 4 +
                    [ctypes.c_void_p, ctypes.c_void_p]),
+    'csmri_magnitude_clamp': (ctypes.c_int, [_c_float_p, _c_float_p] + [ctypes.c_int] * 3 +
+                              [ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
+    'csmri_psnr_sum': (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p] + [ctypes.c_int] * 3 +
+                       [ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
     # tuning knob used by bench.py only (not declared in include/csmri_dc.h)
     'csmri_set_variant': (ctypes.c_int, [ctypes.c_int]),
     'csmri_set_tuning': (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),

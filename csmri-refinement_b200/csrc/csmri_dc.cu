@@ -409,6 +409,51 @@ __global__ void expand_mask_target_kernel(const float* __restrict__ img,
 }
 
 // ---------------------------------------------------------------------------
+// reporting-side pointwise ops on the DC output
+//   magnitude_clamp : out = clamp(sqrt(re^2 + im^2), lo, hi)   utils/tensor_transforms.py:62-75
+//                     + data/reconstruction/rec_transforms.py:79-85 (output_transform)
+//   psnr_sum        : sum over all pixels of (|pred|_c - |target|_c)^2, the MSE numerator of
+//                     metrics/image_metrics.py:7-19, in one pass over both tensors
+// Squares, sum and square root are rounded separately (no FMA contraction) so
+// the magnitudes are bit-identical to torch's (a**2 + b**2) ** 0.5.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float magnitude_clamped(float re, float im, float lo, float hi) {
+  const float m = __fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+  return fminf(fmaxf(m, lo), hi);
+}
+
+__global__ void magnitude_clamp_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                       size_t plane, size_t total, float lo, float hi) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / plane, r = i - b * plane;
+    out[i] = magnitude_clamped(x[b * 2 * plane + r], x[b * 2 * plane + plane + r], lo, hi);
+  }
+}
+
+__global__ void psnr_sum_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                double* __restrict__ sum_sq, size_t plane, size_t total, float lo,
+                                float hi) {
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / plane, r = i - b * plane, o = b * 2 * plane + r;
+    const float d = magnitude_clamped(pred[o], pred[o + plane], lo, hi) -
+                    magnitude_clamped(target[o], target[o + plane], lo, hi);
+    acc += (double)d * (double)d;
+  }
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  __shared__ double part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (threadIdx.x == 0) atomicAdd(sum_sq, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -1061,6 +1106,34 @@ int csmri_fft2(const float* x, float* out, int B, int H, int W, int inverse, voi
   const float sc = 1.0f / sqrtf((float)H * (float)W);
   CSMRI_TRY(launch_fft_rows(x, nullptr, (float*)scratch, B, H, W, 1.0f, 0.0f, inverse != 0, 0, s));
   CSMRI_TRY(launch_fft_strip((const float*)scratch, out, B, H, W, sc, inverse != 0, nullptr, s));
+  return CSMRI_OK;
+}
+
+int csmri_magnitude_clamp(const float* x, float* out, int B, int H, int W, float lo, float hi,
+                          void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0) return fail(CSMRI_E_SHAPE, "bad shape %dx%dx%d", B, H, W);
+  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr(out, "out"));
+  const size_t plane = (size_t)H * W, total = plane * B;
+  const int blocks = (int)((total + 1023) / 1024 < 148 * 16 ? (total + 1023) / 1024 : 148 * 16);
+  magnitude_clamp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, plane, total, lo, hi);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+int csmri_psnr_sum(const float* pred, const float* target, double* sum_sq, int B, int H, int W,
+                   float lo, float hi, void* stream) {
+  if (B <= 0 || H <= 0 || W <= 0) return fail(CSMRI_E_SHAPE, "bad shape %dx%dx%d", B, H, W);
+  CSMRI_TRY(check_ptr(pred, "pred"));
+  CSMRI_TRY(check_ptr(target, "target"));
+  if (sum_sq == nullptr || ((uintptr_t)sum_sq & 7u) != 0)
+    return fail(CSMRI_E_ALIGN, "sum_sq must be a non-NULL 8-byte aligned device double");
+  const size_t plane = (size_t)H * W, total = plane * B;
+  const int blocks = (int)((total + 1023) / 1024 < 148 * 8 ? (total + 1023) / 1024 : 148 * 8);
+  CSMRI_CUDA(cudaMemsetAsync(sum_sq, 0, sizeof(double), (cudaStream_t)stream));
+  psnr_sum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, target, sum_sq, plane, total, lo,
+                                                           hi);
+  CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }
 

@@ -137,6 +137,21 @@ int csmri_undersample(const float* img, const unsigned char* rows, float* inp,
 int csmri_fft2(const float* x, float* out, int B, int H, int W, int inverse,
                void* scratch, void* stream);
 
+/* ---- reporting-side pointwise ops on the DC output ---------------------------
+ * csmri_magnitude_clamp replaces complex_abs (utils/tensor_transforms.py:62-75)
+ * followed by torch.clamp(., lo, hi) as in output_transform
+ * (data/reconstruction/rec_transforms.py:79-85):
+ *   x (B,2,H,W) -> out (B,1,H,W) = clamp(sqrt(re^2 + im^2), lo, hi), bit-identical
+ *   to the torch expression (separately rounded squares, sum, sqrt).
+ * csmri_psnr_sum fuses that transform of prediction and target with the squared
+ * error reduction of compute_psnr (metrics/image_metrics.py:7-19):
+ *   *sum_sq (device double) = sum over B*H*W pixels of (|pred|_c - |target|_c)^2;
+ *   PSNR = 10*log10(1 / (sum_sq / (B*H*W))).  Any H, W > 0. */
+int csmri_magnitude_clamp(const float* x, float* out, int B, int H, int W,
+                          float lo, float hi, void* stream);
+int csmri_psnr_sum(const float* pred, const float* target, double* sum_sq,
+                   int B, int H, int W, float lo, float hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

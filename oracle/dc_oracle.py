@@ -20,6 +20,9 @@ It restates, in numpy / ``torch.fft``, the arithmetic of these reference files
 * ``data/reconstruction/deep_med_lib/utils/compressed_sensing.py:515-529`` numpy DC
 * ``data/reconstruction/deep_med_lib/utils/dnn_io.py:4-22,47-61``          2-channel packing
 * ``data/reconstruction/deep_med_lib/my_pytorch/myImageTransformations.py:1215-1238`` Undersample group
+* ``data/reconstruction/deep_med_lib/my_pytorch/myImageTransformations.py:105-117,935-954`` CenterCropInKspace
+* ``utils/tensor_transforms.py:62-75``, ``data/reconstruction/rec_transforms.py:79-85``,
+  ``metrics/image_metrics.py:7-19``  complex_abs / output_transform / PSNR
 
 Parity pinning: the reference ships no golden vectors and its torch DC cannot
 run (CUDA-only ``pytorch_fft``, legacy autograd Functions).  The oracle is
@@ -192,6 +195,44 @@ def undersample_group(image, mask, rng=None):
                           to_tensor_format(mask, mask=True),
                           to_tensor_format(image)], axis=1)
     return grp.squeeze().transpose((1, 2, 0))
+
+
+def center_crop_in_kspace(img, size):
+    """myImageTransformations.CenterCropInKspace (:935-954) for one (nx,ny[,c])
+    array: centred FFT2 over axes (0,1), crop_image_at (:105-117) around
+    (nx//2, ny//2), centred inverse, magnitude."""
+    sx, sy = (size, size) if np.isscalar(size) else size
+    nx, ny = img.shape[:2]
+    ax = (0, 1)
+    k = np.fft.fftshift(np.fft.fft2(np.fft.ifftshift(img, axes=ax), norm='ortho', axes=ax), axes=ax)
+    cx, cy, r1, r2 = nx // 2, ny // 2, sx // 2, sy // 2
+    x1, x2, y1, y2 = cx - r1, cx + r1, cy - r2, cy + r2
+    x1_, x2_, y1_, y2_ = max(x1, 0), min(x2, nx), max(y1, 0), min(y2, ny)
+    crop = k[x1_:x2_, y1_:y2_]
+    crop = np.pad(crop, ((x1_ - x1, x2 - x2_), (y1_ - y1, y2 - y2_)) + ((0, 0),) * (crop.ndim - 2),
+                  'constant')
+    out = np.fft.fftshift(np.fft.ifft2(np.fft.ifftshift(crop, axes=ax), norm='ortho', axes=ax),
+                          axes=ax)
+    return abs(out)
+
+
+def complex_abs_np(x):
+    """utils/tensor_transforms.py:62-75 on a (B,2,H,W) float32 array -> (B,1,H,W),
+    with torch's operation order (separately rounded squares, sum, sqrt)."""
+    x = np.asarray(x, dtype=np.float32)
+    return np.sqrt(x[:, 0] * x[:, 0] + x[:, 1] * x[:, 1], dtype=np.float32)[:, None]
+
+
+def output_transform_np(pred, target):
+    """rec_transforms.py:79-85."""
+    return (np.clip(complex_abs_np(pred), 0.0, 1.0), np.clip(complex_abs_np(target), 0.0, 1.0))
+
+
+def psnr_np(pred, target):
+    """metrics/image_metrics.py:7-19 on output_transform(pred, target)."""
+    p, t = output_transform_np(pred, target)
+    mse = np.mean((p.astype(np.float64) - t.astype(np.float64)) ** 2)
+    return 10.0 * np.log10(1.0 / mse)
 
 
 # --------------------------------------------------------------------------

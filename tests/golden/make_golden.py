@@ -170,6 +170,22 @@ def main():
     fix['dc_noisy_0p1'] = dcn.numpy()
     np.savez_compressed(os.path.join(HERE, 'recnet_tiny.npz'), **fix)
 
+    # ---- 6. loader tail and reporting transform ---------------------------------
+    from utils.tensor_transforms import complex_abs
+    import data.reconstruction.rec_transforms as rt
+    im64 = rs.uniform(0, 1, (64, 64, 1))
+    tail = {'im64': im64,
+            'crop_same': mit.CenterCropInKspace(64)(im64.copy()),
+            'crop_32': mit.CenterCropInKspace(32)(im64.copy()),
+            'crop_pad96': mit.CenterCropInKspace(96)(im64.copy())}
+    pt = torch.from_numpy((rs.normal(size=(2, 2, 32, 32)) * 0.7).astype(np.float32))
+    tt = torch.from_numpy((rs.normal(size=(2, 2, 32, 32)) * 0.7).astype(np.float32))
+    op, ot = rt.output_transform()(pt, tt)
+    tail.update(pred=pt.numpy(), target=tt.numpy(), abs_pred=complex_abs(pt).numpy(),
+                out_pred=op.numpy(), out_target=ot.numpy(),
+                psnr=np.float64(10. * np.log10(1. / torch.nn.functional.mse_loss(op, ot).item())))
+    np.savez_compressed(os.path.join(HERE, 'loader_tail.npz'), **tail)
+
     tot = sum(os.path.getsize(os.path.join(HERE, f))
               for f in os.listdir(HERE) if f.endswith('.npz'))
     print('golden fixtures written, %d bytes' % tot)

@@ -413,3 +413,46 @@ def test_host_pipeline_matches_oracle_and_falls_back():
     assert orc.rel_l2(h_gx.numpy(), orc.dc_adjoint_np(g, mask2)) < TOL
     with pytest.raises(ValueError):
         pipe.forward_backward(torch.from_numpy(x), hk0, hm, hg, h_out, h_gx)
+
+
+def test_loader_tail_and_reporting_gpu(golden_dir):
+    """rec_transforms mirror on the GPU: k-space centre crop, max normalisation,
+    fused magnitude/clamp (bit-exact) and PSNR against the reference's outputs."""
+    from csmri_refinement_b200 import rec_transforms as rt
+    g = np.load(os.path.join(golden_dir, 'loader_tail.npz'))
+    im = torch.from_numpy(np.ascontiguousarray(g['im64'][:, :, 0]).astype(np.float32))[None].cuda()
+    same = rt.center_crop_in_kspace(im, 64)[0].cpu().numpy()
+    assert orc.rel_l2(same, g['crop_same'][:, :, 0]) < TOL
+    c32 = rt.center_crop_in_kspace(im, 32)[0].cpu().numpy()
+    assert c32.shape == (32, 32) and orc.rel_l2(c32, g['crop_32'][:, :, 0]) < TOL
+    with pytest.raises(RuntimeError, match='unsupported slice size'):
+        rt.center_crop_in_kspace(im, 96)                       # 96 is not a supported FFT size
+    nrm = rt.normalize_by_max(im * 3.0)
+    assert abs(float(nrm.max()) - 1.0) < 1e-7
+    pred, target = _cuda(g['pred'], g['target'])
+    # bit-exact against the (correctly rounded) oracle; the reference fixture came
+    # from torch's CPU sqrt, which is 1 ulp off on ~1 % of the inputs
+    ulp = dict(rtol=2.4e-7, atol=0)
+    assert np.array_equal(rt.magnitude(pred).cpu().numpy(), orc.complex_abs_np(g['pred']))
+    assert np.allclose(rt.magnitude(pred).cpu().numpy(), g['abs_pred'], **ulp)
+    p, t = rt.output_transform()(pred, target)
+    po, to = orc.output_transform_np(g['pred'], g['target'])
+    assert np.array_equal(p.cpu().numpy(), po) and np.array_equal(t.cpu().numpy(), to)
+    assert np.allclose(p.cpu().numpy(), g['out_pred'], **ulp)
+    assert abs(rt.psnr(pred, target) - float(g['psnr'])) < 1e-4
+    # the whole test-time loader tail, against the oracle chain
+    n = 64
+    imgs = np.random.RandomState(4).uniform(0, 1, (3, n, n)).astype(np.float32)
+    tr = rt.TestTransform({'sampling_scheme': 'varden', 'acceleration_factor': 4,
+                           'variable_acceleration': False}, image_size=n, num_images=3)
+    batch = tr(torch.from_numpy(imgs).cuda())
+    rng = np.random.RandomState(0)
+    masks = [orc.cartesian_mask((1, n, n), 4, 8, False, rng) for _ in range(3)]
+    for i in range(3):
+        x = orc.center_crop_in_kspace(imgs[i][:, :, None].astype(np.float64), n)
+        x = x / np.max(np.abs(x))
+        grp = orc.undersample_group(x, masks[i], rng).transpose(2, 0, 1)
+        assert np.array_equal(batch['mask'][i].cpu().numpy(), grp[4:6])
+        assert orc.rel_l2(batch['inp'][i].cpu().numpy(), grp[0:2]) < TOL
+        assert orc.rel_l2(batch['kspace'][i].cpu().numpy(), grp[2:4]) < TOL
+        assert orc.rel_l2(batch['target'][i].cpu().numpy(), grp[6:8]) < TOL
