@@ -456,3 +456,28 @@ def test_loader_tail_and_reporting_gpu(golden_dir):
         assert orc.rel_l2(batch['inp'][i].cpu().numpy(), grp[0:2]) < TOL
         assert orc.rel_l2(batch['kspace'][i].cpu().numpy(), grp[2:4]) < TOL
         assert orc.rel_l2(batch['target'][i].cpu().numpy(), grp[6:8]) < TOL
+
+
+def test_integration_md_binding_runs_as_written():
+    """The ctypes stub INTEGRATION.md shows a reference maintainer (unified
+    csmri_dc_prepare / csmri_dc_forward / csmri_dc_adjoint entry points) is
+    executed verbatim against the built library, for both mask kinds."""
+    import re
+    from csmri_refinement_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    code = re.search(r'```python\n(# data/reconstruction/.*?)```', text, re.S).group(1)
+    code = code.replace("ctypes.CDLL('libcsmri_dc.so')", 'ctypes.CDLL(%r)' % _lib.LIB_PATH)
+    ns = {}
+    exec(compile(code, 'INTEGRATION.md', 'exec'), ns)
+    for general in (False, True):
+        for noise in (None, 0.2):
+            x, k0, mask = _problem(2, 128, 128, acc=4, seed=41, general=general)
+            xd, k0d, md = _cuda(x, k0, mask)
+            xd.requires_grad_(True)
+            out = ns['DataConsistencyInKspace'](noise_lvl=noise).perform(xd, k0d, md)
+            assert orc.rel_l2(out.detach().cpu().numpy(), orc.dc_perform_np(x, k0, mask, noise)) < TOL
+            w = np.random.RandomState(8).normal(size=x.shape).astype(np.float32)
+            (wd,) = _cuda(w)
+            (out * wd).sum().backward()
+            assert orc.rel_l2(xd.grad.cpu().numpy(), orc.dc_adjoint_np(w, mask, noise)) < TOL
