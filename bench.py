@@ -390,7 +390,7 @@ def main():
     # same work through the streamed public API: chunks of 32 slices on three
     # streams (H2D / DC forward+adjoint incl. prepare / D2H), full-duplex PCIe
     from csmri_refinement_b200 import hostpipe
-    pipe = hostpipe.HostDCPipeline(dev, chunk=32, depth=3)
+    pipe = hostpipe.HostDCPipeline(dev, chunk=64, depth=3)
     for _ in range(2):
         pipe.forward_backward(hx, hk0, hm, hw, h_out, h_gx)
     barrier()
@@ -409,7 +409,7 @@ def main():
            'h2d_bytes_per_step': 4 * tensor_bytes, 'd2h_bytes_per_step': 2 * tensor_bytes,
            'steps': e2e_steps, 'ms_per_step': e2e_ms / e2e_steps,
            'api': 'hostpipe.HostDCPipeline.forward_backward: pinned host x/k0/mask/grad-seed in, '
-                  'out/grad_x back to pinned host, 32-slice chunks on 3 streams; includes the '
+                  'out/grad_x back to pinned host, 64-slice chunks on 3 streams; includes the '
                   'per-chunk prepare and the row-constancy verification read',
            'unpipelined': e2e_simple}
 
