@@ -35,6 +35,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/csmri_dc.h"
 #include "dc_core.cuh"
 #include "dc_pipe.cuh"
@@ -479,12 +482,14 @@ static int cuda_fail(cudaError_t e, const char* what) {
 // shares it
 static int strip_radix(int H) { return H == 320 ? 40 : (H <= 64 ? 8 : (H <= 256 ? 16 : 32)); }
 
+static std::mutex g_host_mutex;   // guards the lazily filled host-side tables
 static bool g_tw_uploaded[64] = {false};
 
 static int ensure_init() {
   int dev = 0;
   CSMRI_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(CSMRI_E_CUDA, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_host_mutex);
   if (g_tw_uploaded[dev]) return CSMRI_OK;
   static bool host_ready = false;
   if (!host_ready) {
@@ -566,6 +571,7 @@ static int set_smem(K kernel, int bytes) {
   int dev = 0;
   CSMRI_CUDA(cudaGetDevice(&dev));
   const void* fn = (const void*)kernel;
+  std::lock_guard<std::mutex> lock(g_host_mutex);
   for (int i = 0; i < g_smem_optin_n; ++i)
     if (g_smem_optin[i].fn == fn && g_smem_optin[i].dev == dev && g_smem_optin[i].bytes >= bytes)
       return CSMRI_OK;
@@ -575,7 +581,7 @@ static int set_smem(K kernel, int bytes) {
 }
 
 __device__ unsigned g_sched[128];     // 64 x (tiles handed out, retired CTAs), zero = armed
-static unsigned g_sched_next = 0;
+static std::atomic<unsigned> g_sched_next{0};   // launches may come from several host threads
 static int g_use_pdl = 1;             // programmatic dependent launch for the strip kernels
 static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_set_tuning
 static long long* g_trace = nullptr;  // tuning probe: per-CTA timeline buffers (2 x 1024 x 40)
@@ -661,7 +667,7 @@ static int launch_strip_pipe_wt(const float* x, const float* residual, const flo
   if (grid > ntiles) grid = ntiles;
   unsigned* sched = nullptr;
   CSMRI_CUDA(cudaGetSymbolAddress((void**)&sched, g_sched));
-  sched += 2 * ((g_sched_next++) & 63);
+  sched += 2 * (g_sched_next.fetch_add(1u) & 63u);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(CW * L::T);
@@ -718,7 +724,7 @@ static int launch_strip_pipev_wt(const float* x, const float* residual, const fl
   // to 64 launches may be in flight on different streams at once
   unsigned* sched = nullptr;
   CSMRI_CUDA(cudaGetSymbolAddress((void**)&sched, g_sched));
-  sched += 2 * ((g_sched_next++) & 63);
+  sched += 2 * (g_sched_next.fetch_add(1u) & 63u);
   long long* trace =
       g_trace ? g_trace + (size_t)((g_trace_launch++) & 1) * 1024 * 40 : nullptr;
   cudaLaunchConfig_t cfg = {};

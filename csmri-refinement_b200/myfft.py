@@ -46,7 +46,7 @@ def _tensor_key(t):
 
 
 _PLAN_CACHE = collections.OrderedDict()
-_PLAN_CACHE_SIZE = 4
+_PLAN_CACHE_SIZE = 2     # each entry pins k0, mask and the prepared k0 term of one batch
 _ASSUME_ROW_CONSTANT = None     # process-wide default, see assume_row_constant()
 
 
@@ -71,7 +71,7 @@ def get_plan(k0, mask, noise_lvl=None, assume_row_constant=None):
 
     The cache keeps the two tensors alive, so their storage cannot be handed
     to another batch while an entry exists; in-place writes bump ``_version``
-    and miss.  Entries are evicted LRU (4 batches).
+    and miss.  Entries are evicted LRU (2 batches).
     """
     v = float(noise_lvl) if noise_lvl else 0.0
     if assume_row_constant is None:
