@@ -9,25 +9,28 @@
 //   models/recnet.py:147-148                                      residual add
 //   data/reconstruction/deep_med_lib/utils/compressed_sensing.py:460-512 undersample
 //
+// The math every Cartesian kernel relies on: Cartesian masks are constant
+// along W (compressed_sensing.py:115-116), so the W-axis transforms of FFT2 /
+// iFFT2 cancel around the blend and DC becomes, per image column,
+//     out = iFFT_H(D * FFT_H(x) + addend),
+// with D (per row) and addend = iFFT_W(c*k0) prepared once per batch.
+//
 // Kernels
-//   dc_strip_row_kernel    the hot one.  Cartesian masks are constant along W
-//                          (compressed_sensing.py:115-116), so the W-axis
-//                          transforms of FFT2 / iFFT2 cancel around the blend
-//                          and DC becomes, per image column,
-//                            out = iFFT_H(D * FFT_H(x) + addend)
-//                          with addend = iFFT_W(c*k0) prepared once per batch.
-//                          A CTA owns an H x 32 column strip of one slice:
-//                          coalesced 128-byte row segments straight into
-//                          registers, two register-FFT passes per direction
-//                          with one shared-memory exchange each, blend in
-//                          registers, store.  x is read once, out written once.
-//   dc_strip_dense_kernel  same column pass for an arbitrary dense mask, on a
+//   dc_strip_pipev_kernel  (dc_pipev.cuh) the hot one: persistent, TMA-fed,
+//                          two image columns per thread, dynamic tile
+//                          scheduler, programmatic dependent launch.
+//   dc_strip_pipe_kernel   (dc_pipe.cuh) one-column twin, used for 320 / 512.
+//   dc_strip_row_kernel    direct global->register variant of the same math:
+//                          sizes without a pipelined instantiation (32, 1024)
+//                          and pointers that are not 16-byte aligned.
+//   dc_strip_dense_kernel  the column pass for an arbitrary dense mask, on a
 //                          row-transformed (hybrid) tensor.
-//   fft_strip_kernel       single column DFT (prepare / fft2 / undersample).
+//   fft_strip_kernel       single column DFT (fft2 / undersample).
 //   fft_rows_kernel        single row DFT; the threads of a row sit in adjacent
 //                          lanes, so HBM <-> register traffic is coalesced without
 //                          a staging transpose.
 //   mask_rows_kernel       proves row-constancy and builds the D table.
+//   magnitude_clamp_kernel, psnr_sum_kernel   reporting-side pointwise ops.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>

@@ -1,22 +1,29 @@
-// TMA-fed, persistent version of the Cartesian DC strip kernel (sm_100a).
+// TMA-fed, persistent version of the Cartesian DC strip kernel (sm_100a), one
+// image column per thread.  Also home of the mbarrier / TMA PTX wrappers the
+// two-column kernel (dc_pipev.cuh, the default for 64..256) shares.
 //
 // The direct kernel (dc_strip_row_kernel) stalls on global-load latency: ncu
 // shows long_scoreboard as the dominant stall with HBM at ~50 %.  Here the
 // loads are taken off the instruction stream:
 //
 //   * one elected thread issues cp.async.bulk.tensor (TMA) box loads
-//     {CW columns x H rows x 2 planes} of x and of the addend into shared
-//     memory, completion signalled on an mbarrier (complete_tx::bytes);
-//   * the CTA is persistent (grid = resident CTAs) and walks tiles
-//     tile = blockIdx.x + i*gridDim.x; the load of tile i+1 is issued as soon
-//     as tile i has been pulled into registers, so HBM latency hides behind
-//     the register FFTs of tile i;
+//     {CW columns x H rows x 2 planes} of x and of the hybrid-space k0 term
+//     ("addend") into shared memory, completion signalled on an mbarrier
+//     (complete_tx::bytes);
+//   * the CTA is persistent (grid = resident CTAs); the load of its next tile
+//     is issued as soon as the current one has been pulled into registers, so
+//     HBM latency hides behind the register FFTs;
+//   * tiles are handed out by an atomic counter one tile ahead (CTAs drift by
+//     microseconds; a static round-robin leaves the fast ones idle at the end);
 //   * the D row of the next slice rides along as a 1-D bulk copy on the same
-//     mbarrier;
+//     mbarrier; the addend buffer is released with an mbarrier arrive instead
+//     of a CTA-wide barrier;
+//   * launched with programmatic stream serialization: the barrier-init
+//     prologue overlaps the previous kernel's tail (griddepcontrol.wait);
 //   * results go straight from registers to HBM (coalesced row segments).
 //
 // Shared memory per CTA: exchange H*CW*8 + x tile H*CW*8 + addend tile
-// H*CW*8 + 2 D rows.  256^2 with CW=16: 96 KiB + 2 KiB -> two CTAs per SM.
+// H*CW*8 + 2 D rows + twiddle table.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
