@@ -481,3 +481,22 @@ def test_integration_md_binding_runs_as_written():
             (wd,) = _cuda(w)
             (out * wd).sum().backward()
             assert orc.rel_l2(xd.grad.cpu().numpy(), orc.dc_adjoint_np(w, mask, noise)) < TOL
+
+
+def test_single_slice_and_second_device():
+    """B=1 (fewer tiles than resident CTAs) and, when the box has one, a
+    non-default device (per-device twiddle upload, scheduler slots, stream)."""
+    myfft, _, _, _ = _mods()
+    x, k0, mask = _problem(1, 256, 256, acc=8, seed=77)
+    ref = orc.dc_perform_np(x, k0, mask)
+    devices = ['cuda:0'] + (['cuda:1'] if torch.cuda.device_count() > 1 else [])
+    for d in devices:
+        xd, k0d, md = (torch.from_numpy(a).to(d) for a in (x, k0, mask))
+        xd.requires_grad_(True)
+        with torch.cuda.stream(torch.cuda.Stream(d)):
+            out = myfft.DataConsistencyInKspace().perform(xd, k0d, md)
+            (g,) = torch.autograd.grad(out.sum(), xd)
+        torch.cuda.synchronize(d)
+        assert out.device == xd.device
+        assert orc.rel_l2(out.detach().cpu().numpy(), ref) < TOL, d
+        assert orc.rel_l2(g.cpu().numpy(), orc.dc_adjoint_np(np.ones_like(x), mask)) < TOL, d
