@@ -815,7 +815,9 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
     case 512:
       if (tma) return launch_strip_pipe_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
-    case 1024: return launch_strip_row_cfg<1024, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
+    case 1024:
+      if (tma) return launch_strip_pipe_cfg<1024, 32, 8, 1>(x, residual, dtab, addend, out, B, W, s);
+      return launch_strip_row_cfg<1024, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
   }
   return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
 }
