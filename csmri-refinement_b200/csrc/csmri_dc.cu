@@ -143,13 +143,15 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
 //   ADJ = false: Y = blend(s*K, k0, mask)  (myfft.py:139 / :141 as written)
 //   ADJ = true : Y = D * s*K, D = (1-m) or (1-m)+m/(1+v)
 // ---------------------------------------------------------------------------
-template <int H, int E, int CW, bool NOISY, bool ADJ>
-__global__ void __launch_bounds__(CW*(H / E))
+template <int H, int E, int CW, bool NOISY, bool ADJ, int WT, int MINB>
+__global__ void __launch_bounds__(CW*(H / E), MINB)
     dc_strip_dense_kernel(const float* __restrict__ hyb, const float* __restrict__ k0,
-                          const float* __restrict__ mask, float* __restrict__ out, int W,
-                          int nstrips, float s, float nv) {
+                          const float* __restrict__ mask, float* __restrict__ out, int W_rt,
+                          int nstrips_rt, float s, float nv) {
   typedef LineFFT<H, E, CW> L;
   constexpr int T = L::T;
+  const int W = WT ? WT : W_rt;                 // compile-time pitch for square slices
+  const int nstrips = WT ? WT / CW : nstrips_rt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf* sm = reinterpret_cast<cf*>(smem_raw);
   cf* tw_s = reinterpret_cast<cf*>(smem_raw + L::kSmemBytes);
@@ -224,12 +226,14 @@ __global__ void __launch_bounds__(CW*(H / E))
 //   rows  : optional (B,H) uint8 multiplier on OUTPUT rows (undersample mask)
 //   out2  : optional second destination for the same values
 // ---------------------------------------------------------------------------
-template <int H, int E, int CW, bool INV>
-__global__ void __launch_bounds__(CW*(H / E))
-    fft_strip_kernel(const float* __restrict__ in, float* __restrict__ out, int W, int nstrips,
-                     float scale, const unsigned char* __restrict__ rows) {
+template <int H, int E, int CW, bool INV, int WT, int MINB>
+__global__ void __launch_bounds__(CW*(H / E), MINB)
+    fft_strip_kernel(const float* __restrict__ in, float* __restrict__ out, int W_rt,
+                     int nstrips_rt, float scale, const unsigned char* __restrict__ rows) {
   typedef LineFFT<H, E, CW> L;
   constexpr int T = L::T;
+  const int W = WT ? WT : W_rt;
+  const int nstrips = WT ? WT / CW : nstrips_rt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cf* sm = reinterpret_cast<cf*>(smem_raw);
   cf* tw_s = reinterpret_cast<cf*>(smem_raw + L::kSmemBytes);
@@ -822,23 +826,31 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
   return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
 }
 
-template <int H, int E, int CW>
+template <int H, int E, int CW, int MINB>
 static int launch_strip_dense_cfg(const float* hyb, const float* k0, const float* mask, float* out,
                                   int B, int W, float sc, float nv, bool noisy, bool adj,
                                   cudaStream_t s) {
   typedef LineFFT<H, E, CW> L;
   const int nstrips = W / CW;
   const dim3 grid(B * nstrips), block(CW * L::T);
-#define CSMRI_DENSE(N_, A_)                                                           \
+  constexpr int smem = L::kSmemBytes + L::kTwBytes;
+#define CSMRI_DENSE(N_, A_, WT_)                                                      \
   {                                                                                   \
-    auto kern = dc_strip_dense_kernel<H, E, CW, N_, A_>;                              \
-    CSMRI_TRY(set_smem(kern, L::kSmemBytes + L::kTwBytes));                                         \
-    kern<<<grid, block, L::kSmemBytes + L::kTwBytes, s>>>(hyb, k0, mask, out, W, nstrips, sc, nv); \
+    auto kern = dc_strip_dense_kernel<H, E, CW, N_, A_, WT_, MINB>;                   \
+    CSMRI_TRY(set_smem(kern, smem));                                                  \
+    kern<<<grid, block, smem, s>>>(hyb, k0, mask, out, W, nstrips, sc, nv);           \
   }
-  if (noisy && adj) CSMRI_DENSE(true, true)
-  else if (noisy) CSMRI_DENSE(true, false)
-  else if (adj) CSMRI_DENSE(false, true)
-  else CSMRI_DENSE(false, false)
+  if (W == H) {
+    if (noisy && adj) CSMRI_DENSE(true, true, H)
+    else if (noisy) CSMRI_DENSE(true, false, H)
+    else if (adj) CSMRI_DENSE(false, true, H)
+    else CSMRI_DENSE(false, false, H)
+  } else {
+    if (noisy && adj) CSMRI_DENSE(true, true, 0)
+    else if (noisy) CSMRI_DENSE(true, false, 0)
+    else if (adj) CSMRI_DENSE(false, true, 0)
+    else CSMRI_DENSE(false, false, 0)
+  }
 #undef CSMRI_DENSE
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
@@ -848,31 +860,35 @@ static int launch_strip_dense(const float* hyb, const float* k0, const float* ma
                               int B, int H, int W, float sc, float nv, bool noisy, bool adj,
                               cudaStream_t s) {
   switch (H) {
-    case 32: return launch_strip_dense_cfg<32, 8, 32>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
-    case 64: return launch_strip_dense_cfg<64, 8, 32>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
-    case 128: return launch_strip_dense_cfg<128, 16, 32>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
-    case 256: return launch_strip_dense_cfg<256, 16, 32>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
-    case 512: return launch_strip_dense_cfg<512, 32, 16>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
-    case 1024: return launch_strip_dense_cfg<1024, 32, 16>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
-    case 320: return launch_strip_dense_cfg<320, 40, 32>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 32: return launch_strip_dense_cfg<32, 8, 32, 1>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 64: return launch_strip_dense_cfg<64, 8, 32, 1>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 128: return launch_strip_dense_cfg<128, 16, 32, 2>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 256: return launch_strip_dense_cfg<256, 16, 16, 3>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 512: return launch_strip_dense_cfg<512, 32, 16, 1>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 1024: return launch_strip_dense_cfg<1024, 32, 16, 1>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
+    case 320: return launch_strip_dense_cfg<320, 40, 32, 1>(hyb, k0, mask, out, B, W, sc, nv, noisy, adj, s);
   }
   return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
 }
 
-template <int H, int E, int CW>
+template <int H, int E, int CW, int MINB>
 static int launch_fft_strip_cfg(const float* in, float* out, int B, int W, float scale, bool inv,
                                 const unsigned char* rows, cudaStream_t s) {
   typedef LineFFT<H, E, CW> L;
   const int nstrips = W / CW;
-  if (inv) {
-    auto kern = fft_strip_kernel<H, E, CW, true>;
-    CSMRI_TRY(set_smem(kern, L::kSmemBytes + L::kTwBytes));
-    kern<<<B * nstrips, CW * L::T, L::kSmemBytes + L::kTwBytes, s>>>(in, out, W, nstrips, scale, rows);
-  } else {
-    auto kern = fft_strip_kernel<H, E, CW, false>;
-    CSMRI_TRY(set_smem(kern, L::kSmemBytes + L::kTwBytes));
-    kern<<<B * nstrips, CW * L::T, L::kSmemBytes + L::kTwBytes, s>>>(in, out, W, nstrips, scale, rows);
+  constexpr int smem = L::kSmemBytes + L::kTwBytes;
+#define CSMRI_FSTRIP(I_, WT_)                                                                \
+  {                                                                                          \
+    auto kern = fft_strip_kernel<H, E, CW, I_, WT_, MINB>;                                   \
+    CSMRI_TRY(set_smem(kern, smem));                                                         \
+    kern<<<B * nstrips, CW * L::T, smem, s>>>(in, out, W, nstrips, scale, rows);             \
   }
+  if (W == H) {
+    if (inv) CSMRI_FSTRIP(true, H) else CSMRI_FSTRIP(false, H)
+  } else {
+    if (inv) CSMRI_FSTRIP(true, 0) else CSMRI_FSTRIP(false, 0)
+  }
+#undef CSMRI_FSTRIP
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }
@@ -880,13 +896,13 @@ static int launch_fft_strip_cfg(const float* in, float* out, int B, int W, float
 static int launch_fft_strip(const float* in, float* out, int B, int H, int W, float scale, bool inv,
                             const unsigned char* rows, cudaStream_t s) {
   switch (H) {
-    case 32: return launch_fft_strip_cfg<32, 8, 32>(in, out, B, W, scale, inv, rows, s);
-    case 64: return launch_fft_strip_cfg<64, 8, 32>(in, out, B, W, scale, inv, rows, s);
-    case 128: return launch_fft_strip_cfg<128, 16, 32>(in, out, B, W, scale, inv, rows, s);
-    case 256: return launch_fft_strip_cfg<256, 16, 32>(in, out, B, W, scale, inv, rows, s);
-    case 512: return launch_fft_strip_cfg<512, 32, 16>(in, out, B, W, scale, inv, rows, s);
-    case 1024: return launch_fft_strip_cfg<1024, 32, 16>(in, out, B, W, scale, inv, rows, s);
-    case 320: return launch_fft_strip_cfg<320, 40, 32>(in, out, B, W, scale, inv, rows, s);
+    case 32: return launch_fft_strip_cfg<32, 8, 32, 1>(in, out, B, W, scale, inv, rows, s);
+    case 64: return launch_fft_strip_cfg<64, 8, 32, 1>(in, out, B, W, scale, inv, rows, s);
+    case 128: return launch_fft_strip_cfg<128, 16, 32, 2>(in, out, B, W, scale, inv, rows, s);
+    case 256: return launch_fft_strip_cfg<256, 16, 16, 4>(in, out, B, W, scale, inv, rows, s);
+    case 512: return launch_fft_strip_cfg<512, 32, 16, 1>(in, out, B, W, scale, inv, rows, s);
+    case 1024: return launch_fft_strip_cfg<1024, 32, 16, 1>(in, out, B, W, scale, inv, rows, s);
+    case 320: return launch_fft_strip_cfg<320, 40, 32, 1>(in, out, B, W, scale, inv, rows, s);
   }
   return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
 }
