@@ -500,3 +500,20 @@ def test_single_slice_and_second_device():
         assert out.device == xd.device
         assert orc.rel_l2(out.detach().cpu().numpy(), ref) < TOL, d
         assert orc.rel_l2(g.cpu().numpy(), orc.dc_adjoint_np(np.ones_like(x), mask)) < TOL, d
+
+
+def test_custom_op_registration_opcheck():
+    """torch.library.opcheck: schema, fake-tensor (meta) kernels and autograd
+    registration of the csmri:: ops are consistent (SURVEY 8b 'Registration')."""
+    myfft, ops, _, _ = _mods()
+    x, k0, mask = _problem(2, 64, 64, seed=51)
+    xd, k0d, md = _cuda(x, k0, mask)
+    dtab, addend, flag = ops.dc_prepare(k0d, md, 0.0)
+    tests = ('test_schema', 'test_faketensor', 'test_autograd_registration')
+    torch.library.opcheck(ops.dc_prepare, (k0d, md, 0.0), test_utils=tests[:2])
+    torch.library.opcheck(ops.dc_cartesian, (xd.clone().requires_grad_(True), None, dtab, addend),
+                          test_utils=tests)
+    torch.library.opcheck(ops.dc_cartesian, (xd, xd.clone(), dtab, None), test_utils=tests[:2])
+    torch.library.opcheck(ops.dc_general, (xd.clone().requires_grad_(True), None, k0d, md, 0.1),
+                          test_utils=tests)
+    torch.library.opcheck(ops.dc_general_adjoint, (xd, md, 0.1), test_utils=tests[:2])
