@@ -57,6 +57,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -162,8 +165,11 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
     mbar_init(bar_a, 1);
     mbar_init(bar_ae, NT);
     fence_barrier_init();
+    prefetch_tensormap(&tm_x);
+    if (ADD) prefetch_tensormap(&tm_add);
   }
-  // programmatic dependent launch (see dc_pipev.cuh): the prologue above overlaps
+  L::fill_twiddles(tw_s, threadIdx.x, NT);   // immutable table: safe before the wait
+  // programmatic dependent launch (see dc_pipev.cuh): everything above overlaps
   // the previous kernel's tail, its results are visible after the wait
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -171,7 +177,6 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
     issue_x(tile, 0);
     if (ADD) issue_a(tile);
   }
-  L::fill_twiddles(tw_s, threadIdx.x, NT);
   __syncthreads();   // barriers initialised, twiddle table filled
 
   uint32_t phase = 0;

@@ -98,7 +98,10 @@ __global__ void __launch_bounds__((CW / 2) * (H / E), MINB)
     mbar_init(bar_a, 1);
     mbar_init(bar_ae, NT);
     fence_barrier_init();
+    prefetch_tensormap(&tm_x);
+    if (ADD) prefetch_tensormap(&tm_add);
   }
+  L::Base::fill_twiddles(tw_s, threadIdx.x, NT);   // immutable table: safe before the wait
   // Programmatic dependent launch: everything above overlapped the tail of the
   // previous kernel in the stream; its results are visible after this wait, and
   // the kernel after us may start its own prologue as our CTAs retire.
@@ -108,7 +111,6 @@ __global__ void __launch_bounds__((CW / 2) * (H / E), MINB)
     issue_x(tile, 0);
     if (ADD) issue_a(tile);
   }
-  L::Base::fill_twiddles(tw_s, threadIdx.x, NT);
   __syncthreads();
 
   const float2* xs_re = reinterpret_cast<const float2*>(xbuf);
