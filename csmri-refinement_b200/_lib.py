@@ -56,7 +56,7 @@ _SIGNATURES = {
                          [ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     'csmri_dc_adjoint': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 3 +
                          [ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
-    'csmri_undersample': (ctypes.c_int, [_c_float_p, ctypes.c_void_p] + [_c_float_p] * 4 +
+    'csmri_undersample': (ctypes.c_int, [_c_float_p, ctypes.c_void_p] + [_c_float_p] * 6 +
                           [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_void_p]),
     'csmri_fft2': (ctypes.c_int, [_c_float_p, _c_float_p] + [ctypes.c_int] * 4 +
                    [ctypes.c_void_p, ctypes.c_void_p]),

@@ -399,6 +399,18 @@ __global__ void mask_rows_kernel(const float* __restrict__ mask, int B, int H, i
   }
 }
 
+// D table (noiseless: D = 1 - m) straight from the sampled-line table, in the
+// strip kernels' slot order - what mask_rows_kernel derives from a dense mask
+__global__ void dtab_from_rows_kernel(const unsigned char* __restrict__ rows, int B, int H, int E,
+                                      float* __restrict__ dtab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, h = i - b * H, T = H / E;
+  const int k1 = h % E, k2 = h / E;
+  const float m = rows[i] ? 1.0f : 0.0f;
+  dtab[(size_t)b * H + (k1 % T) * E + (k1 / T) * T + k2] = (1.0f - m) / (float)H;
+}
+
 // real image + row table -> dense 2-channel mask and (img, 0) target
 __global__ void expand_mask_target_kernel(const float* __restrict__ img,
                                           const unsigned char* __restrict__ rows,
@@ -1097,8 +1109,8 @@ int csmri_dc_adjoint(const float* grad_out, const float* mask, const float* dtab
 }
 
 int csmri_undersample(const float* img, const unsigned char* rows, float* inp, float* kspace,
-                      float* mask, float* target, int B, int H, int W, void* scratch,
-                      void* stream) {
+                      float* mask, float* target, float* dtab, float* addend, int B, int H, int W,
+                      void* scratch, void* stream) {
   CSMRI_TRY(check_shape(B, H, W));
   CSMRI_TRY(check_ptr(img, "img"));
   if (rows == nullptr) return fail(CSMRI_E_NULLPTR, "rows is NULL");
@@ -1109,15 +1121,27 @@ int csmri_undersample(const float* img, const unsigned char* rows, float* inp, f
   CSMRI_TRY(check_ptr(scratch, "scratch"));
   CSMRI_TRY(ensure_init());
   cudaStream_t s = (cudaStream_t)stream;
+  if ((dtab == nullptr) != (addend == nullptr))
+    return fail(CSMRI_E_ARG, "dtab and addend must be given together");
+  if (dtab != nullptr) {
+    CSMRI_TRY(check_ptr(dtab, "dtab"));
+    CSMRI_TRY(check_ptr(addend, "addend"));
+  }
   float* hyb = (float*)scratch;
   const float sc = 1.0f / sqrtf((float)H * (float)W);
   // x_f = fft2(x, ortho); x_fu = mask * x_f          (compressed_sensing.py:509-510)
   CSMRI_TRY(launch_fft_rows(img, nullptr, hyb, B, H, W, 1.0f, 0.0f, false, 3, s));
   CSMRI_TRY(launch_fft_strip(hyb, kspace, B, H, W, sc, false, rows, s));
   // x_u = ifft2(x_fu, ortho)                         (compressed_sensing.py:511)
-  CSMRI_TRY(launch_fft_rows(kspace, nullptr, hyb, B, H, W, 1.0f, 0.0f, true, 0, s));
-  CSMRI_TRY(launch_fft_strip(hyb, inp, B, H, W, sc, true, nullptr, s));
+  // The row-inverse of x_fu, scaled by 1/sqrt(HW), is exactly the hybrid-space k0
+  // term the DC strip kernels add (csmri_dc_prepare's `addend`): when the caller
+  // wants the DC plan it is written there instead of into scratch, for free.
+  float* mid = addend != nullptr ? addend : hyb;
+  CSMRI_TRY(launch_fft_rows(kspace, nullptr, mid, B, H, W, sc, 0.0f, true, 0, s));
+  CSMRI_TRY(launch_fft_strip(mid, inp, B, H, W, 1.0f, true, nullptr, s));
   expand_mask_target_kernel<<<148 * 8, 256, 0, s>>>(img, rows, mask, target, B, H, W);
+  if (dtab != nullptr)
+    dtab_from_rows_kernel<<<(B * H + 255) / 256, 256, 0, s>>>(rows, B, H, strip_radix(H), dtab);
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }

@@ -26,9 +26,16 @@ class DCPlan(object):
 
     __slots__ = ('k0', 'mask', 'noise_lvl', 'dtab', 'addend', 'row_constant', 'key')
 
-    def __init__(self, k0, mask, noise_lvl, assume_row_constant=None):
+    def __init__(self, k0, mask, noise_lvl, assume_row_constant=None, prepared=None):
         v = float(noise_lvl) if noise_lvl else 0.0   # `if v:` of myfft.py:137
         self.k0, self.mask, self.noise_lvl = k0, mask, v
+        if prepared is not None:
+            # handed over by the loader (undersampling.undersample): the mask is
+            # row-constant by construction and (dtab, addend) already exist
+            self.dtab, self.addend = prepared
+            self.row_constant = True
+            self.key = None
+            return
         dtab, addend, flag = ops.dc_prepare(k0.detach(), mask.detach(), v)
         self.dtab, self.addend = dtab, addend
         if assume_row_constant is None:
@@ -46,7 +53,7 @@ def _tensor_key(t):
 
 
 _PLAN_CACHE = collections.OrderedDict()
-_PLAN_CACHE_SIZE = 2     # each entry pins k0, mask and the prepared k0 term of one batch
+_PLAN_CACHE_SIZE = 4     # keys; an entry pins k0, mask and the prepared k0 term of one batch
 _ASSUME_ROW_CONSTANT = None     # process-wide default, see assume_row_constant()
 
 
@@ -71,7 +78,7 @@ def get_plan(k0, mask, noise_lvl=None, assume_row_constant=None):
 
     The cache keeps the two tensors alive, so their storage cannot be handed
     to another batch while an entry exists; in-place writes bump ``_version``
-    and miss.  Entries are evicted LRU (2 batches).
+    and miss.  Entries are evicted LRU (4 keys = 2-4 batches).
     """
     v = float(noise_lvl) if noise_lvl else 0.0
     if assume_row_constant is None:
@@ -84,6 +91,21 @@ def get_plan(k0, mask, noise_lvl=None, assume_row_constant=None):
     plan = DCPlan(k0, mask, v, assume_row_constant)
     plan.key = key
     _PLAN_CACHE[key] = plan
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def register_plan(k0, mask, dtab, addend):
+    """Install a noiseless plan the loader produced as a by-product
+    (``ops.undersample(..., with_plan=True)``): the first DC layer then needs no
+    prepare pass and no device->host read for this batch."""
+    plan = DCPlan(k0, mask, 0.0, prepared=(dtab, addend))
+    for arc in (None, True):
+        key = (_tensor_key(k0), _tensor_key(mask), 0.0, arc)
+        _PLAN_CACHE[key] = plan
+        _PLAN_CACHE.move_to_end(key)
+    plan.key = key
     while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
         _PLAN_CACHE.popitem(last=False)
     return plan

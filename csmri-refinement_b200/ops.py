@@ -217,10 +217,12 @@ def fft2_planar(x: torch.Tensor, inverse: bool = False) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # undersampling (cs.undersample + to_tensor_format, compressed_sensing.py:460-512)
 # ---------------------------------------------------------------------------
-def undersample(img: torch.Tensor, rows: torch.Tensor):
+def undersample(img: torch.Tensor, rows: torch.Tensor, with_plan: bool = False):
     """img (B,H,W) float32 CUDA, rows (B,H) uint8 CUDA (1 = sampled line)
     -> dict(inp, kspace, mask, target), each (B,2,H,W) float32
-    (the batch dict of scar_segmentation.py:212-218)."""
+    (the batch dict of scar_segmentation.py:212-218).  With ``with_plan`` also
+    returns (dtab, addend): the noiseless DC plan of (kspace, mask), a by-product
+    of the same kernels."""
     if img.dim() != 3 or img.dtype != torch.float32 or not img.is_cuda:
         raise ValueError('img must be a float32 CUDA tensor of shape (B,H,W)')
     B, H, W = img.shape
@@ -231,7 +233,12 @@ def undersample(img: torch.Tensor, rows: torch.Tensor):
         outs = [torch.empty((B, 2, H, W), dtype=torch.float32, device=img.device)
                 for _ in range(5)]
         inp, kspace, mask, target, scratch = outs
+        dtab = torch.empty((B, H), dtype=torch.float32, device=img.device) if with_plan else None
+        addend = scratch if with_plan else None      # doubles as the intermediate
         _lib.check(_lib.lib().csmri_undersample(
-            _ptr(img), _ptr(rows), _ptr(inp), _ptr(kspace), _ptr(mask), _ptr(target), B, H, W,
-            _ptr(scratch), _stream()))
-    return {'inp': inp, 'kspace': kspace, 'mask': mask, 'target': target}
+            _ptr(img), _ptr(rows), _ptr(inp), _ptr(kspace), _ptr(mask), _ptr(target),
+            _ptr(dtab), _ptr(addend), B, H, W, _ptr(scratch), _stream()))
+    batch = {'inp': inp, 'kspace': kspace, 'mask': mask, 'target': target}
+    if with_plan:
+        return batch, (dtab, addend)
+    return batch

@@ -72,14 +72,24 @@ def consume_noise_draws(rng, shape):
     rng.normal(0, 1, shape)
 
 
-def undersample(img, rows):
+def undersample(img, rows, register_dc_plan=True):
     """GPU ``cs.undersample`` + tensor formatting.  ``img`` (B,H,W) float32
     CUDA; ``rows`` (B,H) uint8 (numpy or tensor).  Returns the batch dict
-    ``{inp, kspace, mask, target}`` of scar_segmentation.py:212-218."""
+    ``{inp, kspace, mask, target}`` of scar_segmentation.py:212-218.
+
+    With ``register_dc_plan`` the per-batch constants of the (noiseless) DC
+    layers - which fall out of the same kernels - are registered with
+    :mod:`myfft`, so ``RecNet.forward`` on this batch runs without a prepare
+    pass and without any host synchronisation."""
     if isinstance(rows, np.ndarray):
         rows = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.uint8))
     rows = rows.to(device=img.device, dtype=torch.uint8, non_blocking=True)
-    return ops.undersample(img, rows)
+    if not register_dc_plan:
+        return ops.undersample(img, rows)
+    from . import myfft
+    batch, (dtab, addend) = ops.undersample(img, rows, with_plan=True)
+    myfft.register_plan(batch['kspace'], batch['mask'], dtab, addend)
+    return batch
 
 
 class Undersample(object):

@@ -126,10 +126,16 @@ int csmri_dc_adjoint(const float* grad_out, const float* mask,
  *                  chosen on the HOST by compressed_sensing.py:82-123 because
  *                  numpy's legacy RandomState cannot be reproduced on device)
  *   inp, kspace, mask, target: (B,2,H,W) outputs
+ *   dtab (B,H), addend (B,2,H,W): optional (both or neither).  The noiseless DC
+ *                  plan csmri_dc_prepare would compute for (kspace, mask): the
+ *                  row-inverse of x_fu is an intermediate of x_u anyway, so a
+ *                  loader that asks for it saves the prepare pass and the
+ *                  row-constancy read (the mask is row-constant by construction).
  */
 int csmri_undersample(const float* img, const unsigned char* rows, float* inp,
-                      float* kspace, float* mask, float* target, int B, int H,
-                      int W, void* scratch, void* stream);
+                      float* kspace, float* mask, float* target, float* dtab,
+                      float* addend, int B, int H, int W, void* scratch,
+                      void* stream);
 
 /* Plain ortho FFT2 / iFFT2 of a planar complex batch (Fft2d / Ifft2d forward,
  * myfft.py:78-128); inverse != 0 selects the inverse.  Used by the tests to

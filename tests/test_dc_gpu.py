@@ -517,3 +517,37 @@ def test_custom_op_registration_opcheck():
     torch.library.opcheck(ops.dc_general, (xd.clone().requires_grad_(True), None, k0d, md, 0.1),
                           test_utils=tests)
     torch.library.opcheck(ops.dc_general_adjoint, (xd, md, 0.1), test_utils=tests[:2])
+
+
+def test_loader_hands_over_the_dc_plan(monkeypatch):
+    """undersampling.undersample registers the (noiseless) DC plan it gets for
+    free; RecNet then runs without a prepare pass or host read, and the result
+    equals the one computed from a freshly prepared plan."""
+    myfft, ops, recnet, us = _mods()
+    B, n = 3, 128
+    img = torch.rand(B, n, n, device='cuda')
+    rows = us.cartesian_rows((B, n, n), 4, 8, False, np.random.RandomState(2))
+    myfft.clear_plan_cache()
+    batch = us.undersample(img, rows)
+    x = torch.randn(B, 2, n, n, device='cuda')
+    handed = myfft.get_plan(batch['kspace'], batch['mask'])
+    assert handed.row_constant
+    out_handed = myfft.data_consistency(x, batch['kspace'], batch['mask'])
+    fresh = myfft.DCPlan(batch['kspace'], batch['mask'], 0.0)
+    assert fresh.row_constant
+    assert torch.equal(handed.dtab, fresh.dtab)
+    assert (handed.addend - fresh.addend).norm().item() < 1e-6 * fresh.addend.norm().item()
+    out_fresh = ops.dc_cartesian(x, None, fresh.dtab, fresh.addend)
+    assert (out_handed - out_fresh).norm().item() < 1e-6 * out_fresh.norm().item()
+    ref = orc.dc_perform_np(x.cpu().numpy(), batch['kspace'].cpu().numpy(),
+                            batch['mask'].cpu().numpy())
+    assert orc.rel_l2(out_handed.cpu().numpy(), ref) < TOL
+
+    def boom(*a, **k):
+        raise AssertionError('prepare must not run for a loader-prepared batch')
+    monkeypatch.setattr(ops, 'dc_prepare', boom)
+    net = recnet.construct_model({'num_blocks': 2, 'num_convs': 2, 'num_filters': 4}).cuda()
+    net(batch['inp'], batch['kspace'], batch['mask']).sum().backward()
+    # a noisy layer is a different plan: it does need the prepare pass
+    with pytest.raises(AssertionError):
+        myfft.DataConsistencyInKspace(noise_lvl=0.1).perform(x, batch['kspace'], batch['mask'])
