@@ -277,16 +277,87 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
 }
 
 // ---------------------------------------------------------------------------
+// Loader step for Cartesian (row-constant) sampling, column part.  With
+// m[h, w] = r[h] the zero-filled image is F^-1(m . F x) = F_H^-1(r . F_H x): the
+// W-axis transforms cancel, so one pass over the real image column gives
+//   target = (x, 0)                                   dnn_io.py:47-61
+//   hyb    = r[k] * FFT_H(x)[k] / H                   masked hybrid-space rows; this is
+//                                                     also the DC plan's `addend`
+//   inp    = iFFT_H(hyb)                              compressed_sensing.py:511
+// and k-space itself follows from the sampled rows of hyb alone (row kernel,
+// PRE = 4).  Replaces row FFT -> column FFT + mask -> row iFFT -> column iFFT.
+// ---------------------------------------------------------------------------
+template <int H, int E, int CW, int WT, int MINB>
+__global__ void __launch_bounds__(CW*(H / E), MINB)
+    undersample_strip_kernel(const float* __restrict__ img, const unsigned char* __restrict__ rows,
+                             float* __restrict__ target, float* __restrict__ hyb,
+                             float* __restrict__ inp, int W_rt, int nstrips_rt) {
+  typedef LineFFT<H, E, CW> L;
+  constexpr int T = L::T;
+  const int W = WT ? WT : W_rt;
+  const int nstrips = WT ? WT / CW : nstrips_rt;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cf* sm = reinterpret_cast<cf*>(smem_raw);
+  cf* tw_s = reinterpret_cast<cf*>(smem_raw + L::kSmemBytes);
+  L::fill_twiddles(tw_s, threadIdx.x, CW * T);
+
+  const int lane = threadIdx.x % CW;
+  const int j = threadIdx.x / CW;
+  const int b = blockIdx.x / nstrips;
+  const int strip = blockIdx.x - b * nstrips;
+  const size_t plane = (size_t)H * W;
+  const size_t base_img = (size_t)b * plane + (size_t)strip * CW + lane;
+  const size_t base = (size_t)b * 2 * plane + (size_t)strip * CW + lane;
+
+  cf v[E];
+#pragma unroll
+  for (int i = 0; i < E; ++i) v[i] = mk(ld_stream(img + base_img + (size_t)(j + T * i) * W), 0.0f);
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    const size_t o = (size_t)(j + T * i) * W;
+    st_stream(target + base + o, v[i].x);
+    st_stream(target + base + plane + o, 0.0f);
+  }
+  __syncthreads();  // twiddle table ready
+  L::template a_front<false>(v, sm, tw_s, j, lane);
+  __syncthreads();
+  L::template a_back<false>(v, sm, j, lane);
+  constexpr float inv_h = 1.0f / (float)H;
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const int k = L::k_index(j, r);
+    const float m = rows[(size_t)b * H + k] ? 1.0f : 0.0f;
+    v[r] = mk((v[r].x * inv_h) * m, (v[r].y * inv_h) * m);
+    const size_t o = (size_t)k * W;
+    st_stream(hyb + base + o, v[r].x);
+    st_stream(hyb + base + plane + o, v[r].y);
+  }
+  L::template b_front<true>(v, sm, j, lane);
+  __syncthreads();
+  L::template b_back<true>(v, sm, tw_s, j, lane);
+#pragma unroll
+  for (int i = 0; i < E; ++i) {
+    const size_t o = (size_t)(j + T * i) * W;
+    st_stream(inp + base + o, v[i].x);
+    st_stream(inp + base + plane + o, v[i].y);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // single row DFT along W.  A CTA owns RT = CW rows of one plane pair; the tile
 // is staged through shared memory so that global accesses stay coalesced while
 // the lanes of a warp own different rows.
 //   PRE: 0 none, 1 add `aux` (residual), 2 multiply by cmul*aux (aux = mask),
-//        3 real input (imaginary plane absent / zero)
+//        3 real input (imaginary plane absent / zero),
+//        4 sampled rows only: rows with rowsel[b, h] == 0 are neither read nor
+//          transformed, their output is zero; the dense 2-channel mask
+//          (dnn_io.py:56-59) is written alongside into mask_out
 // ---------------------------------------------------------------------------
 template <int W, int E, int R, bool INV, int PRE>
 __global__ void __launch_bounds__(R*(W / E))
     fft_rows_kernel(const float* __restrict__ in, const float* __restrict__ aux,
-                    float* __restrict__ out, int H, float scale, float cmulv) {
+                    float* __restrict__ out, int H, float scale, float cmulv,
+                    const unsigned char* __restrict__ rowsel, float* __restrict__ mask_out) {
   // The T = W/E threads of one row sit in adjacent lanes (thread j holds
   // x[j + T*i]), so for every i the lanes read / write consecutive floats:
   // global traffic goes straight between HBM and registers in T*4-byte
@@ -320,11 +391,13 @@ __global__ void __launch_bounds__(R*(W / E))
   const size_t off_in = (PRE == 3 ? (size_t)b * plane : (size_t)b * 2 * plane) + (size_t)row * W + j;
   const size_t off = (size_t)b * 2 * plane + (size_t)row * W + j;
 
+  // PRE == 4: uniform over the T threads (adjacent lanes) that share a row
+  const bool on = (PRE != 4) || rowsel[(size_t)b * H + row] != 0;
   cf v[E];
 #pragma unroll
   for (int i = 0; i < E; ++i) {
-    float re = ld_stream(in + off_in + T * i);
-    float im = (PRE == 3) ? 0.0f : ld_stream(in + off_in + plane + T * i);
+    float re = on ? ld_stream(in + off_in + T * i) : 0.0f;
+    float im = (PRE == 3 || !on) ? 0.0f : ld_stream(in + off_in + plane + T * i);
     if (PRE == 1) {
       re += ld_stream(aux + off + T * i);
       im += ld_stream(aux + off + plane + T * i);
@@ -334,28 +407,37 @@ __global__ void __launch_bounds__(R*(W / E))
     }
     v[i] = mk(re, im);
   }
-  RegFFT<E, INV>::run(v);
+  if (on) RegFFT<E, INV>::run(v);
   __syncthreads();   // twiddle table ready
+  if (on) {
 #pragma unroll
-  for (int k1 = 1; k1 < E; ++k1) {
-    const cf w = tw_t[k1 * T + j];
-    v[k1] = INV ? cmul_conj(v[k1], w) : cmul(v[k1], w);
+    for (int k1 = 1; k1 < E; ++k1) {
+      const cf w = tw_t[k1 * T + j];
+      v[k1] = INV ? cmul_conj(v[k1], w) : cmul(v[k1], w);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < E; ++k1) sm[k1 * TP + j] = v[k1];
   }
-#pragma unroll
-  for (int k1 = 0; k1 < E; ++k1) sm[k1 * TP + j] = v[k1];
   __syncthreads();
+  if (on) {
 #pragma unroll
-  for (int q = 0; q < Q; ++q)
+    for (int q = 0; q < Q; ++q)
 #pragma unroll
-    for (int j2 = 0; j2 < T; ++j2) v[q * T + j2] = sm[(q * T + j) * TP + j2];
+      for (int j2 = 0; j2 < T; ++j2) v[q * T + j2] = sm[(q * T + j) * TP + j2];
 #pragma unroll
-  for (int q = 0; q < Q; ++q) RegFFT<T, INV>::run(v + q * T);
+    for (int q = 0; q < Q; ++q) RegFFT<T, INV>::run(v + q * T);
+  }
   // thread t = j holds X[(q*T + t) + E*k2] in v[q*T + k2]: consecutive t -> consecutive k
 #pragma unroll
   for (int rr = 0; rr < E; ++rr) {
     const int k0i = (rr / T) * T + E * (rr % T);          // + j
     st_stream(out + off + k0i, v[rr].x * scale);
     st_stream(out + off + plane + k0i, v[rr].y * scale);
+    if (PRE == 4) {
+      const float m = on ? 1.0f : 0.0f;
+      st_stream(mask_out + off + k0i, m);
+      st_stream(mask_out + off + plane + k0i, m);
+    }
   }
 }
 
@@ -409,25 +491,6 @@ __global__ void dtab_from_rows_kernel(const unsigned char* __restrict__ rows, in
   const int k1 = h % E, k2 = h / E;
   const float m = rows[i] ? 1.0f : 0.0f;
   dtab[(size_t)b * H + (k1 % T) * E + (k1 / T) * T + k2] = (1.0f - m) / (float)H;
-}
-
-// real image + row table -> dense 2-channel mask and (img, 0) target
-__global__ void expand_mask_target_kernel(const float* __restrict__ img,
-                                          const unsigned char* __restrict__ rows,
-                                          float* __restrict__ mask, float* __restrict__ target,
-                                          int B, int H, int W) {
-  const size_t plane = (size_t)H * W;
-  const size_t n = (size_t)B * plane;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const size_t b = i / plane, rem = i - b * plane;
-    const int h = (int)(rem / W);
-    const float m = rows[b * H + h] ? 1.0f : 0.0f;
-    mask[b * 2 * plane + rem] = m;
-    mask[b * 2 * plane + plane + rem] = m;
-    target[b * 2 * plane + rem] = img[i];
-    target[b * 2 * plane + plane + rem] = 0.0f;
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -663,12 +726,12 @@ static int sm_count() {
   return n;
 }
 
-template <int H, int E, int CW, int MINB, int WT, bool ADD>
+template <int H, int E, int CW, int MINB, int WT, bool ADD, bool INPL>
 static int launch_strip_pipe_wt(const float* x, const float* residual, const float* dtab,
                                 const float* addend, float* out, int B, int W, cudaStream_t s) {
   typedef LineFFT<H, E, CW> L;
-  typedef PipeSmem<H, E, CW, ADD> S;
-  auto kern = dc_strip_pipe_kernel<H, E, CW, MINB, WT, ADD>;
+  typedef PipeSmem<H, E, CW, ADD, INPL> S;
+  auto kern = dc_strip_pipe_kernel<H, E, CW, MINB, WT, ADD, INPL>;
   CSMRI_TRY(set_smem(kern, S::kBytes));
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
@@ -704,18 +767,24 @@ static int launch_strip_pipe_wt(const float* x, const float* residual, const flo
 }
 
 // MINB_F / MINB_A: resident CTAs per SM asked of the compiler for the forward
-// (x + addend tiles in smem) and adjoint (x tile only) instantiations
-template <int H, int E, int CW, int MINB_F, int MINB_A = MINB_F>
+// (x + addend tiles in smem) and adjoint (x tile only) instantiations;
+// INPL_F / INPL_A: x tile shares the exchange buffer (see dc_pipe.cuh)
+template <int H, int E, int CW, int MINB_F, int MINB_A = MINB_F, bool INPL_F = false,
+          bool INPL_A = false>
 static int launch_strip_pipe_cfg(const float* x, const float* residual, const float* dtab,
                                  const float* addend, float* out, int B, int W, cudaStream_t s) {
   if (addend != nullptr) {
     if (W == H)
-      return launch_strip_pipe_wt<H, E, CW, MINB_F, H, true>(x, residual, dtab, addend, out, B, W, s);
-    return launch_strip_pipe_wt<H, E, CW, MINB_F, 0, true>(x, residual, dtab, addend, out, B, W, s);
+      return launch_strip_pipe_wt<H, E, CW, MINB_F, H, true, INPL_F>(x, residual, dtab, addend, out,
+                                                                     B, W, s);
+    return launch_strip_pipe_wt<H, E, CW, MINB_F, 0, true, INPL_F>(x, residual, dtab, addend, out, B,
+                                                                   W, s);
   }
   if (W == H)
-    return launch_strip_pipe_wt<H, E, CW, MINB_A, H, false>(x, residual, dtab, addend, out, B, W, s);
-  return launch_strip_pipe_wt<H, E, CW, MINB_A, 0, false>(x, residual, dtab, addend, out, B, W, s);
+    return launch_strip_pipe_wt<H, E, CW, MINB_A, H, false, INPL_A>(x, residual, dtab, addend, out,
+                                                                    B, W, s);
+  return launch_strip_pipe_wt<H, E, CW, MINB_A, 0, false, INPL_A>(x, residual, dtab, addend, out, B,
+                                                                  W, s);
 }
 
 template <int H, int E, int CW, int MINB, int WT, bool ADD>
@@ -825,8 +894,17 @@ static int launch_strip_row(const float* x, const float* residual, const float* 
       // two (forward) / three (adjoint) per SM
       if (tma) return launch_strip_pipev_cfg<256, 16, 16, 2, 3>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<256, 16, 16, 4>(x, residual, dtab, addend, out, B, W, s);
+    // 320: a 40 KiB strip per buffer leaves room for one prefetching CTA of 4
+    // warps; with the x tile landing in the exchange buffer (INPL) two (forward)
+    // / three (adjoint) CTAs fit: forward 81 -> 68 us at B=164.  Variant 1 = the
+    // prefetching layout, kept for A/B runs.  At 512 / 1024 both layouts time
+    // the same (issue-bound, not occupancy-bound: profiles/README.md), so they
+    // keep the prefetching one.
     case 320:
-      if (tma) return launch_strip_pipe_cfg<320, 40, 16, 1, 2>(x, residual, dtab, addend, out, B, W, s);
+      if (tma && g_strip_variant == 1)
+        return launch_strip_pipe_cfg<320, 40, 16, 1, 2>(x, residual, dtab, addend, out, B, W, s);
+      if (tma)
+        return launch_strip_pipe_cfg<320, 40, 16, 2, 3, true, true>(x, residual, dtab, addend, out, B, W, s);
       return launch_strip_row_cfg<320, 40, 32, 1>(x, residual, dtab, addend, out, B, W, s);
     case 512:
       if (tma) return launch_strip_pipe_cfg<512, 32, 16, 1>(x, residual, dtab, addend, out, B, W, s);
@@ -919,10 +997,45 @@ static int launch_fft_strip(const float* in, float* out, int B, int H, int W, fl
   return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
 }
 
+template <int H, int E, int CW, int MINB>
+static int launch_undersample_strip_cfg(const float* img, const unsigned char* rows, float* target,
+                                        float* hyb, float* inp, int B, int W, cudaStream_t s) {
+  typedef LineFFT<H, E, CW> L;
+  const int nstrips = W / CW;
+  constexpr int smem = L::kSmemBytes + L::kTwBytes;
+  if (W == H) {
+    auto kern = undersample_strip_kernel<H, E, CW, H, MINB>;
+    CSMRI_TRY(set_smem(kern, smem));
+    kern<<<B * nstrips, CW * L::T, smem, s>>>(img, rows, target, hyb, inp, W, nstrips);
+  } else {
+    auto kern = undersample_strip_kernel<H, E, CW, 0, MINB>;
+    CSMRI_TRY(set_smem(kern, smem));
+    kern<<<B * nstrips, CW * L::T, smem, s>>>(img, rows, target, hyb, inp, W, nstrips);
+  }
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+// (E, T) per H must match strip_radix(H): hyb doubles as the DC plan's addend
+static int launch_undersample_strip(const float* img, const unsigned char* rows, float* target,
+                                    float* hyb, float* inp, int B, int H, int W, cudaStream_t s) {
+  switch (H) {
+    case 32: return launch_undersample_strip_cfg<32, 8, 32, 1>(img, rows, target, hyb, inp, B, W, s);
+    case 64: return launch_undersample_strip_cfg<64, 8, 32, 1>(img, rows, target, hyb, inp, B, W, s);
+    case 128: return launch_undersample_strip_cfg<128, 16, 32, 2>(img, rows, target, hyb, inp, B, W, s);
+    case 256: return launch_undersample_strip_cfg<256, 16, 16, 3>(img, rows, target, hyb, inp, B, W, s);
+    case 512: return launch_undersample_strip_cfg<512, 32, 16, 1>(img, rows, target, hyb, inp, B, W, s);
+    case 1024: return launch_undersample_strip_cfg<1024, 32, 16, 1>(img, rows, target, hyb, inp, B, W, s);
+    case 320: return launch_undersample_strip_cfg<320, 40, 32, 1>(img, rows, target, hyb, inp, B, W, s);
+  }
+  return fail(CSMRI_E_SHAPE, "unsupported H=%d", H);
+}
+
 // ---- row launches -----------------------------------------------------------
 template <int W, int E, int R>
 static int launch_fft_rows_cfg(const float* in, const float* aux, float* out, int B, int H,
-                               float scale, float cmulv, bool inv, int pre, cudaStream_t s) {
+                               float scale, float cmulv, bool inv, int pre, cudaStream_t s,
+                               const unsigned char* rowsel = nullptr, float* mask_out = nullptr) {
   constexpr int T = W / E;
   constexpr int smem = (R * E * (T + 1) + W) * (int)sizeof(cf);
   if (H % R != 0) return fail(CSMRI_E_SHAPE, "H=%d is not a multiple of %d", H, R);
@@ -931,11 +1044,13 @@ static int launch_fft_rows_cfg(const float* in, const float* aux, float* out, in
   {                                                                     \
     auto kern = fft_rows_kernel<W, E, R, I_, P_>;                       \
     CSMRI_TRY(set_smem(kern, smem));                                    \
-    kern<<<grid, block, smem, s>>>(in, aux, out, H, scale, cmulv);      \
+    kern<<<grid, block, smem, s>>>(in, aux, out, H, scale, cmulv,       \
+                                   rowsel, mask_out);                   \
   }
   if (!inv && pre == 0) CSMRI_ROWS(false, 0)
   else if (!inv && pre == 1) CSMRI_ROWS(false, 1)
   else if (!inv && pre == 3) CSMRI_ROWS(false, 3)
+  else if (!inv && pre == 4) CSMRI_ROWS(false, 4)
   else if (inv && pre == 0) CSMRI_ROWS(true, 0)
   else if (inv && pre == 2) CSMRI_ROWS(true, 2)
   else return fail(CSMRI_E_ARG, "row kernel variant inv=%d pre=%d not instantiated", (int)inv, pre);
@@ -945,15 +1060,18 @@ static int launch_fft_rows_cfg(const float* in, const float* aux, float* out, in
 }
 
 static int launch_fft_rows(const float* in, const float* aux, float* out, int B, int H, int W,
-                           float scale, float cmulv, bool inv, int pre, cudaStream_t s) {
+                           float scale, float cmulv, bool inv, int pre, cudaStream_t s,
+                           const unsigned char* rowsel = nullptr, float* mask_out = nullptr) {
+  if ((pre == 4) != (rowsel != nullptr && mask_out != nullptr))
+    return fail(CSMRI_E_ARG, "row selection needs pre == 4, a row table and a mask destination");
   switch (W) {
-    case 32: return launch_fft_rows_cfg<32, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);   // T=4
-    case 64: return launch_fft_rows_cfg<64, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);   // T=8
-    case 128: return launch_fft_rows_cfg<128, 16, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s);  // T=8
-    case 256: return launch_fft_rows_cfg<256, 16, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s);  // T=16
-    case 512: return launch_fft_rows_cfg<512, 32, 8>(in, aux, out, B, H, scale, cmulv, inv, pre, s);   // T=16
-    case 1024: return launch_fft_rows_cfg<1024, 32, 8>(in, aux, out, B, H, scale, cmulv, inv, pre, s);  // T=32
-    case 320: return launch_fft_rows_cfg<320, 40, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s);  // T=8
+    case 32: return launch_fft_rows_cfg<32, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s, rowsel, mask_out);   // T=4
+    case 64: return launch_fft_rows_cfg<64, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s, rowsel, mask_out);   // T=8
+    case 128: return launch_fft_rows_cfg<128, 16, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s, rowsel, mask_out);  // T=8
+    case 256: return launch_fft_rows_cfg<256, 16, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s, rowsel, mask_out);  // T=16
+    case 512: return launch_fft_rows_cfg<512, 32, 8>(in, aux, out, B, H, scale, cmulv, inv, pre, s, rowsel, mask_out);   // T=16
+    case 1024: return launch_fft_rows_cfg<1024, 32, 8>(in, aux, out, B, H, scale, cmulv, inv, pre, s, rowsel, mask_out);  // T=32
+    case 320: return launch_fft_rows_cfg<320, 40, 16>(in, aux, out, B, H, scale, cmulv, inv, pre, s, rowsel, mask_out);  // T=8
   }
   return fail(CSMRI_E_SHAPE, "unsupported W=%d", W);
 }
@@ -1127,19 +1245,17 @@ int csmri_undersample(const float* img, const unsigned char* rows, float* inp, f
     CSMRI_TRY(check_ptr(dtab, "dtab"));
     CSMRI_TRY(check_ptr(addend, "addend"));
   }
-  float* hyb = (float*)scratch;
-  const float sc = 1.0f / sqrtf((float)H * (float)W);
-  // x_f = fft2(x, ortho); x_fu = mask * x_f          (compressed_sensing.py:509-510)
-  CSMRI_TRY(launch_fft_rows(img, nullptr, hyb, B, H, W, 1.0f, 0.0f, false, 3, s));
-  CSMRI_TRY(launch_fft_strip(hyb, kspace, B, H, W, sc, false, rows, s));
-  // x_u = ifft2(x_fu, ortho)                         (compressed_sensing.py:511)
-  // The row-inverse of x_fu, scaled by 1/sqrt(HW), is exactly the hybrid-space k0
-  // term the DC strip kernels add (csmri_dc_prepare's `addend`): when the caller
-  // wants the DC plan it is written there instead of into scratch, for free.
-  float* mid = addend != nullptr ? addend : hyb;
-  CSMRI_TRY(launch_fft_rows(kspace, nullptr, mid, B, H, W, sc, 0.0f, true, 0, s));
-  CSMRI_TRY(launch_fft_strip(mid, inp, B, H, W, 1.0f, true, nullptr, s));
-  expand_mask_target_kernel<<<148 * 8, 256, 0, s>>>(img, rows, mask, target, B, H, W);
+  // x_f = fft2(x, ortho); x_fu = mask * x_f; x_u = ifft2(x_fu, ortho)
+  // (compressed_sensing.py:509-511) for a row-constant mask, in two passes:
+  // columns (target, masked hybrid rows, zero-filled image), then the sampled
+  // rows only (k-space, dense mask).  The masked hybrid rows, scaled by 1/H,
+  // are exactly the k0 term the DC strip kernels add (csmri_dc_prepare's
+  // `addend`): when the caller wants the DC plan they are written there
+  // instead of into scratch, for free.
+  float* hyb = addend != nullptr ? addend : (float*)scratch;
+  CSMRI_TRY(launch_undersample_strip(img, rows, target, hyb, inp, B, H, W, s));
+  CSMRI_TRY(launch_fft_rows(hyb, nullptr, kspace, B, H, W, sqrtf((float)H) / sqrtf((float)W), 0.0f,
+                            false, 4, s, rows, mask));
   if (dtab != nullptr)
     dtab_from_rows_kernel<<<(B * H + 255) / 256, 256, 0, s>>>(rows, B, H, strip_radix(H), dtab);
   CSMRI_CUDA(cudaGetLastError());

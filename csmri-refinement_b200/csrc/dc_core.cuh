@@ -147,8 +147,16 @@ struct LineFFT {
   }
   template <bool INV>
   static CSMRI_HD void b_back(cf* v, const cf* sm, const cf* tw_s, int j, int lane) {
+    b_back_load(v, sm, j, lane);
+    b_back_compute<INV>(v, tw_s, j);
+  }
+  // the two steps of b_back, for callers that recycle the exchange buffer in between
+  static CSMRI_HD void b_back_load(cf* v, const cf* sm, int j, int lane) {
 #pragma unroll
     for (int k1 = 0; k1 < E; ++k1) v[k1] = sm[(k1 * TP + j) * CW + lane];
+  }
+  template <bool INV>
+  static CSMRI_HD void b_back_compute(cf* v, const cf* tw_s, int j) {
     apply_twiddles<INV>(v, tw_s, j);
     RegFFT<E, INV>::run(v);
   }

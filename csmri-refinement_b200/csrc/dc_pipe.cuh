@@ -24,6 +24,14 @@
 //
 // Shared memory per CTA: exchange H*CW*8 + x tile H*CW*8 + addend tile
 // H*CW*8 + 2 D rows + twiddle table.
+//
+// INPL ("in place") trades the one-tile-ahead prefetch for occupancy: the x
+// tile lands in the exchange buffer itself (one extra CTA barrier between
+// "everyone has its column in registers" and the first exchange store) and the
+// next tile is requested once the inverse half has read its last exchange slot.
+// The load latency is then hidden by a second resident CTA instead of by the
+// CTA's own pipeline.  For the tall sizes (320, 512, 1024), where a column strip
+// is 40-64 KiB, that is the difference between one and two CTAs per SM.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -59,6 +67,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -96,7 +107,7 @@ __device__ __forceinline__ float ld_stream_f32(const float* p) {
   return v;
 }
 
-template <int H, int E, int CW, bool ADD = true>
+template <int H, int E, int CW, bool ADD = true, bool INPL = false>
 struct PipeSmem {
   static constexpr int kRowChunks = (H + 255) / 256;          // TMA box dims are <= 256
   static constexpr int kTileFloats = 2 * H * CW;
@@ -104,10 +115,15 @@ struct PipeSmem {
   static constexpr int kExchBytes = (LineFFT<H, E, CW>::kSmemBytes + 127) / 128 * 128;
   static constexpr int kDBytes = 2 * H * 4;
   static constexpr int kTwBytes = LineFFT<H, E, CW>::kTwBytes;
-  static constexpr int kBytes = kExchBytes + (ADD ? 2 : 1) * kTileBytes + kDBytes + kTwBytes + 64;
+  // byte offsets: exchange | x tile (aliases the exchange when INPL) | addend | D | twiddles
+  static constexpr int kXOff = INPL ? 0 : kExchBytes;
+  static constexpr int kAOff = INPL ? (kExchBytes > kTileBytes ? kExchBytes : kTileBytes)
+                                    : kExchBytes + kTileBytes;
+  static constexpr int kDOff = kAOff + (ADD ? kTileBytes : 0);
+  static constexpr int kBytes = kDOff + kDBytes + kTwBytes + 64;
 };
 
-template <int H, int E, int CW, int MINB, int WT, bool ADD>
+template <int H, int E, int CW, int MINB, int WT, bool ADD, bool INPL>
 __global__ void __launch_bounds__(CW*(H / E), MINB)
     dc_strip_pipe_kernel(const __grid_constant__ CUtensorMap tm_x,
                          const __grid_constant__ CUtensorMap tm_add,
@@ -118,21 +134,22 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
   const int W = WT ? WT : W_rt;
   const int nstrips = WT ? WT / CW : nstrips_rt;
   typedef LineFFT<H, E, CW> L;
-  typedef PipeSmem<H, E, CW, ADD> S;
+  typedef PipeSmem<H, E, CW, ADD, INPL> S;
   constexpr int T = L::T;
   constexpr int NT = CW * T;
   // NB: no integer arithmetic on this pointer - it would demote every access
   // below from LDS/STS to generic LD/ST (seen in the first ncu source page).
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   cf* sm = reinterpret_cast<cf*>(smem_dyn);
-  float* xbuf = reinterpret_cast<float*>(smem_dyn + S::kExchBytes);
-  float* abuf = xbuf + S::kTileFloats;                      // absent when !ADD
-  float* dbuf = xbuf + (ADD ? 2 : 1) * S::kTileFloats;      // [2][H]
+  float* xbuf = reinterpret_cast<float*>(smem_dyn + S::kXOff);
+  float* abuf = reinterpret_cast<float*>(smem_dyn + S::kAOff);   // absent when !ADD
+  float* dbuf = reinterpret_cast<float*>(smem_dyn + S::kDOff);   // [2][H]
   cf* tw_s = reinterpret_cast<cf*>(dbuf + 2 * H);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tw_s + H);
   const uint32_t bar_x = smem_u32(&bars[0]);    // x tile (+ D row) landed
   const uint32_t bar_a = smem_u32(&bars[1]);    // addend tile landed
   const uint32_t bar_ae = smem_u32(&bars[2]);   // addend tile consumed by all NT threads
+  const uint32_t bar_f = smem_u32(&bars[3]);    // INPL: exchange buffer free for the next x tile
 
   const int lane = threadIdx.x % CW;
   const int j = threadIdx.x / CW;
@@ -164,6 +181,7 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
     mbar_init(bar_x, 1);
     mbar_init(bar_a, 1);
     mbar_init(bar_ae, NT);
+    mbar_init(bar_f, NT);
     fence_barrier_init();
     prefetch_tensormap(&tm_x);
     if (ADD) prefetch_tensormap(&tm_add);
@@ -212,10 +230,11 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
 
     if (threadIdx.x == 0)
       next_tile[slot ^ 1] = (int)atomicAdd(&sched[0], 1u) + (int)gridDim.x;
+    if (INPL) __syncthreads();   // the exchange stores below overwrite the x tile
     L::template a_front<false>(v, sm, tw_s, j, lane);
     __syncthreads();  // exchange written; x tile consumed by everyone; next_tile visible
     const int next = next_tile[slot ^ 1];
-    if (threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
+    if (!INPL && threadIdx.x == 0 && next < ntiles) issue_x(next, slot ^ 1);
 
     L::template a_back<false>(v, sm, j, lane);
     L::apply_dtab(v, dbuf + slot * H + j * E);
@@ -230,7 +249,20 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
     }
     L::template b_front<true>(v, sm, j, lane);
     __syncthreads();
-    L::template b_back<true>(v, sm, tw_s, j, lane);
+    if (INPL) {
+      L::b_back_load(v, sm, j, lane);
+      // generic-proxy accesses to the buffer are ordered before the TMA write
+      // of the next tile by fence + arrive (all NT threads) / wait (thread 0)
+      fence_proxy_async_smem();
+      mbar_arrive(bar_f);
+      if (threadIdx.x == 0 && next < ntiles) {
+        mbar_wait(bar_f, phase);
+        issue_x(next, slot ^ 1);
+      }
+      L::template b_back_compute<true>(v, tw_s, j);
+    } else {
+      L::template b_back<true>(v, sm, tw_s, j, lane);
+    }
     {
       float* pr = out + gbase;
       float* pi = pr + plane;

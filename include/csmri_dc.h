@@ -128,9 +128,15 @@ int csmri_dc_adjoint(const float* grad_out, const float* mask,
  *   inp, kspace, mask, target: (B,2,H,W) outputs
  *   dtab (B,H), addend (B,2,H,W): optional (both or neither).  The noiseless DC
  *                  plan csmri_dc_prepare would compute for (kspace, mask): the
- *                  row-inverse of x_fu is an intermediate of x_u anyway, so a
+ *                  masked hybrid-space rows are an intermediate anyway, so a
  *                  loader that asks for it saves the prepare pass and the
  *                  row-constancy read (the mask is row-constant by construction).
+ * Two passes (the mask is constant along W, so x_u = F_H^-1(r . F_H x)): a column
+ * kernel writes target, the masked hybrid rows and inp; a row kernel transforms
+ * the sampled rows only into kspace and writes the dense mask.  Masked k-space
+ * entries are +0.0 (the reference's `mask * x_f` leaves signed zeros; no
+ * consumer can tell them apart).  scratch: one (B,2,H,W) tensor, unused when
+ * addend is given.
  */
 int csmri_undersample(const float* img, const unsigned char* rows, float* inp,
                       float* kspace, float* mask, float* target, float* dtab,

@@ -1,13 +1,17 @@
 // Memory-pattern ceiling for the column-strip access of the DC kernels:
-// copy a (B,2,256,256) fp32 tensor strip by strip (CW columns x 256 rows x 2
+// copy a (B,2,N,N) fp32 tensor (N = 256 by default) strip by strip (CW columns x 256 rows x 2
 // planes per CTA, all loads issued before the stores, like the real kernel)
 // with 32-bit or 128-bit accesses, against a linear copy.
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench_strip tools/ubench_strip_copy.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 
-constexpr int N = 256;
-constexpr int B = 256;
+#ifndef UB_N
+#define UB_N 256
+#define UB_B 256
+#endif
+constexpr int N = UB_N;   // -DUB_N=512 -DUB_B=64 for the other slice sizes
+constexpr int B = UB_B;
 
 __device__ __forceinline__ float ldf(const float* p) {
   float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
@@ -83,6 +87,8 @@ template <typename F> static float timeit(F launch, int reps) {
 }
 
 template <int CW, int VEC, int THREADS, int TWO> static void report(const char* name) {
+  if (N % CW != 0 || (2 * N) % (THREADS / (CW / VEC)) != 0 ||
+      2 * N / (THREADS / (CW / VEC)) * VEC > 200) return;   // shape does not tile / fit registers
   float ms = timeit([](int i) {
     strip_copy<CW, VEC, THREADS, TWO><<<B * (N / CW), THREADS>>>(A[i & 1], C[i & 1], O); }, 20);
   printf("  strip CW=%-3d %3d-bit %4d thr %-10s %8.2f us %6.0f GB/s (%s)\n", CW, VEC * 32, THREADS, name,
