@@ -116,13 +116,15 @@ def make_batch(dev, B, n, seed):
 
 
 def recnet_train_bench(dev, rank, world, steps=8, warmup=3, batch=32, n=256, blocks=5, convs=5,
-                       filters=32):
+                       filters=32, tf32=False):
     """BASELINE configs[2]: RecNet D5C5 MSE training step, batch 32 per GPU,
     batch-sharded, one flat-bucket NCCL allreduce per step, fp32 (no TF32),
     whole step captured in a CUDA graph.  Returns slices/s over all ranks."""
     import torch.distributed as dist
     from csmri_refinement_b200 import parallel, recnet, undersampling
-    torch.backends.cudnn.allow_tf32 = False
+    # tf32=True is torch's stock conv setting (TF32 tensor cores): a context
+    # number only, the parity gate (1e-5) is stated for fp32 arithmetic
+    torch.backends.cudnn.allow_tf32 = bool(tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True              # let cuDNN pick its fastest fp32 algorithms
     torch.manual_seed(0)                               # identical replicas on every rank
@@ -154,10 +156,12 @@ def recnet_train_bench(dev, rank, world, steps=8, warmup=3, batch=32, n=256, blo
         ms = float(t.item())
     return {'metric': 'recnet_train_slices_per_s', 'value': world * batch * steps / (ms * 1e-3),
             'unit': UNIT, 'ms_per_step': ms / steps, 'steps': steps,
-            'config': 'RecNet D%dC%d nf=%d, MSE + Adam(2e-4), batch %d/GPU, %dx%d, fp32 convs '
-                      '(cuDNN, TF32 off), DC = fused strip kernel, CUDA-graph step, '
+            'config': 'RecNet D%dC%d nf=%d, MSE + Adam(2e-4), batch %d/GPU, %dx%d, %s, '
+                      'DC = fused strip kernel, CUDA-graph step, '
                       'flat-bucket NCCL allreduce (%d bytes)' % (
-                          blocks, convs, filters, batch, n, n, trainer.bucket.nbytes()),
+                          blocks, convs, filters, batch, n, n,
+                          'cuDNN convs with TF32 tensor cores (torch default; not parity-gated)'
+                          if tf32 else 'fp32 convs (cuDNN, TF32 off)', trainer.bucket.nbytes()),
             'loss': float(loss.item())}
 
 
@@ -451,8 +455,10 @@ def main():
     if not args.no_recnet:
         try:
             line['recnet_train'] = recnet_train_bench(dev, rank, world)
+            line['recnet_train']['tf32_convs'] = recnet_train_bench(dev, rank, world, tf32=True)
         except Exception as e:  # secondary leg: never lose the headline line
-            line['recnet_train'] = {'error': repr(e)[:300]}
+            line.setdefault('recnet_train', {})['error'] = repr(e)[:300]
+        torch.backends.cudnn.allow_tf32 = False
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline()
     elif rank == 0:

@@ -64,6 +64,16 @@ _SIGNATURES = {
                               [ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
     'csmri_psnr_sum': (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p] + [ctypes.c_int] * 3 +
                        [ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
+    'csmri_plane_minmax': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int, ctypes.c_int,
+                                                             ctypes.c_longlong, ctypes.c_void_p]),
+    'csmri_plane_scale': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int, ctypes.c_int,
+                                                            ctypes.c_longlong, ctypes.c_longlong,
+                                                            ctypes.c_int, ctypes.c_void_p]),
+    'csmri_refine_real_penalty_add': (ctypes.c_int, [_c_float_p] * 6 + [ctypes.c_int] * 3 +
+                                      [ctypes.c_void_p]),
+    'csmri_refine_partials': (ctypes.c_int, []),
+    'csmri_refine_real_penalty_add_backward': (ctypes.c_int, [_c_float_p] * 6 + [ctypes.c_int] * 3 +
+                                               [ctypes.c_void_p]),
     # tuning knob used by bench.py only (not declared in include/csmri_dc.h)
     'csmri_set_variant': (ctypes.c_int, [ctypes.c_int]),
     'csmri_set_tuning': (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),

@@ -45,6 +45,7 @@
 #include "dc_core.cuh"
 #include "dc_pipe.cuh"
 #include "dc_pipev.cuh"
+#include "refine_ops.cuh"
 
 namespace csmri {
 
@@ -1300,6 +1301,99 @@ int csmri_psnr_sum(const float* pred, const float* target, double* sum_sq, int B
   CSMRI_CUDA(cudaMemsetAsync(sum_sq, 0, sizeof(double), (cudaStream_t)stream));
   psnr_sum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, target, sum_sq, plane, total, lo,
                                                            hi);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+// ---- refinement-path pointwise ops (refine_ops.cuh) ---------------------------
+static const int kRefinePartials = 32;
+
+static int plane_chunks(int n) {
+  const int c = (n + 2047) / 2048;
+  return c < 1 ? 1 : (c > kRefinePartials ? kRefinePartials : c);
+}
+
+static int plane_minmax_impl(const float* x, float* minimum, float* maximum, int planes, int n,
+                             long long pitch, cudaStream_t s) {
+  unsigned* kmin = reinterpret_cast<unsigned*>(minimum);
+  unsigned* kmax = reinterpret_cast<unsigned*>(maximum);
+  minmax_init_kernel<<<(planes + 255) / 256, 256, 0, s>>>(kmin, kmax, planes);
+  minmax_reduce_kernel<<<dim3(plane_chunks(n), planes), 256, 0, s>>>(x, kmin, kmax, n, pitch);
+  minmax_finish_kernel<<<(planes + 255) / 256, 256, 0, s>>>(minimum, maximum, planes);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+int csmri_plane_minmax(const float* x, float* minimum, float* maximum, int planes, int n,
+                       long long pitch, void* stream) {
+  if (planes <= 0 || planes > 65535 || n <= 0 || pitch < n)
+    return fail(CSMRI_E_SHAPE, "bad plane shape: planes=%d n=%d pitch=%lld", planes, n, pitch);
+  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr(minimum, "minimum"));
+  CSMRI_TRY(check_ptr(maximum, "maximum"));
+  return plane_minmax_impl(x, minimum, maximum, planes, n, pitch, (cudaStream_t)stream);
+}
+
+int csmri_plane_scale(const float* x, const float* minimum, const float* maximum, float* out,
+                      int planes, int n, long long pitch_in, long long pitch_out, int mode,
+                      void* stream) {
+  if (planes <= 0 || planes > 65535 || n <= 0 || pitch_in < n || pitch_out < n)
+    return fail(CSMRI_E_SHAPE, "bad plane shape: planes=%d n=%d pitch=%lld/%lld", planes, n,
+                pitch_in, pitch_out);
+  if (mode < 0 || mode > 2) return fail(CSMRI_E_ARG, "mode must be 0, 1 or 2 (got %d)", mode);
+  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr(minimum, "minimum"));
+  CSMRI_TRY(check_ptr(maximum, "maximum"));
+  CSMRI_TRY(check_ptr(out, "out"));
+  const dim3 grid((n + 1023) / 1024 > 64 ? 64 : (n + 1023) / 1024, planes);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 0) plane_map_kernel<0><<<grid, 256, 0, s>>>(x, minimum, maximum, out, n, pitch_in, pitch_out);
+  else if (mode == 1) plane_map_kernel<1><<<grid, 256, 0, s>>>(x, minimum, maximum, out, n, pitch_in, pitch_out);
+  else plane_map_kernel<2><<<grid, 256, 0, s>>>(x, minimum, maximum, out, n, pitch_in, pitch_out);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+int csmri_refine_partials(void) { return kRefinePartials; }
+
+static int check_refine_shape(int B, int H, int W) {
+  if (B <= 0 || B > 65535 || H <= 0 || W <= 0 || (long long)H * W > 0x3fffffff)
+    return fail(CSMRI_E_SHAPE, "bad shape %dx%dx%d", B, H, W);
+  return CSMRI_OK;
+}
+
+int csmri_refine_real_penalty_add(const float* pretrained, const float* learnable,
+                                  const float* scale, float* pred, float* minimum, float* maximum,
+                                  int B, int H, int W, void* stream) {
+  CSMRI_TRY(check_refine_shape(B, H, W));
+  CSMRI_TRY(check_ptr(pretrained, "pretrained"));
+  CSMRI_TRY(check_ptr(learnable, "learnable"));
+  CSMRI_TRY(check_ptr(scale, "scale"));
+  CSMRI_TRY(check_ptr(pred, "pred"));
+  CSMRI_TRY(check_ptr(minimum, "minimum"));
+  CSMRI_TRY(check_ptr(maximum, "maximum"));
+  const int n = H * W;
+  cudaStream_t s = (cudaStream_t)stream;
+  CSMRI_TRY(plane_minmax_impl(pretrained, minimum, maximum, B, n, 2LL * n, s));
+  const dim3 grid((n + 1023) / 1024 > 64 ? 64 : (n + 1023) / 1024, B);
+  refine_forward_kernel<<<grid, 256, 0, s>>>(pretrained, learnable, scale, minimum, maximum, pred, n);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+int csmri_refine_real_penalty_add_backward(const float* grad_pred, const float* learnable,
+                                           const float* scale, const float* maximum,
+                                           float* grad_learnable, float* grad_scale_partial, int B,
+                                           int H, int W, void* stream) {
+  CSMRI_TRY(check_refine_shape(B, H, W));
+  CSMRI_TRY(check_ptr(grad_pred, "grad_pred"));
+  CSMRI_TRY(check_ptr(learnable, "learnable"));
+  CSMRI_TRY(check_ptr(scale, "scale"));
+  CSMRI_TRY(check_ptr(maximum, "maximum"));
+  CSMRI_TRY(check_ptr(grad_learnable, "grad_learnable"));
+  CSMRI_TRY(check_ptr(grad_scale_partial, "grad_scale_partial"));
+  refine_backward_kernel<<<dim3(kRefinePartials, B), 256, 0, (cudaStream_t)stream>>>(
+      grad_pred, learnable, scale, maximum, grad_learnable, grad_scale_partial, H * W);
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }

@@ -164,6 +164,41 @@ int csmri_magnitude_clamp(const float* x, float* out, int B, int H, int W,
 int csmri_psnr_sum(const float* pred, const float* target, double* sum_sq,
                    int B, int H, int W, float lo, float hi, void* stream);
 
+/* ---- refinement-path pointwise ops --------------------------------------------
+ * A "plane" is n contiguous floats; plane p starts at x + p*pitch (floats), so the
+ * real channel of a (B,2,H,W) tensor is addressed with n = H*W, pitch = 2*H*W.
+ *
+ * csmri_plane_minmax: minimum[p] = min x[p,:], maximum[p] = max(x[p,:] - minimum[p])
+ *   - the two reductions of _scale (models/refinement_wrapper.py:66-69) and of
+ *   magnitude_image (utils/tensor_transforms.py:95-97) in one pass.
+ * csmri_plane_scale, mode 0: out = (x - min) / max            (magnitude_image, :96-98)
+ *                    mode 1: out = (x - min) / max * 2 - 1    (_scale, :68-71)
+ *                    mode 2: out = ((x + 1) / 2) * max + min  (_unscale, :89-91)
+ * csmri_refine_real_penalty_add: RefinementWrapper._refinement_real_penalty_add
+ *   (models/refinement_wrapper.py:173-197) given the learnable model's output:
+ *   pred[:,0] = _unscale(_scale(pretrained[:,0]) + scale * learnable), pred[:,1] =
+ *   pretrained[:,1]; minimum / maximum (B) are returned for the backward.
+ *   pretrained, pred (B,2,H,W); learnable (B,1,H,W); scale: device scalar (the
+ *   nn.Parameter).  The pretrained output is treated as detached (:211-212,226-227).
+ * csmri_refine_real_penalty_add_backward: grad_learnable (B,1,H,W) and
+ *   csmri_refine_partials() partial sums per slice of d/d scale
+ *   (grad_scale_partial, B * partials floats; their total is the gradient).
+ * All are rounded op by op like the reference's tensor expressions: bit-identical
+ * to the torch evaluation for finite inputs.  Any H, W > 0. */
+int csmri_plane_minmax(const float* x, float* minimum, float* maximum, int planes,
+                       int n, long long pitch, void* stream);
+int csmri_plane_scale(const float* x, const float* minimum, const float* maximum,
+                      float* out, int planes, int n, long long pitch_in,
+                      long long pitch_out, int mode, void* stream);
+int csmri_refine_real_penalty_add(const float* pretrained, const float* learnable,
+                                  const float* scale, float* pred, float* minimum,
+                                  float* maximum, int B, int H, int W, void* stream);
+int csmri_refine_partials(void);
+int csmri_refine_real_penalty_add_backward(const float* grad_pred, const float* learnable,
+                                           const float* scale, const float* maximum,
+                                           float* grad_learnable, float* grad_scale_partial,
+                                           int B, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

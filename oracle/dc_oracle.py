@@ -275,3 +275,65 @@ def rel_l2(a, b):
     b = np.asarray(b, dtype=np.float64)
     den = np.linalg.norm(b.ravel())
     return float(np.linalg.norm((a - b).ravel()) / (den if den > 0 else 1.0))
+
+
+# ---------------------------------------------------------------------------
+# refinement-path pointwise ops
+# ---------------------------------------------------------------------------
+def scale_np(x):
+    """models/refinement_wrapper.py:51-73 ``_scale``: per example and channel,
+    (x - min) / max(x - min) * 2 - 1, evaluated op by op in float32.
+    -> (scaled (B,C,H,W), minimum (B,C,1), maximum (B,C,1))"""
+    x = np.asarray(x, dtype=np.float32)
+    b, c, h, w = x.shape
+    out = x.reshape(b, c, h * w)
+    minimum = out.min(axis=2, keepdims=True)
+    out = out - minimum
+    maximum = out.max(axis=2, keepdims=True)
+    out = out / maximum
+    out = out * np.float32(2) - np.float32(1)
+    return out.reshape(b, c, h, w), minimum, maximum
+
+
+def unscale_np(t, minimum, maximum):
+    """models/refinement_wrapper.py:76-92 ``_unscale``: ((t + 1) / 2) * max + min."""
+    t = np.asarray(t, dtype=np.float32)
+    b, c, h, w = t.shape
+    out = t.reshape(b, c, h * w)
+    out = (out + np.float32(1)) / np.float32(2)
+    out = out * maximum + minimum
+    return out.reshape(b, c, h, w)
+
+
+def magnitude_image_np(x):
+    """utils/tensor_transforms.py:78-99: complex_abs, then min-max to (0, 1)."""
+    m = complex_abs_np(np.asarray(x, dtype=np.float32))
+    b, c, h, w = m.shape
+    out = m.reshape(b, c, h * w)
+    minimum = out.min(axis=2, keepdims=True)
+    out = out - minimum
+    maximum = out.max(axis=2, keepdims=True)
+    return (out / maximum).reshape(b, c, h, w)
+
+
+def refinement_real_penalty_add_torch(out_pretrained, out_learnable, scale):
+    """models/refinement_wrapper.py:173-197 with the learnable model's output
+    given: the real channel of the (detached) pretrained output is scaled to
+    (-1, 1), ``scale * out_learnable`` is added, the sum is mapped back with the
+    same min / max; the imaginary channel passes through.  torch, so that
+    autograd supplies the reference gradients."""
+    import torch
+    real = out_pretrained[:, 0].unsqueeze(1).contiguous()
+    imag = out_pretrained[:, 1].unsqueeze(1).contiguous()
+    b, c, h, w = real.shape
+    out = real.view(b, c, h * w)
+    minimum, _ = out.min(dim=2, keepdim=True)
+    out = out - minimum
+    maximum, _ = out.max(dim=2, keepdim=True)
+    out = out / maximum
+    scaled = (out * 2 - 1).view(b, c, h, w)
+    refined = scaled + scale * out_learnable
+    o = refined.view(b, c, h * w)
+    o = (o + 1) / 2
+    o = o * maximum + minimum
+    return torch.cat((o.view(b, c, h, w), imag), dim=1)

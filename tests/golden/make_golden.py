@@ -16,6 +16,10 @@ Everything stored here is an output of unmodified reference code imported from
   list, recnet.py:128-134) swapped for an op that chains the reference blend
   with ``torch.fft`` (the reference's own FFT wrapper is CUDA-only).
 
+* ``_scale`` / ``_unscale`` / ``_refinement_real_penalty_add``
+  models/refinement_wrapper.py:51-92,173-197 and ``magnitude_image``
+  utils/tensor_transforms.py:78-99
+
 The fixtures are small (< 1 MB in total) and are what pins ``oracle/``.
 """
 import os
@@ -185,6 +189,29 @@ def main():
                 out_pred=op.numpy(), out_target=ot.numpy(),
                 psnr=np.float64(10. * np.log10(1. / torch.nn.functional.mse_loss(op, ot).item())))
     np.savez_compressed(os.path.join(HERE, 'loader_tail.npz'), **tail)
+
+    # ---- 7. refinement-path pointwise ops (models/refinement_wrapper.py:51-92,173-197,
+    #         utils/tensor_transforms.py:78-99) ------------------------------------
+    import models.refinement_wrapper as rw
+    from utils.tensor_transforms import magnitude_image
+    xs = torch.from_numpy((rs.normal(size=(3, 2, 32, 48)) * 1.3 + 0.2).astype(np.float32))
+    scaled, mn, mx = rw._scale(xs)
+    ref = {'x': xs.numpy(), 'scaled': scaled.numpy(), 'minimum': mn.numpy(),
+           'maximum': mx.numpy(), 'unscaled': rw._unscale(scaled * 1.5, mn, mx).numpy(),
+           'magnitude_image': magnitude_image(xs).numpy()}
+    pre = torch.from_numpy(rs.normal(size=(3, 2, 32, 48)).astype(np.float32))
+    learn = torch.from_numpy((rs.normal(size=(3, 1, 32, 48)) * 0.3).astype(np.float32))
+    learn.requires_grad_(True)
+    scale_p = torch.nn.Parameter(torch.tensor([0.37]))
+    fake_self = types.SimpleNamespace(scale=scale_p, learnable_model=lambda inp: learn,
+                                      _learnable_model_input_fn=lambda inp, out: inp)
+    res = rw.RefinementWrapper._refinement_real_penalty_add(fake_self, None, pre)
+    cot = torch.from_numpy(rs.normal(size=(3, 2, 32, 48)).astype(np.float32))
+    (res['pred'] * cot).sum().backward()
+    ref.update(pre=pre.numpy(), learn=learn.detach().numpy(), scale=scale_p.detach().numpy(),
+               pred=res['pred'].detach().numpy(), cot=cot.numpy(),
+               grad_learn=learn.grad.numpy(), grad_scale=scale_p.grad.numpy())
+    np.savez_compressed(os.path.join(HERE, 'refinement_ops.npz'), **ref)
 
     tot = sum(os.path.getsize(os.path.join(HERE, f))
               for f in os.listdir(HERE) if f.endswith('.npz'))

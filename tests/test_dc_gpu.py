@@ -551,3 +551,45 @@ def test_loader_hands_over_the_dc_plan(monkeypatch):
     # a noisy layer is a different plan: it does need the prepare pass
     with pytest.raises(AssertionError):
         myfft.DataConsistencyInKspace(noise_lvl=0.1).perform(x, batch['kspace'], batch['mask'])
+
+
+def test_refinement_ops_gpu(golden_dir):
+    """scale / unscale / magnitude_image / refinement_real_penalty_add against the
+    reference-generated fixture (bit-exact where torch CPU and CUDA round alike)
+    and against the oracle at an odd, non-square size."""
+    from csmri_refinement_b200 import refinement_ops as ro
+    g = np.load(os.path.join(golden_dir, 'refinement_ops.npz'))
+    x = torch.from_numpy(g['x']).cuda()
+    s, mn, mx = ro.scale(x)
+    assert mn.shape == (3, 2, 1) and mx.shape == (3, 2, 1)
+    assert np.array_equal(mn.cpu().numpy(), g['minimum'])
+    assert np.array_equal(mx.cpu().numpy(), g['maximum'])
+    assert np.array_equal(s.cpu().numpy(), g['scaled'])
+    assert np.array_equal(ro.unscale(s * 1.5, mn, mx).cpu().numpy(), g['unscaled'])
+    assert np.array_equal(ro.magnitude_image(x).cpu().numpy(), orc.magnitude_image_np(g['x']))
+
+    pre = torch.from_numpy(g['pre']).cuda()
+    learn = torch.from_numpy(g['learn']).cuda().requires_grad_(True)
+    sc = torch.nn.Parameter(torch.from_numpy(g['scale']).cuda())
+    res = ro.refinement_real_penalty_add(pre, learn, sc)
+    assert set(res) == {'pred', 'pretrained', 'prescaled_refinement', 'scaled_refinement'}
+    (res['pred'] * torch.from_numpy(g['cot']).cuda()).sum().backward()
+    assert np.array_equal(res['pred'].detach().cpu().numpy(), g['pred'])
+    assert np.array_equal(learn.grad.cpu().numpy(), g['grad_learn'])
+    np.testing.assert_allclose(sc.grad.cpu().numpy(), g['grad_scale'], rtol=1e-5)
+
+    # odd, non-square, negative-heavy planes; B*C planes > chunks
+    rs = np.random.RandomState(5)
+    y = (rs.normal(size=(5, 3, 37, 53)) * 3 - 2).astype(np.float32)
+    s2, mn2, mx2 = ro.scale(torch.from_numpy(y).cuda())
+    so, mno, mxo = orc.scale_np(y)
+    assert np.array_equal(mn2.cpu().numpy(), mno) and np.array_equal(mx2.cpu().numpy(), mxo)
+    assert np.array_equal(s2.cpu().numpy(), so)
+    big = torch.randn(2, 1, 512, 512, device='cuda')
+    s3, mn3, mx3 = ro.scale(big)
+    assert s3.min().item() == -1.0 and s3.max().item() == 1.0
+    assert torch.equal(mn3.flatten(), big.flatten(1).min(1).values)
+    with pytest.raises(RuntimeError):
+        ro.scale(torch.zeros(1, 1, 4, 4))                    # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        ro.refinement_real_penalty_add(pre.clone().requires_grad_(True), learn, sc)
