@@ -54,6 +54,18 @@ def test_abi_rejects_bad_arguments_without_touching_the_gpu(built_lib):
         built_lib.check(lib.csmri_fft2(8, 8, 1, 48, 48, 0, 8, None))
 
 
+def test_header_is_plain_c_and_usable_without_python(built_lib, tmp_path):
+    """include/csmri_dc.h compiles as pedantic C99 and a dlopen client gets the
+    documented error codes (tests/abi_client.c)."""
+    exe = str(tmp_path / 'abi_client')
+    subprocess.run(['gcc', '-std=c99', '-pedantic', '-Wall', '-Wextra', '-Werror',
+                    '-I', os.path.join(ROOT, 'include'), '-o', exe,
+                    os.path.join(ROOT, 'tests', 'abi_client.c'), '-ldl'], check=True)
+    out = subprocess.run([exe, built_lib.LIB_PATH], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert 'abi ok' in out.stdout
+
+
 def test_sass_is_blackwell_native(built_lib):
     """The hot kernel uses the packed fp32 pipe (FFMA2/FADD2, sm_100 only)."""
     sass = subprocess.run(['cuobjdump', '-sass', built_lib.LIB_PATH], capture_output=True,
