@@ -161,7 +161,8 @@ def recnet_train_bench(dev, rank, world, steps=8, warmup=3, batch=32, n=256, blo
                       'flat-bucket NCCL allreduce (%d bytes)' % (
                           blocks, convs, filters, batch, n, n,
                           'cuDNN convs with TF32 tensor cores (torch default; not parity-gated)'
-                          if tf32 else 'fp32 convs (cuDNN, TF32 off)', trainer.bucket.nbytes()),
+                          if tf32 else 'fp32 convs (cuDNN forward / data gradient, TF32 off; weight '
+                          'gradient = csmri_conv3x3_wgrad)', trainer.bucket.nbytes()),
             'loss': float(loss.item())}
 
 

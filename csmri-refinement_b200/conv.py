@@ -1,0 +1,95 @@
+"""nn.Conv2d whose weight gradient runs through ``csmri_conv3x3_wgrad``.
+
+RecNet's convolutions (models/recnet.py:37-48) stay what they are in the
+reference - ``torch.nn.Conv2d`` modules with the same parameters, state-dict
+keys and forward arithmetic (cuDNN).  Only the backward-weight product of the
+fp32 training step (training/runner.py:154-178) is rerouted: cuDNN's kernel for
+these shapes is 64 % of the whole D5C5 step on a B200
+(profiles/r1_recnet_step_kernels.txt).  Covered: channel counts that are
+multiples of 32 on both sides, and RecNet's thin first / last layers (2 -> 32,
+32 -> 2).  Anything else (other kernel sizes, strides, dilations, CPU tensors)
+keeps torch's own backward.
+"""
+import torch
+from torch import nn
+
+from . import _lib
+
+_ENABLED = True
+
+
+def set_fast_wgrad(flag):
+    """Switch the hand-written weight gradient on / off (A/B timing, tests)."""
+    global _ENABLED
+    _ENABLED = bool(flag)
+
+
+def conv3x3_wgrad(x, grad_out, pad):
+    """dW (CO,CI,3,3) of a stride-1 3x3 convolution; x (N,CI,H+2-2*pad,W+2-2*pad),
+    grad_out (N,CO,H,W), float32 CUDA."""
+    x, grad_out = x.contiguous(), grad_out.contiguous()
+    n, ci = x.shape[0], x.shape[1]
+    co, h, w = grad_out.shape[1], grad_out.shape[2], grad_out.shape[3]
+    lib = _lib.lib()
+    with torch.cuda.device(x.device):
+        dw = torch.empty((co, ci, 3, 3), dtype=torch.float32, device=x.device)
+        ws = torch.empty((lib.csmri_conv3x3_wgrad_workspace_bytes(ci, co) // 4,),
+                         dtype=torch.float32, device=x.device)
+        _lib.check(lib.csmri_conv3x3_wgrad(
+            x.data_ptr(), grad_out.data_ptr(), dw.data_ptr(), ws.data_ptr(), n, ci, co, h, w,
+            int(pad), torch.cuda.current_stream().cuda_stream))
+    return dw
+
+
+def _eligible(x, weight, stride, padding, dilation, groups):
+    if not (_ENABLED and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32):
+        return False
+    if tuple(weight.shape[2:]) != (3, 3) or groups != 1:
+        return False
+    if tuple(stride) != (1, 1) or tuple(dilation) != (1, 1) or tuple(padding) not in ((0, 0), (1, 1)):
+        return False
+    co, ci = weight.shape[0], weight.shape[1]
+    h = x.shape[2] - 2 + 2 * padding[0]
+    w = x.shape[3] - 2 + 2 * padding[1]
+    if h <= 0 or w <= 0 or w % 32 != 0:
+        return False
+    if (ci, co) in ((2, 32), (32, 2)):          # RecNet's first / last layer of a block
+        return h % 16 == 0
+    return ci % 32 == 0 and co % 32 == 0 and h % 4 == 0
+
+
+class _Conv3x3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, pad):
+        ctx.save_for_backward(x, weight)
+        ctx.pad = pad
+        ctx.has_bias = bias is not None
+        return torch.ops.aten.convolution(x, weight, bias, [1, 1], [pad, pad], [1, 1], False,
+                                          [0, 0], 1)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        pad = ctx.pad
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        grad_out = grad_out.contiguous()
+        gx = gb = gw = None
+        if need_x or need_b:
+            gx, _, gb = torch.ops.aten.convolution_backward(
+                grad_out, x, weight, [weight.shape[0]], [1, 1], [pad, pad], [1, 1], False, [0, 0],
+                1, [need_x, False, need_b])
+        if need_w:
+            gw = conv3x3_wgrad(x, grad_out, pad)
+        return gx, gw, gb, None
+
+
+class Conv2d(nn.Conv2d):
+    """Drop-in ``nn.Conv2d``: same constructor, parameters and forward values."""
+
+    def forward(self, x):
+        if self.padding_mode == 'zeros' and not isinstance(self.padding, str) and \
+                _eligible(x, self.weight, self.stride, self.padding, self.dilation, self.groups) \
+                and torch.is_grad_enabled() and self.weight.requires_grad:
+            return _Conv3x3.apply(x, self.weight, self.bias, int(self.padding[0]))
+        return super(Conv2d, self).forward(x)

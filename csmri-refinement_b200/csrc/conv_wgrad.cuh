@@ -1,0 +1,296 @@
+// Weight gradient of RecNet's 3x3 convolutions (models/recnet.py:37-48), fp32.
+//
+//   dW[co][ci][ky][kx] = sum_{n,y,x} dY[n][co][y][x] * X[n][ci][y + ky - p][x + kx - p]
+//
+// Why it is here: in the fp32 training step (training/runner.py:154-178) cuDNN's
+// weight-gradient kernel for this shape (32 -> 32 channels, batch 32, 256^2) runs
+// at ~15 TFLOP/s and is HALF of the whole step (profiles/r1_recnet_step_kernels.txt);
+// the DC operator, the subject of this library, is 0.2 % of it.
+//
+// The product is a (CO x 9*CI) GEMM with a huge reduction dimension (all
+// pixels), so the CTAs split the pixels: each one accumulates the complete
+// 32 x 32 x 9 block of weight gradients for its tiles in registers (36 per
+// thread: lane = input channel, warp = group of 4 output channels, 9 taps) and
+// the partial blocks are summed by a second kernel in a fixed order
+// (deterministic, no atomics).  Per pixel a thread issues 18 packed FFMA2
+// (two output channels per instruction), fed by one broadcast LDS.128 of dY and
+// three conflict-free LDS of the sliding 3x3 input window: the FP32 pipe is the
+// bound, shared memory and issue slots stay below it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft_regs.cuh"
+
+namespace csmri {
+
+constexpr int kWgC = 32;                    // channel block (input and output)
+constexpr int kWgTW = 32, kWgTH = 4;        // output pixels per tile
+constexpr int kWgPR = kWgTH + 2, kWgPC = kWgTW + 2;
+constexpr int kWgXS = kWgC + 1;             // input patch [row][col][ci], ci-stride 1, col-stride 33
+constexpr int kWgDS = 36;                   // dY tile [pixel][co], pixel-stride 36 (16-byte aligned rows)
+constexpr int kWgSmemFloats = kWgPR * kWgPC * kWgXS + kWgTH * kWgTW * kWgDS;
+constexpr int kWgBlock = kWgC * kWgC * 9;   // floats per partial block
+
+// 4-byte asynchronous copy global -> shared (LDGSTS); !valid writes a zero.  All
+// ~42 copies a thread makes for a tile are in flight together: the first version
+// loaded through registers inside a loop and spent more time waiting for those
+// serialised loads than computing (1.29 ms per layer, now see profiles/).
+__device__ __forceinline__ void wg_copy4(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(valid ? 4 : 0)
+               : "memory");
+}
+
+// grid: (CTAs sharing the pixel tiles, CO / 32, CI / 32); block: 256
+__global__ void __launch_bounds__(256, 4)
+    conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                         float* __restrict__ partial, int CI, int CO, int H, int W, int HI, int WI,
+                         int pad, int tiles_x, int tiles_y, int ntiles) {
+  extern __shared__ __align__(16) float wg_smem[];
+  float* X_s = wg_smem;
+  float* D_s = wg_smem + kWgPR * kWgPC * kWgXS;
+  const int lane = threadIdx.x & 31;        // input channel within the block
+  const int warp = threadIdx.x >> 5;        // group of four output channels
+  const int co0 = blockIdx.y * kWgC, ci0 = blockIdx.z * kWgC;
+
+  cf acc[9][2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = mk(0.0f, 0.0f);
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / (tiles_x * tiles_y);
+    const int rem = tile - n * tiles_x * tiles_y;
+    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const int y0 = ty * kWgTH, x0 = tx * kWgTW;
+    __syncthreads();   // everyone is done with the previous tile
+    // Warp w stages input channels 4w .. 4w+3 (6 patch rows each) and dY channels
+    // 4w .. 4w+3 (4 rows each), lanes along x.  Everything but the per-tile base
+    // pointer and the edge predicates is a compile-time offset: the first version
+    // recomputed (channel, row) from a loop counter and spent 28 % of the kernel's
+    // instructions (on the same pipe as the FFMA2s) on address arithmetic.
+    {
+      // column / row indices are clamped into the image so that every source
+      // address is valid; out-of-image elements are copies of size 0 (zero fill)
+      const int gx = x0 + lane - pad, gx2 = gx + kWgTW;
+      const bool ok0 = gx >= 0 && gx < WI;
+      const bool ok1 = gx2 >= 0 && gx2 < WI;
+      const int cx0 = min(max(gx, 0), WI - 1), cx1 = min(max(gx2, 0), WI - 1);
+      const size_t chs = (size_t)HI * WI;
+      const float* src_c = x + ((size_t)n * CI + ci0 + warp * 4) * chs;
+      float* dst_c = X_s + lane * kWgXS + warp * 4;
+#pragma unroll
+      for (int r = 0; r < kWgPR; ++r) {
+        const int gy = y0 + r - pad;
+        const bool row_ok = gy >= 0 && gy < HI;
+        const float* src = src_c + (size_t)min(max(gy, 0), HI - 1) * WI;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float* dst = dst_c + r * kWgPC * kWgXS + c;
+          wg_copy4(dst, src + cx0, row_ok && ok0);
+          if (lane < 2) wg_copy4(dst + kWgTW * kWgXS, src + cx1, row_ok && ok1);
+          src += chs;
+        }
+      }
+      const size_t ohs = (size_t)H * W;
+      const float* dsrc = dy + (((size_t)n * CO + co0 + warp * 4) * H + y0) * W + x0 + lane;
+      float* ddst = D_s + lane * kWgDS + warp * 4;
+#pragma unroll
+      for (int r = 0; r < kWgTH; ++r) {
+        const float* src = dsrc + (size_t)r * W;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          wg_copy4(ddst + r * kWgTW * kWgDS + c, src, true);
+          src += ohs;
+        }
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < kWgTH; ++r) {
+      cf w[3][3];   // sliding window, every value duplicated into both halves of a pair
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const float a = X_s[((r + ky) * kWgPC + 0) * kWgXS + lane];
+        const float b = X_s[((r + ky) * kWgPC + 1) * kWgXS + lane];
+        w[ky][1] = mk(a, a);
+        w[ky][2] = mk(b, b);
+      }
+#pragma unroll
+      for (int xx = 0; xx < kWgTW; ++xx) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float c = X_s[((r + ky) * kWgPC + xx + 2) * kWgXS + lane];
+          w[ky][0] = w[ky][1];
+          w[ky][1] = w[ky][2];
+          w[ky][2] = mk(c, c);
+        }
+        const float4 d = *reinterpret_cast<const float4*>(&D_s[(r * kWgTW + xx) * kWgDS + warp * 4]);
+        const cf d01 = mk(d.x, d.y), d23 = mk(d.z, d.w);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            acc[ky * 3 + kx][0] = f2fma(d01, w[ky][kx], acc[ky * 3 + kx][0]);
+            acc[ky * 3 + kx][1] = f2fma(d23, w[ky][kx], acc[ky * 3 + kx][1]);
+          }
+      }
+    }
+  }
+  // partial block in dW order: [co][ci][tap]
+  float* dst = partial +
+               ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kWgBlock;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    dst[((warp * 4 + 0) * kWgC + lane) * 9 + t] = acc[t][0].x;
+    dst[((warp * 4 + 1) * kWgC + lane) * 9 + t] = acc[t][0].y;
+    dst[((warp * 4 + 2) * kWgC + lane) * 9 + t] = acc[t][1].x;
+    dst[((warp * 4 + 3) * kWgC + lane) * 9 + t] = acc[t][1].y;
+  }
+}
+
+// dw[co][ci][tap] = sum over the `nparts` partial blocks of its channel-block pair
+// grid: (36, CO / 32, CI / 32); block 256
+__global__ void __launch_bounds__(256)
+    conv3x3_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int CI,
+                                int nparts) {
+  const int e = blockIdx.x * 256 + threadIdx.x;         // element of the 32 x 32 x 9 block
+  const float* src = partial + (size_t)(blockIdx.z * gridDim.y + blockIdx.y) * nparts * kWgBlock + e;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  int p = 0;
+  for (; p + 4 <= nparts; p += 4) {
+    s0 += src[(size_t)p * kWgBlock];
+    s1 += src[(size_t)(p + 1) * kWgBlock];
+    s2 += src[(size_t)(p + 2) * kWgBlock];
+    s3 += src[(size_t)(p + 3) * kWgBlock];
+  }
+  for (; p < nparts; ++p) s0 += src[(size_t)p * kWgBlock];
+  const int co = e / (kWgC * 9), r = e - co * (kWgC * 9);
+  const int ci = r / 9, t = r - ci * 9;
+  dw[((size_t)(blockIdx.y * kWgC + co) * CI + blockIdx.z * kWgC + ci) * 9 + t] = (s0 + s1) + (s2 + s3);
+}
+
+
+// ---------------------------------------------------------------------------
+// Thin layers: RecNet's first (2 -> 32) and last (32 -> 2) convolution of every
+// block.  Only 576 weight gradients, so the work is streaming x and dY once
+// (HBM-bound; cuDNN needs ~1 ms per layer, the traffic is worth ~50 us).
+// Lanes own pixels (coalesced row segments straight from global memory, no
+// staging), the 8 warps split the wide channel dimension, a thread keeps
+// CIT * COT * 9 = 72 accumulators and a sliding 3 x 3 window per input channel;
+// lanes are folded with shuffles once per CTA, CTAs by the reduce kernel.
+//   WIDE_OUT: CI = CIT = 2,  CO = 8 * COT = 32   (warp = group of 4 output channels)
+//  !WIDE_OUT: CI = 8 * CIT = 32, CO = COT = 2    (warp = group of 4 input channels)
+// ---------------------------------------------------------------------------
+constexpr int kWtRows = 16;                  // rows per tile (tile = 32 x 16 pixels)
+
+template <int CIT, int COT, bool WIDE_OUT>
+__global__ void __launch_bounds__(256, 2)
+    conv3x3_wgrad_thin_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                              float* __restrict__ partial, int H, int W, int HI, int WI, int pad,
+                              int tiles_x, int tiles_y, int ntiles) {
+  constexpr int CI = WIDE_OUT ? CIT : 8 * CIT;
+  constexpr int CO = WIDE_OUT ? 8 * COT : COT;
+  static_assert(COT % 2 == 0, "output channels are processed in pairs");
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int cib = WIDE_OUT ? 0 : warp * CIT;
+  const int cob = WIDE_OUT ? warp * COT : 0;
+
+  cf acc[CIT][9][COT / 2];
+#pragma unroll
+  for (int c = 0; c < CIT; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int o = 0; o < COT / 2; ++o) acc[c][t][o] = mk(0.0f, 0.0f);
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = tile / (tiles_x * tiles_y);
+    const int rem = tile - n * tiles_x * tiles_y;
+    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const int y0 = ty * kWtRows, gx0 = tx * 32 + lane - pad;
+    const float* xn = x + ((size_t)n * CI + cib) * HI * WI;
+    const float* dn = dy + (((size_t)n * CO + cob) * H + y0) * W + tx * 32 + lane;
+    auto load_row = [&](int c, int gy, float* dst) {   // x[c][gy][gx0 .. gx0 + 2], zero outside
+      const bool row_ok = gy >= 0 && gy < HI;
+      const float* src = xn + ((size_t)c * HI + (row_ok ? gy : 0)) * WI;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int gx = gx0 + kx;
+        dst[kx] = (row_ok && gx >= 0 && gx < WI) ? __ldg(src + gx) : 0.0f;
+      }
+    };
+    float win[CIT][3][3];
+#pragma unroll
+    for (int c = 0; c < CIT; ++c) {
+      load_row(c, y0 - pad, win[c][1]);
+      load_row(c, y0 - pad + 1, win[c][2]);
+    }
+#pragma unroll 2
+    for (int r = 0; r < kWtRows; ++r) {
+      float d[COT];
+#pragma unroll
+      for (int o = 0; o < COT; ++o) d[o] = __ldg(dn + ((size_t)o * H + r) * W);
+#pragma unroll
+      for (int c = 0; c < CIT; ++c) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          win[c][0][kx] = win[c][1][kx];
+          win[c][1][kx] = win[c][2][kx];
+        }
+        load_row(c, y0 + r + 2 - pad, win[c][2]);
+      }
+#pragma unroll
+      for (int c = 0; c < CIT; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int o = 0; o < COT / 2; ++o)
+              acc[c][ky * 3 + kx][o] = f2fma(mk(d[2 * o], d[2 * o + 1]),
+                                             mk(win[c][ky][kx], win[c][ky][kx]),
+                                             acc[c][ky * 3 + kx][o]);
+    }
+  }
+  // fold the 32 pixels-lanes, then lane 0 writes the warp's 72 sums in dW order [co][ci][tap]
+  float* dst = partial + (size_t)blockIdx.x * (CI * CO * 9);
+#pragma unroll
+  for (int c = 0; c < CIT; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int o = 0; o < COT / 2; ++o) {
+        float a = acc[c][t][o].x, b = acc[c][t][o].y;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, m);
+          b += __shfl_xor_sync(0xffffffffu, b, m);
+        }
+        if (lane == 0) {
+          dst[((cob + 2 * o) * CI + cib + c) * 9 + t] = a;
+          dst[((cob + 2 * o + 1) * CI + cib + c) * 9 + t] = b;
+        }
+      }
+}
+
+// dw[e] = sum_p partial[p][e], e < n_elem (fixed order)
+__global__ void __launch_bounds__(64)
+    wgrad_thin_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int n_elem,
+                             int nparts) {
+  const int e = blockIdx.x * 64 + threadIdx.x;
+  if (e >= n_elem) return;
+  float s0 = 0.0f, s1 = 0.0f;
+  int p = 0;
+  for (; p + 2 <= nparts; p += 2) {
+    s0 += partial[(size_t)p * n_elem + e];
+    s1 += partial[(size_t)(p + 1) * n_elem + e];
+  }
+  if (p < nparts) s0 += partial[(size_t)p * n_elem + e];
+  dw[e] = s0 + s1;
+}
+
+}  // namespace csmri

@@ -46,6 +46,7 @@
 #include "dc_pipe.cuh"
 #include "dc_pipev.cuh"
 #include "refine_ops.cuh"
+#include "conv_wgrad.cuh"
 
 namespace csmri {
 
@@ -1394,6 +1395,84 @@ int csmri_refine_real_penalty_add_backward(const float* grad_pred, const float* 
   CSMRI_TRY(check_ptr(grad_scale_partial, "grad_scale_partial"));
   refine_backward_kernel<<<dim3(kRefinePartials, B), 256, 0, (cudaStream_t)stream>>>(
       grad_pred, learnable, scale, maximum, grad_learnable, grad_scale_partial, H * W);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+// ---- 3x3 convolution weight gradient (conv_wgrad.cuh) --------------------------
+static const int kWgMaxCtas = 640;   // >= 4 resident CTAs on each of up to 160 SMs
+
+static bool wgrad_thin(int CI, int CO) { return (CI == 2 && CO == 32) || (CI == 32 && CO == 2); }
+
+static int wgrad_check_channels(int CI, int CO) {
+  if (wgrad_thin(CI, CO)) return CSMRI_OK;
+  if (CI <= 0 || CO <= 0 || CI % kWgC != 0 || CO % kWgC != 0 || CI > 1024 || CO > 1024)
+    return fail(CSMRI_E_SHAPE,
+                "conv3x3_wgrad needs CI and CO multiples of %d, or 2 -> 32 / 32 -> 2 (got %d, %d)",
+                kWgC, CI, CO);
+  return CSMRI_OK;
+}
+
+static int wgrad_parts(int CI, int CO, int cap) {
+  const int blocks = (CI / kWgC) * (CO / kWgC);
+  const int parts = cap / blocks;
+  return parts < 1 ? 1 : parts;
+}
+
+size_t csmri_conv3x3_wgrad_workspace_bytes(int CI, int CO) {
+  if (wgrad_check_channels(CI, CO) != CSMRI_OK) return 0;
+  if (wgrad_thin(CI, CO)) return (size_t)kWgMaxCtas * CI * CO * 9 * sizeof(float);
+  return (size_t)wgrad_parts(CI, CO, kWgMaxCtas) * (CI / kWgC) * (CO / kWgC) * kWgBlock *
+         sizeof(float);
+}
+
+int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* workspace, int N, int CI,
+                        int CO, int H, int W, int pad, void* stream) {
+  CSMRI_TRY(wgrad_check_channels(CI, CO));
+  const bool thin = wgrad_thin(CI, CO);
+  const int th = thin ? kWtRows : kWgTH;
+  if (N <= 0 || H <= 0 || W <= 0 || H % th != 0 || W % kWgTW != 0)
+    return fail(CSMRI_E_SHAPE, "conv3x3_wgrad needs H %% %d == 0 and W %% %d == 0 (got %dx%dx%d)",
+                th, kWgTW, N, H, W);
+  if (pad != 0 && pad != 1) return fail(CSMRI_E_ARG, "pad must be 0 or 1 (got %d)", pad);
+  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr(dy, "dy"));
+  CSMRI_TRY(check_ptr(dw, "dw"));
+  CSMRI_TRY(check_ptr(workspace, "workspace"));
+  if (((uintptr_t)dy & 15u) != 0) return fail(CSMRI_E_ALIGN, "dy is not 16-byte aligned");
+  const int tiles_x = W / kWgTW, tiles_y = H / th;
+  const long long ntiles_ll = (long long)N * tiles_x * tiles_y;
+  if (ntiles_ll > 0x7fffffffLL) return fail(CSMRI_E_SHAPE, "too many tiles");
+  const int ntiles = (int)ntiles_ll;
+  int cap = sm_count() * 4;
+  if (cap > kWgMaxCtas) cap = kWgMaxCtas;
+  int parts = wgrad_parts(CI, CO, cap);
+  if (parts > ntiles) parts = ntiles;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (thin) {
+    int ctas = sm_count() * 2;
+    if (ctas > kWgMaxCtas) ctas = kWgMaxCtas;
+    if (ctas > ntiles) ctas = ntiles;
+    const int HI = H + 2 - 2 * pad, WI = W + 2 - 2 * pad;
+    if (CI == 2)
+      conv3x3_wgrad_thin_kernel<2, 4, true><<<ctas, 256, 0, s>>>(
+          x, dy, (float*)workspace, H, W, HI, WI, pad, tiles_x, tiles_y, ntiles);
+    else
+      conv3x3_wgrad_thin_kernel<4, 2, false><<<ctas, 256, 0, s>>>(
+          x, dy, (float*)workspace, H, W, HI, WI, pad, tiles_x, tiles_y, ntiles);
+    wgrad_thin_reduce_kernel<<<(CI * CO * 9 + 63) / 64, 64, 0, s>>>((const float*)workspace, dw,
+                                                                    CI * CO * 9, ctas);
+    CSMRI_CUDA(cudaGetLastError());
+    return CSMRI_OK;
+  }
+  constexpr int smem = kWgSmemFloats * (int)sizeof(float);
+  CSMRI_TRY(set_smem(conv3x3_wgrad_kernel, smem));
+  const dim3 grid(parts, CO / kWgC, CI / kWgC);
+  conv3x3_wgrad_kernel<<<grid, 256, smem, s>>>(x, dy, (float*)workspace, CI, CO, H, W,
+                                               H + 2 - 2 * pad, W + 2 - 2 * pad, pad, tiles_x,
+                                               tiles_y, ntiles);
+  conv3x3_wgrad_reduce_kernel<<<dim3(kWgBlock / 256, CO / kWgC, CI / kWgC), 256, 0, s>>>(
+      (const float*)workspace, dw, CI, parts);
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }

@@ -15,7 +15,10 @@ What differs is only how the work is issued:
 * zero "same" padding is given to cuDNN as the convolution's own padding
   instead of a separate ZeroPad2d pass over HBM (an ``nn.Identity`` keeps the
   Sequential indices, hence the checkpoint keys, unchanged).
-The convolutions stay cuDNN fp32 through torch.
+The convolutions stay cuDNN fp32 through torch, except for the
+weight gradient of the 3x3 layers between equal multiples of 32 channels, which
+:mod:`csmri_refinement_b200.conv` computes with its own kernel (cuDNN's is half
+of the fp32 training step on a B200).
 """
 import math
 
@@ -23,6 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import myfft
+from .conv import Conv2d
 
 RECNET_REQUIRED_PARAMS = ['num_blocks', 'num_convs', 'num_filters']
 RECNET_OPTIONAL_PARAMS = ['num_final_outputs', 'dilations_per_conv', 'kernel_size',
@@ -42,15 +46,15 @@ def _pad_and_conv(in_ch, out_ch, kernel_size, dilation, mode):
     total = _same_padding(kernel_size, dilation)
     side = total // 2
     if mode == 'zero' and total % 2 == 0:
-        return nn.Identity(), nn.Conv2d(in_ch, out_ch, kernel_size=kernel_size, stride=1,
-                                        bias=True, dilation=dilation, padding=side)
+        return nn.Identity(), Conv2d(in_ch, out_ch, kernel_size=kernel_size, stride=1,
+                                     bias=True, dilation=dilation, padding=side)
     layers = {'zero': nn.ZeroPad2d, 'reflection': nn.ReflectionPad2d,
               'replication': nn.ReplicationPad2d}
     if mode not in layers:
         raise ValueError('Unknown padding mode %r' % (mode,))
     pad = side if total % 2 == 0 else (side, side + 1, side, side + 1)
-    return layers[mode](pad), nn.Conv2d(in_ch, out_ch, kernel_size=kernel_size, stride=1,
-                                        bias=True, dilation=dilation)
+    return layers[mode](pad), Conv2d(in_ch, out_ch, kernel_size=kernel_size, stride=1,
+                                     bias=True, dilation=dilation)
 
 
 class ConvBlock(nn.Module):

@@ -199,6 +199,24 @@ int csmri_refine_real_penalty_add_backward(const float* grad_pred, const float* 
                                            float* grad_learnable, float* grad_scale_partial,
                                            int B, int H, int W, void* stream);
 
+/* ---- training step: weight gradient of RecNet's 3x3 convolutions --------------
+ * The backward-weight half of torch.nn.Conv2d(CI, CO, 3, stride=1) as RecNet
+ * builds it (models/recnet.py:37-48), i.e. what autograd computes for `weight`
+ * in Runner._train_step (training/runner.py:154-178):
+ *   dw[co][ci][ky][kx] = sum_{n,y,x} dy[n][co][y][x] * x[n][ci][y+ky-pad][x+kx-pad]
+ *   x  (N, CI, H + 2 - 2*pad, W + 2 - 2*pad)   pad = 0: input already padded by the
+ *                                              reference's ZeroPad2d layer; pad = 1:
+ *                                              zero padding inside the convolution
+ *   dy (N, CO, H, W);  dw (CO, CI, 3, 3), overwritten;  fp32 throughout, summed in a
+ *   fixed order (deterministic).
+ * CI and CO multiples of 32 with H a multiple of 4, or the thin layers 2 -> 32 and
+ * 32 -> 2 with H a multiple of 16; W a multiple of 32.  Anything else is
+ * CSMRI_E_SHAPE (the caller keeps its own convolution backend for those).
+ * workspace: csmri_conv3x3_wgrad_workspace_bytes(CI, CO) bytes of device memory. */
+size_t csmri_conv3x3_wgrad_workspace_bytes(int CI, int CO);
+int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* workspace,
+                        int N, int CI, int CO, int H, int W, int pad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -593,3 +593,56 @@ def test_refinement_ops_gpu(golden_dir):
         ro.scale(torch.zeros(1, 1, 4, 4))                    # CPU tensor: no fallback
     with pytest.raises(RuntimeError):
         ro.refinement_real_penalty_add(pre.clone().requires_grad_(True), learn, sc)
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 32, 32, 32, 1), (2, 32, 32, 8, 64, 0),
+                                   (3, 64, 32, 36, 96, 1), (1, 32, 64, 4, 32, 1),
+                                   (2, 2, 32, 32, 64, 1), (3, 32, 2, 16, 32, 1),
+                                   (2, 2, 32, 16, 96, 0), (2, 32, 2, 48, 32, 0)])
+def test_conv3x3_wgrad_matches_torch(shape):
+    """csmri_conv3x3_wgrad against autograd's fp32 weight gradient (TF32 off) and an
+    fp64 evaluation: (N, CI, CO, H, W, pad)."""
+    from csmri_refinement_b200 import conv
+    n, ci, co, h, w, pad = shape
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device='cuda').manual_seed(sum(shape))
+    x = torch.randn(n, ci, h + 2 - 2 * pad, w + 2 - 2 * pad, device='cuda', generator=g)
+    gy = torch.randn(n, co, h, w, device='cuda', generator=g)
+    wt = torch.randn(co, ci, 3, 3, device='cuda', generator=g, dtype=torch.float64,
+                     requires_grad=True)
+    torch.nn.functional.conv2d(x.double(), wt, None, 1, pad).backward(gy.double())
+    got = conv.conv3x3_wgrad(x, gy, pad)
+    assert got.shape == (co, ci, 3, 3)
+    assert orc.rel_l2(got.cpu().numpy(), wt.grad.cpu().numpy()) < 2e-6
+    again = conv.conv3x3_wgrad(x, gy, pad)
+    assert torch.equal(got, again)                       # fixed summation order
+    with pytest.raises(RuntimeError):
+        conv.conv3x3_wgrad(x[:, :1], gy, pad)            # unsupported channel count
+
+
+def test_recnet_training_gradients_with_fast_wgrad():
+    """RecNet nf=32 loss gradients with the hand-written weight gradient vs torch's
+    own backward for every parameter (north_star gate: rel-L2 <= 1e-5)."""
+    myfft, ops, recnet, us = _mods()
+    from csmri_refinement_b200 import conv
+    torch.backends.cudnn.allow_tf32 = False
+    B, n = 2, 64
+    img = torch.rand(B, n, n, device='cuda')
+    rows = us.cartesian_rows((B, n, n), 4, 8, False, np.random.RandomState(4))
+    batch = us.undersample(img, rows)
+    torch.manual_seed(0)
+    net = recnet.construct_model({'num_blocks': 2, 'num_convs': 4, 'num_filters': 32}).cuda()
+    grads = {}
+    for fast in (True, False):
+        conv.set_fast_wgrad(fast)
+        net.zero_grad(set_to_none=True)
+        out = net(batch['inp'], batch['kspace'], batch['mask'])
+        torch.nn.functional.mse_loss(out, batch['target']).backward()
+        grads[fast] = {k: p.grad.clone() for k, p in net.named_parameters()}
+    conv.set_fast_wgrad(True)
+    used = 0
+    for k in grads[True]:
+        a, b = grads[True][k], grads[False][k]
+        assert (a - b).norm().item() <= 1e-5 * b.norm().item() + 1e-12, k
+        used += int(not torch.equal(a, b))
+    assert used >= 8          # thick and thin layers really took the other kernels
