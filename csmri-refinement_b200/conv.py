@@ -58,38 +58,94 @@ def _eligible(x, weight, stride, padding, dilation, groups):
     return ci % 32 == 0 and co % 32 == 0 and h % 4 == 0
 
 
+def _aligned16(t):
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
+def bias_lrelu_(z, bias, slope):
+    """z <- leaky_relu(z + bias[c], slope) in one pass, in place (z contiguous NCHW)."""
+    n, c, h, w = z.shape
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.lib().csmri_bias_lrelu(z.data_ptr(), bias.data_ptr(), n, c, h, w,
+                                               float(slope), torch.cuda.current_stream().cuda_stream))
+    return z
+
+
+def bias_lrelu_backward(grad_y, y, slope):
+    """-> (grad_z, grad_bias) from the forward OUTPUT y, one pass over grad_y and y."""
+    grad_y = _aligned16(grad_y.contiguous())
+    n, c, h, w = y.shape
+    with torch.cuda.device(y.device):
+        grad_z = torch.empty_like(y)
+        grad_b = torch.empty((c,), dtype=torch.float32, device=y.device)
+        partial = torch.empty((n * c * 8,), dtype=torch.float32, device=y.device)
+        _lib.check(_lib.lib().csmri_bias_lrelu_backward(
+            grad_y.data_ptr(), y.data_ptr(), grad_z.data_ptr(), grad_b.data_ptr(),
+            partial.data_ptr(), n, c, h, w, float(slope), torch.cuda.current_stream().cuda_stream))
+    return grad_z, grad_b
+
+
 class _Conv3x3(torch.autograd.Function):
+    """conv (+ bias) [+ LeakyReLU when ``slope`` is given]; forward and data gradient
+    stay cuDNN, the rest runs through libcsmri_dc."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, pad):
-        ctx.save_for_backward(x, weight)
-        ctx.pad = pad
+    def forward(ctx, x, weight, bias, pad, slope):
+        ctx.pad, ctx.slope = pad, slope
         ctx.has_bias = bias is not None
-        return torch.ops.aten.convolution(x, weight, bias, [1, 1], [pad, pad], [1, 1], False,
-                                          [0, 0], 1)
+        if slope is None:
+            ctx.save_for_backward(x, weight)
+            return torch.ops.aten.convolution(x, weight, bias, [1, 1], [pad, pad], [1, 1], False,
+                                              [0, 0], 1)
+        y = torch.ops.aten.convolution(x, weight, None, [1, 1], [pad, pad], [1, 1], False,
+                                       [0, 0], 1)
+        bias_lrelu_(y, bias, slope)
+        ctx.save_for_backward(x, weight, y)
+        return y
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, weight = ctx.saved_tensors
         pad = ctx.pad
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
         grad_out = grad_out.contiguous()
         gx = gb = gw = None
-        if need_x or need_b:
-            gx, _, gb = torch.ops.aten.convolution_backward(
-                grad_out, x, weight, [weight.shape[0]], [1, 1], [pad, pad], [1, 1], False, [0, 0],
-                1, [need_x, False, need_b])
+        if ctx.slope is None:
+            x, weight = ctx.saved_tensors
+            if need_x or need_b:
+                gx, _, gb = torch.ops.aten.convolution_backward(
+                    grad_out, x, weight, [weight.shape[0]], [1, 1], [pad, pad], [1, 1], False,
+                    [0, 0], 1, [need_x, False, need_b])
+        else:
+            x, weight, y = ctx.saved_tensors
+            grad_out, gb = bias_lrelu_backward(grad_out, y, ctx.slope)
+            if not need_b:
+                gb = None
+            if need_x:
+                gx = torch.ops.aten.convolution_backward(
+                    grad_out, x, weight, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
+                    [True, False, False])[0]
         if need_w:
             gw = conv3x3_wgrad(x, grad_out, pad)
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
 class Conv2d(nn.Conv2d):
-    """Drop-in ``nn.Conv2d``: same constructor, parameters and forward values."""
+    """Drop-in ``nn.Conv2d``: same constructor, parameters and forward values.
+    ``fused_slope`` (set by the owner, not a constructor argument) makes the
+    module apply the LeakyReLU that follows it in RecNet's blocks, so that bias
+    add and activation are one pass in both directions."""
+
+    fused_slope = None
 
     def forward(self, x):
+        slope = self.fused_slope
         if self.padding_mode == 'zeros' and not isinstance(self.padding, str) and \
                 _eligible(x, self.weight, self.stride, self.padding, self.dilation, self.groups) \
-                and torch.is_grad_enabled() and self.weight.requires_grad:
-            return _Conv3x3.apply(x, self.weight, self.bias, int(self.padding[0]))
-        return super(Conv2d, self).forward(x)
+                and torch.is_grad_enabled() and self.weight.requires_grad \
+                and (slope is None or (self.bias is not None and slope > 0)):
+            return _Conv3x3.apply(x, self.weight, self.bias, int(self.padding[0]), slope)
+        out = super(Conv2d, self).forward(x)
+        if slope is not None:
+            out = nn.functional.leaky_relu(out, slope, inplace=True)
+        return out

@@ -47,6 +47,7 @@
 #include "dc_pipev.cuh"
 #include "refine_ops.cuh"
 #include "conv_wgrad.cuh"
+#include "conv_epilogue.cuh"
 
 namespace csmri {
 
@@ -1473,6 +1474,52 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
                                                tiles_y, ntiles);
   conv3x3_wgrad_reduce_kernel<<<dim3(kWgBlock / 256, CO / kWgC, CI / kWgC), 256, 0, s>>>(
       (const float*)workspace, dw, CI, parts);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+// ---- bias + LeakyReLU epilogue of the convolutions (conv_epilogue.cuh) ---------
+static int check_epilogue(int N, int C, int H, int W, float slope) {
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || (long long)N * C > 65535 ||
+      ((long long)H * W) % 4 != 0 || (long long)H * W > 0x7fffffffLL)
+    return fail(CSMRI_E_SHAPE, "bias_lrelu: bad shape %dx%dx%dx%d (H*W %% 4, N*C <= 65535)", N, C,
+                H, W);
+  if (!(slope > 0.0f)) return fail(CSMRI_E_ARG, "bias_lrelu: slope must be > 0 (got %g)", slope);
+  return CSMRI_OK;
+}
+static int check_ptr16(const void* p, const char* name) {
+  CSMRI_TRY(check_ptr(p, name));
+  if (((uintptr_t)p & 15u) != 0) return fail(CSMRI_E_ALIGN, "%s is not 16-byte aligned", name);
+  return CSMRI_OK;
+}
+
+int csmri_bias_lrelu(float* z, const float* bias, int N, int C, int H, int W, float slope,
+                     void* stream) {
+  CSMRI_TRY(check_epilogue(N, C, H, W, slope));
+  CSMRI_TRY(check_ptr16(z, "z"));
+  CSMRI_TRY(check_ptr(bias, "bias"));
+  const int hw4 = H * W / 4;
+  int chunks = (hw4 + 1023) / 1024;
+  if (chunks > 16) chunks = 16;
+  bias_lrelu_kernel<<<dim3(chunks, N * C), 256, 0, (cudaStream_t)stream>>>((float4*)z, bias, C, hw4,
+                                                                          slope);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+int csmri_bias_lrelu_backward(const float* grad_y, const float* y, float* grad_z, float* grad_bias,
+                              float* partial, int N, int C, int H, int W, float slope,
+                              void* stream) {
+  CSMRI_TRY(check_epilogue(N, C, H, W, slope));
+  CSMRI_TRY(check_ptr16(grad_y, "grad_y"));
+  CSMRI_TRY(check_ptr16(y, "y"));
+  CSMRI_TRY(check_ptr16(grad_z, "grad_z"));
+  CSMRI_TRY(check_ptr(grad_bias, "grad_bias"));
+  CSMRI_TRY(check_ptr(partial, "partial"));
+  cudaStream_t s = (cudaStream_t)stream;
+  bias_lrelu_backward_kernel<<<dim3(kEpChunks, N * C), 256, 0, s>>>(
+      (const float4*)grad_y, (const float4*)y, (float4*)grad_z, partial, H * W / 4, slope);
+  bias_grad_reduce_kernel<<<C, 32, 0, s>>>(partial, grad_bias, N, C);
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }

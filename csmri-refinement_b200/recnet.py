@@ -67,7 +67,10 @@ class ConvBlock(nn.Module):
         modules = []
         for i in range(num_convs - 1):
             pad, conv = _pad_and_conv(in_ch, num_filters, kernel_size, dilations[i], padding)
-            modules += [pad, conv, nn.LeakyReLU(relu_leakiness, inplace=True)]
+            # the activation is applied by the convolution module itself (one fused
+            # bias + LeakyReLU pass); the Identity keeps the Sequential indices
+            conv.fused_slope = relu_leakiness
+            modules += [pad, conv, nn.Identity()]
             in_ch = num_filters
         pad, conv = _pad_and_conv(in_ch, num_outputs, kernel_size, dilations[-1], padding)
         modules += [pad, conv]

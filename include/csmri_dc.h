@@ -217,6 +217,19 @@ size_t csmri_conv3x3_wgrad_workspace_bytes(int CI, int CO);
 int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* workspace,
                         int N, int CI, int CO, int H, int W, int pad, void* stream);
 
+/* Bias + LeakyReLU after a convolution (models/recnet.py:45-48: Conv2d(bias=True)
+ * followed by nn.LeakyReLU(relu_leakiness, inplace=True)), fused into one pass:
+ *   csmri_bias_lrelu:           z (N,C,H,W) <- lrelu(z + bias[c]), in place
+ *   csmri_bias_lrelu_backward:  grad_z = grad_y * (y > 0 ? 1 : slope),
+ *                               grad_bias[c] = sum_{n,h,w} grad_z   (fixed order)
+ * y is the forward OUTPUT; slope > 0.  H*W must be a multiple of 4, pointers
+ * 16-byte aligned.  partial: N*C*8 floats of scratch. */
+int csmri_bias_lrelu(float* z, const float* bias, int N, int C, int H, int W, float slope,
+                     void* stream);
+int csmri_bias_lrelu_backward(const float* grad_y, const float* y, float* grad_z,
+                              float* grad_bias, float* partial, int N, int C, int H, int W,
+                              float slope, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
