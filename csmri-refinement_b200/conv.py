@@ -85,22 +85,47 @@ def bias_lrelu_backward(grad_y, y, slope):
     return grad_z, grad_b
 
 
+def conv3x3_thin(x, weight, bias, slope=0.0):
+    """RecNet's thin layers (2 -> 32 or 32 -> 2 channels, zero padding 1) through
+    ``csmri_conv3x3_thin``: act(conv(x, weight) + bias), slope 0 = no activation."""
+    x, weight = x.contiguous(), weight.contiguous()
+    n, a, h, w = x.shape
+    b = weight.shape[0]
+    with torch.cuda.device(x.device):
+        y = torch.empty((n, b, h, w), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().csmri_conv3x3_thin(
+            x.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
+            y.data_ptr(), n, a, b, h, w, float(slope), torch.cuda.current_stream().cuda_stream))
+    return y
+
+
+def _is_thin(weight, pad):
+    return pad == 1 and (weight.shape[1], weight.shape[0]) in ((2, 32), (32, 2))
+
+
 class _Conv3x3(torch.autograd.Function):
-    """conv (+ bias) [+ LeakyReLU when ``slope`` is given]; forward and data gradient
-    stay cuDNN, the rest runs through libcsmri_dc."""
+    """conv (+ bias) [+ LeakyReLU when ``slope`` is given].  32k -> 32k layers:
+    forward and data gradient stay cuDNN, epilogues and the weight gradient run
+    through libcsmri_dc.  Thin layers (2 -> 32, 32 -> 2): everything does."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, pad, slope):
         ctx.pad, ctx.slope = pad, slope
         ctx.has_bias = bias is not None
+        ctx.thin = _is_thin(weight, pad) and (slope is None or weight.shape[1] == 2)
+        if ctx.thin:
+            y = conv3x3_thin(x, weight, bias, slope or 0.0)
+        elif slope is None:
+            y = torch.ops.aten.convolution(x, weight, bias, [1, 1], [pad, pad], [1, 1], False,
+                                           [0, 0], 1)
+        else:
+            y = torch.ops.aten.convolution(x, weight, None, [1, 1], [pad, pad], [1, 1], False,
+                                           [0, 0], 1)
+            bias_lrelu_(y, bias, slope)
         if slope is None:
             ctx.save_for_backward(x, weight)
-            return torch.ops.aten.convolution(x, weight, bias, [1, 1], [pad, pad], [1, 1], False,
-                                              [0, 0], 1)
-        y = torch.ops.aten.convolution(x, weight, None, [1, 1], [pad, pad], [1, 1], False,
-                                       [0, 0], 1)
-        bias_lrelu_(y, bias, slope)
-        ctx.save_for_backward(x, weight, y)
+        else:
+            ctx.save_for_backward(x, weight, y)
         return y
 
     @staticmethod
@@ -112,19 +137,25 @@ class _Conv3x3(torch.autograd.Function):
         gx = gb = gw = None
         if ctx.slope is None:
             x, weight = ctx.saved_tensors
-            if need_x or need_b:
-                gx, _, gb = torch.ops.aten.convolution_backward(
-                    grad_out, x, weight, [weight.shape[0]], [1, 1], [pad, pad], [1, 1], False,
-                    [0, 0], 1, [need_x, False, need_b])
         else:
             x, weight, y = ctx.saved_tensors
             grad_out, gb = bias_lrelu_backward(grad_out, y, ctx.slope)
             if not need_b:
                 gb = None
-            if need_x:
-                gx = torch.ops.aten.convolution_backward(
-                    grad_out, x, weight, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
-                    [True, False, False])[0]
+        if ctx.thin:
+            if need_b and gb is None:
+                gb = grad_out.sum(dim=(0, 2, 3))
+            if need_x:     # the same kernel family on flipped, transposed weights
+                gx = conv3x3_thin(grad_out, weight.flip(2, 3).transpose(0, 1), None, 0.0)
+        elif ctx.slope is None:
+            if need_x or need_b:
+                gx, _, gb = torch.ops.aten.convolution_backward(
+                    grad_out, x, weight, [weight.shape[0]], [1, 1], [pad, pad], [1, 1], False,
+                    [0, 0], 1, [need_x, False, need_b])
+        elif need_x:
+            gx = torch.ops.aten.convolution_backward(
+                grad_out, x, weight, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
+                [True, False, False])[0]
         if need_w:
             gw = conv3x3_wgrad(x, grad_out, pad)
         return gx, gw, gb, None, None

@@ -223,25 +223,36 @@ __global__ void __launch_bounds__(256, 2)
         dst[kx] = (row_ok && gx >= 0 && gx < WI) ? __ldg(src + gx) : 0.0f;
       }
     };
-    float win[CIT][3][3];
+    // the next row of x and dY is requested before the current one is multiplied
+    // (x only where the registers allow it: two input channels per thread)
+    constexpr bool kPrefetchX = CIT <= 2;
+    float win[CIT][3][3], nxt[kPrefetchX ? CIT : 1][3], dnx[COT];
 #pragma unroll
     for (int c = 0; c < CIT; ++c) {
       load_row(c, y0 - pad, win[c][1]);
       load_row(c, y0 - pad + 1, win[c][2]);
+      if (kPrefetchX) load_row(c, y0 - pad + 2, nxt[c]);
     }
+#pragma unroll
+    for (int o = 0; o < COT; ++o) dnx[o] = __ldg(dn + (size_t)o * H * W);
 #pragma unroll 2
     for (int r = 0; r < kWtRows; ++r) {
       float d[COT];
 #pragma unroll
-      for (int o = 0; o < COT; ++o) d[o] = __ldg(dn + ((size_t)o * H + r) * W);
+      for (int o = 0; o < COT; ++o) {
+        d[o] = dnx[o];
+        if (r + 1 < kWtRows) dnx[o] = __ldg(dn + ((size_t)o * H + r + 1) * W);
+      }
 #pragma unroll
       for (int c = 0; c < CIT; ++c) {
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           win[c][0][kx] = win[c][1][kx];
           win[c][1][kx] = win[c][2][kx];
+          if (kPrefetchX) win[c][2][kx] = nxt[c][kx];
         }
-        load_row(c, y0 + r + 2 - pad, win[c][2]);
+        if (kPrefetchX) load_row(c, y0 + r + 3 - pad, nxt[c]);
+        else load_row(c, y0 + r + 2 - pad, win[c][2]);
       }
 #pragma unroll
       for (int c = 0; c < CIT; ++c)

@@ -48,6 +48,7 @@
 #include "refine_ops.cuh"
 #include "conv_wgrad.cuh"
 #include "conv_epilogue.cuh"
+#include "conv_thin.cuh"
 
 namespace csmri {
 
@@ -1474,6 +1475,36 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
                                                tiles_y, ntiles);
   conv3x3_wgrad_reduce_kernel<<<dim3(kWgBlock / 256, CO / kWgC, CI / kWgC), 256, 0, s>>>(
       (const float*)workspace, dw, CI, parts);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float* y, int N, int A,
+                       int B, int H, int W, float slope, void* stream) {
+  if (!wgrad_thin(A, B))
+    return fail(CSMRI_E_SHAPE, "conv3x3_thin handles 2 -> 32 and 32 -> 2 channels (got %d -> %d)", A, B);
+  if (N <= 0 || H <= 0 || W <= 0 || H % kThinRows != 0 || W % 32 != 0)
+    return fail(CSMRI_E_SHAPE, "conv3x3_thin needs H %% %d == 0 and W %% 32 == 0 (got %dx%dx%d)",
+                kThinRows, N, H, W);
+  if (!(slope >= 0.0f)) return fail(CSMRI_E_ARG, "slope must be >= 0 (got %g)", slope);
+  if (A == 32 && slope != 0.0f)
+    return fail(CSMRI_E_ARG, "the 32 -> 2 layer has no activation (models/recnet.py:48)");
+  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr(w, "w"));
+  CSMRI_TRY(check_ptr(y, "y"));
+  if (x == y) return fail(CSMRI_E_ARG, "y must not alias x");
+  const int tiles_x = W / 32, tiles_y = H / kThinRows;
+  const long long ntiles_ll = (long long)N * tiles_x * tiles_y;
+  if (ntiles_ll > 0x7fffffffLL) return fail(CSMRI_E_SHAPE, "too many tiles");
+  int ctas = sm_count() * 2;
+  if (ctas > ntiles_ll) ctas = (int)ntiles_ll;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (A == 2)
+    conv3x3_thin_out_kernel<<<ctas, 256, 0, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
+                                                 (int)ntiles_ll, slope);
+  else
+    conv3x3_thin_in_kernel<<<ctas, 256, 0, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
+                                                (int)ntiles_ll);
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }

@@ -217,6 +217,15 @@ size_t csmri_conv3x3_wgrad_workspace_bytes(int CI, int CO);
 int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* workspace,
                         int N, int CI, int CO, int H, int W, int pad, void* stream);
 
+/* RecNet's thin 3x3 convolutions (first / last layer of a block, models/recnet.py:
+ * 45-48), stride 1, zero padding 1:  y = act(conv(x, w) + bias)
+ *   x (N,A,H,W), w (B,A,3,3), bias (B) or NULL, y (N,B,H,W);
+ *   (A,B) = (2,32) or (32,2); slope > 0 applies LeakyReLU, slope = 0 none.
+ * The data gradient of such a layer is the same call with w flipped in both
+ * spatial axes and its first two axes transposed.  H % 16 == 0, W % 32 == 0. */
+int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float* y,
+                       int N, int A, int B, int H, int W, float slope, void* stream);
+
 /* Bias + LeakyReLU after a convolution (models/recnet.py:45-48: Conv2d(bias=True)
  * followed by nn.LeakyReLU(relu_leakiness, inplace=True)), fused into one pass:
  *   csmri_bias_lrelu:           z (N,C,H,W) <- lrelu(z + bias[c]), in place

@@ -641,8 +641,40 @@ def test_recnet_training_gradients_with_fast_wgrad():
         grads[fast] = {k: p.grad.clone() for k, p in net.named_parameters()}
     conv.set_fast_wgrad(True)
     used = 0
+    scale = max(v.norm().item() for v in grads[False].values())
     for k in grads[True]:
         a, b = grads[True][k], grads[False][k]
-        assert (a - b).norm().item() <= 1e-5 * b.norm().item() + 1e-12, k
+        if b.norm().item() < 1e-6 * scale:
+            # the bias feeding a DC layer whose mask keeps the DC line: the true
+            # gradient is 0 and both sides hold rounding noise
+            assert (a - b).norm().item() < 1e-6 * scale, k
+        else:
+            assert (a - b).norm().item() <= 1e-5 * b.norm().item(), k
         used += int(not torch.equal(a, b))
     assert used >= 8          # thick and thin layers really took the other kernels
+
+
+@pytest.mark.parametrize('shape', [(2, 2, 32, 32, 64, 0.01), (3, 2, 32, 16, 32, 0.0),
+                                   (2, 32, 2, 48, 96, 0.0), (1, 32, 2, 16, 32, 0.0)])
+def test_conv3x3_thin_matches_torch(shape):
+    """csmri_conv3x3_thin (forward, and as data gradient on flipped / transposed
+    weights) against torch in fp64: (N, A, B, H, W, slope)."""
+    from csmri_refinement_b200 import conv
+    n, a, b, h, w, slope = shape
+    g = torch.Generator(device='cuda').manual_seed(int(sum(shape[:5])))
+    x = torch.randn(n, a, h, w, device='cuda', generator=g)
+    wt = torch.randn(b, a, 3, 3, device='cuda', generator=g) * 0.2
+    bias = torch.randn(b, device='cuda', generator=g)
+    x64 = x.double().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(x64, wt.double(), bias.double(), 1, 1)
+    if slope:
+        ref = torch.nn.functional.leaky_relu(ref, slope)
+    got = conv.conv3x3_thin(x, wt, bias, slope)
+    assert orc.rel_l2(got.cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
+    if not slope:
+        gy = torch.randn(n, b, h, w, device='cuda', generator=g)
+        ref.backward(gy.double())
+        gx = conv.conv3x3_thin(gy, wt.flip(2, 3).transpose(0, 1), None, 0.0)
+        assert orc.rel_l2(gx.cpu().numpy(), x64.grad.cpu().numpy()) < 1e-6
+    with pytest.raises(RuntimeError):
+        conv.conv3x3_thin(x[:, :, :8], wt, bias, slope)      # H % 16 != 0
