@@ -7,7 +7,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from csmri_refinement_b200 import myfft, ops, rec_transforms, undersampling  # noqa: E402
+from csmri_refinement_b200 import (conv, myfft, ops, rec_transforms, recnet, refinement_ops,  # noqa: E402
+                                   undersampling)
 
 dev = torch.device('cuda:0')
 for n, B in ((64, 5), (128, 3), (256, 3), (320, 2), (512, 2), (32, 4)):
@@ -24,3 +25,25 @@ for n, B in ((64, 5), (128, 3), (256, 3), (320, 2), (512, 2), (32, 4)):
     rec_transforms.psnr(out.detach(), batch['target'])
     torch.cuda.synchronize()
     print('ok', n)
+
+# refinement-path pointwise ops
+t = torch.randn(3, 2, 40, 52, device=dev)
+s_, mn, mx = refinement_ops.scale(t)
+refinement_ops.unscale(s_, mn, mx)
+refinement_ops.magnitude_image(t)
+learn = torch.randn(3, 1, 40, 52, device=dev, requires_grad=True)
+sc = torch.nn.Parameter(torch.full((1,), 0.3, device=dev))
+refinement_ops.refinement_real_penalty_add(t, learn, sc)['pred'].sum().backward()
+# training-step kernels: weight gradients (thick / thin), thin convolutions, epilogues,
+# through one small RecNet step (image edges, first / last tiles included)
+for ci, co, h, w, pad in ((32, 32, 8, 32, 1), (64, 32, 4, 64, 0), (2, 32, 16, 32, 1), (32, 2, 32, 64, 0)):
+    conv.conv3x3_wgrad(torch.randn(2, ci, h + 2 - 2 * pad, w + 2 - 2 * pad, device=dev),
+                       torch.randn(2, co, h, w, device=dev), pad)
+img = torch.rand(2, 32, 32, device=dev)
+rows = undersampling.cartesian_rows((2, 32, 32), 4, 8, False, np.random.RandomState(1))
+batch = undersampling.undersample(img, rows)
+net = recnet.construct_model({'num_blocks': 2, 'num_convs': 3, 'num_filters': 32}).to(dev)
+torch.nn.functional.mse_loss(net(batch['inp'], batch['kspace'], batch['mask']),
+                             batch['target']).backward()
+torch.cuda.synchronize()
+print('ok refinement + training-step kernels')
