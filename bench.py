@@ -37,6 +37,29 @@ N = 256
 ACC = 4
 
 
+# Libraries print to stdout on their own (NCCL's version banner under NCCL_DEBUG, cuDNN
+# notices): keep fd 1 for the ONE JSON line and send everything else to stderr.
+_JSON_FD = None
+
+
+def capture_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def measured_peak():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -224,7 +247,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': vals, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'wall_ms_per_step_incl_setup': dt * 1e3,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -237,6 +260,7 @@ def main():
     ap.add_argument('--variant', type=int, default=None, help='kernel tuning variant (debug)')
     ap.add_argument('--no-recnet', action='store_true', help='skip the RecNet training leg')
     args = ap.parse_args()
+    capture_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
     rank = int(os.environ.get('RANK', '0'))
@@ -468,7 +492,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
 
 
 if __name__ == '__main__':
