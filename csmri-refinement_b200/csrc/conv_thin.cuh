@@ -23,27 +23,74 @@
 
 namespace csmri {
 
-constexpr int kThinRows = 16;   // tile = 32 x 16 pixels
+// Staged input row (pitch 36 floats): [0..31] the 32 columns (16-byte aligned),
+// [32] the right halo column; the LEFT halo column sits at [-1], i.e. in the
+// unused tail [35] of the previous row slot (4 lead floats in front of the first),
+// so that column x0 + j is always at offset j, j = -1 .. 32.
+constexpr int kThinPC = 36;
+constexpr int kThinLead = 4;
+constexpr int kThinOutRows = 16;   // thin_out tile: 32 x 16 pixels (input tile 2 x 18 x 34)
+constexpr int kThinInRows = 8;     // thin_in  tile: 32 x  8 pixels (input tile 32 x 10 x 34)
 
-__device__ __forceinline__ void thin_load_row(const float* __restrict__ plane, int gy, int gx0, int H,
-                                              int W, float* dst) {
+__device__ __forceinline__ void thin_copy4(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(valid ? 4 : 0)
+               : "memory");
+}
+
+__device__ __forceinline__ void thin_copy16(float* dst, const float* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(valid ? 16 : 0)
+               : "memory");
+}
+
+// Four staged rows per call: quarter-warp q copies row `gy[q]` of `plane[q]`,
+// columns x0 .. x0+31 as eight 16-byte pieces (x0 is a multiple of 32, so source
+// and destination are aligned), then lanes 8q and 8q+1 add the two halo columns.
+// (4-byte pieces for everything made the copy unit, not HBM, the bound of thin_in.)
+__device__ __forceinline__ void thin_stage_row4(float* dst_row, const float* __restrict__ plane,
+                                                int gy, int x0, int H, int W, int lane) {
+  const int quad = lane & 7;
   const bool row_ok = gy >= 0 && gy < H;
-  const float* src = plane + (size_t)(row_ok ? gy : 0) * W;
-#pragma unroll
-  for (int kx = 0; kx < 3; ++kx) {
-    const int gx = gx0 + kx;
-    dst[kx] = (row_ok && gx >= 0 && gx < W) ? __ldg(src + gx) : 0.0f;
+  const float* src = plane + (size_t)min(max(gy, 0), H - 1) * W;
+  thin_copy16(dst_row + quad * 4, src + x0 + quad * 4, row_ok);
+  if (quad < 2) {
+    const int gx = quad == 0 ? x0 - 1 : x0 + 32;
+    thin_copy4(dst_row + (quad == 0 ? -1 : 32), src + min(max(gx, 0), W - 1),
+               row_ok && gx >= 0 && gx < W);
   }
 }
 
+struct ThinTile {
+  int n, y0, x0;
+};
+__device__ __forceinline__ ThinTile thin_tile(int tile, int tiles_x, int tiles_y, int rows) {
+  ThinTile t;
+  t.n = tile / (tiles_x * tiles_y);
+  const int rem = tile - t.n * tiles_x * tiles_y;
+  const int ty = rem / tiles_x;
+  t.y0 = ty * rows;
+  t.x0 = (rem - ty * tiles_x) * 32;
+  return t;
+}
+
 // y[n][4*warp + o] = act(bias + sum_{c<2, taps} w[4*warp + o][c][tap] * x[n][c][..])
+// The (tiny) input tile of the NEXT tile is staged with cp.async while the current
+// one is multiplied: the row loop never waits for global memory.  (The first
+// version loaded each row from global memory one step ahead and ran at a quarter
+// of the write bandwidth: every step paid an L2 round trip.)
 __global__ void __launch_bounds__(256, 2)
     conv3x3_thin_out_kernel(const float* __restrict__ x, const float* __restrict__ w,
                             const float* __restrict__ bias, float* __restrict__ y, int H, int W,
                             int tiles_x, int tiles_y, int ntiles, float slope) {
-  constexpr int A = 2, B = 32, BT = 4;
+  constexpr int A = 2, B = 32, BT = 4, R = kThinOutRows;
+  constexpr int kBuf = kThinLead + A * (R + 2) * kThinPC;
+  __shared__ __align__(16) float stage[2][kBuf];
   const int lane = threadIdx.x & 31;
-  const int cob = (threadIdx.x >> 5) * BT;
+  const int warp = threadIdx.x >> 5;
+  const int cob = warp * BT;
   cf wp[A][9][BT / 2];
 #pragma unroll
   for (int c = 0; c < A; ++c)
@@ -59,34 +106,45 @@ __global__ void __launch_bounds__(256, 2)
     bp[o] = bias != nullptr ? mk(__ldg(bias + cob + 2 * o), __ldg(bias + cob + 2 * o + 1))
                             : mk(0.0f, 0.0f);
   const size_t plane = (size_t)H * W;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int n = tile / (tiles_x * tiles_y);
-    const int rem = tile - n * tiles_x * tiles_y;
-    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    const int y0 = ty * kThinRows, gx0 = tx * 32 + lane - 1;
-    const float* xn = x + (size_t)n * A * plane;
-    float* yn = y + ((size_t)n * B + cob) * plane + (size_t)y0 * W + tx * 32 + lane;
-    // the row after next is requested before the current row is multiplied:
-    // two row loads per thread are always in flight
-    float win[A][3][3], nxt[A][3];
-#pragma unroll
-    for (int c = 0; c < A; ++c) {
-      thin_load_row(xn + c * plane, y0 - 1, gx0, H, W, win[c][1]);
-      thin_load_row(xn + c * plane, y0, gx0, H, W, win[c][2]);
-      thin_load_row(xn + c * plane, y0 + 1, gx0, H, W, nxt[c]);
+  auto stage_tile = [&](int tile, float* buf) {
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    static_assert(A * (R + 2) % 4 == 0, "rows are staged four at a time");
+    for (int pair = warp * 4 + (lane >> 3); pair < A * (R + 2); pair += 32) {
+      const int c = pair / (R + 2), r = pair - c * (R + 2);
+      thin_stage_row4(buf + kThinLead + pair * kThinPC, x + ((size_t)t.n * A + c) * plane,
+                      t.y0 - 1 + r, t.x0, H, W, lane);
     }
-#pragma unroll 4
-    for (int r = 0; r < kThinRows; ++r) {
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) stage_tile(tile, stage[0]);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const float* cur = stage[it & 1] + kThinLead;
+    const int next = tile + gridDim.x;
+    if (next < ntiles) stage_tile(next, stage[(it + 1) & 1]);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    float* yn = y + ((size_t)t.n * B + cob) * plane + (size_t)t.y0 * W + t.x0 + lane;
+    float win[A][3][3];
 #pragma unroll
-      for (int c = 0; c < A; ++c) {
+    for (int c = 0; c < A; ++c)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        win[c][1][kx] = cur[(c * (R + 2) + 0) * kThinPC + lane + kx - 1];
+        win[c][2][kx] = cur[(c * (R + 2) + 1) * kThinPC + lane + kx - 1];
+      }
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int c = 0; c < A; ++c)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           win[c][0][kx] = win[c][1][kx];
           win[c][1][kx] = win[c][2][kx];
-          win[c][2][kx] = nxt[c][kx];
+          win[c][2][kx] = cur[(c * (R + 2) + r + 2) * kThinPC + lane + kx - 1];
         }
-        thin_load_row(xn + c * plane, y0 + r + 2, gx0, H, W, nxt[c]);
-      }
       cf acc[BT / 2];
 #pragma unroll
       for (int o = 0; o < BT / 2; ++o) acc[o] = bp[o];
@@ -110,81 +168,95 @@ __global__ void __launch_bounds__(256, 2)
         yn[(size_t)(2 * o + 1) * plane + (size_t)r * W] = b;
       }
     }
+    __syncthreads();   // `cur` is the staging target of the next iteration
   }
 }
 
 // y[n][o] = bias[o] + sum_{c<32, taps} w[o][c][tap] * x[n][c][..],  o < 2.
-// Warp g sums input channels 4g .. 4g+3, two at a time (so that weights, window
-// and the prefetched row fit the register budget of two resident CTAs); the 8
-// partial sums of a pixel meet in shared memory once per tile.
+// Warp g sums input channels 4g .. 4g+3 from the cp.async-staged tile (next tile
+// in flight while this one is multiplied); the 8 partial sums of a pixel meet in
+// shared memory once per tile.  Dynamic shared memory: 2 tile buffers + partials.
+constexpr int kThinInBuf = kThinLead + 32 * (kThinInRows + 2) * kThinPC;           // floats
+constexpr int kThinInSmem = (2 * kThinInBuf + 8 * kThinInRows * 32 * 2) * 4;       // bytes
+
 __global__ void __launch_bounds__(256, 2)
     conv3x3_thin_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                            const float* __restrict__ bias, float* __restrict__ y, int H, int W,
                            int tiles_x, int tiles_y, int ntiles) {
-  constexpr int A = 32, AT = 2;
-  __shared__ cf part[8][kThinRows][32];
+  constexpr int A = 32, AT = 4, R = kThinInRows;
+  extern __shared__ __align__(16) float thin_smem[];
+  cf* part = reinterpret_cast<cf*>(thin_smem + 2 * kThinInBuf);   // [8][R][32]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int cib = warp * AT;
+  cf wp[AT][9];
+#pragma unroll
+  for (int c = 0; c < AT; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      wp[c][t] = mk(__ldg(w + (cib + c) * 9 + t), __ldg(w + (A + cib + c) * 9 + t));
   const cf bp = bias != nullptr ? mk(__ldg(bias), __ldg(bias + 1)) : mk(0.0f, 0.0f);
   const size_t plane = (size_t)H * W;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int n = tile / (tiles_x * tiles_y);
-    const int rem = tile - n * tiles_x * tiles_y;
-    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    const int y0 = ty * kThinRows, gx0 = tx * 32 + lane - 1;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const int cib = warp * 4 + half * AT;
-      cf wp[AT][9];
+  auto stage_tile = [&](int tile, float* buf) {   // warp g stages its own four channels
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    const float* xc = x + ((size_t)t.n * A + cib) * plane;
+    static_assert(AT * (R + 2) % 4 == 0, "rows are staged four at a time");
+#pragma unroll 2
+    for (int pair = lane >> 3; pair < AT * (R + 2); pair += 4) {
+      const int c = pair / (R + 2), r = pair - c * (R + 2);
+      thin_stage_row4(buf + kThinLead + (cib * (R + 2) + pair) * kThinPC, xc + c * plane,
+                      t.y0 - 1 + r, t.x0, H, W, lane);
+    }
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) stage_tile(tile, thin_smem);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const float* cur = thin_smem + (it & 1) * kThinInBuf + kThinLead + cib * (R + 2) * kThinPC;
+    const int next = tile + gridDim.x;
+    if (next < ntiles) stage_tile(next, thin_smem + ((it + 1) & 1) * kThinInBuf);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();   // tile landed; previous tile's partial sums have been consumed
+    float win[AT][3][3];
+#pragma unroll
+    for (int c = 0; c < AT; ++c)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        win[c][1][kx] = cur[(c * (R + 2) + 0) * kThinPC + lane + kx - 1];
+        win[c][2][kx] = cur[(c * (R + 2) + 1) * kThinPC + lane + kx - 1];
+      }
+#pragma unroll 2
+    for (int r = 0; r < R; ++r) {
 #pragma unroll
       for (int c = 0; c < AT; ++c)
 #pragma unroll
-        for (int t = 0; t < 9; ++t)
-          wp[c][t] = mk(__ldg(w + (cib + c) * 9 + t), __ldg(w + (A + cib + c) * 9 + t));
-      const float* xn = x + ((size_t)n * A + cib) * plane;
-      float win[AT][3][3], nxt[AT][3];
-#pragma unroll
-      for (int c = 0; c < AT; ++c) {
-        thin_load_row(xn + c * plane, y0 - 1, gx0, H, W, win[c][1]);
-        thin_load_row(xn + c * plane, y0, gx0, H, W, win[c][2]);
-        thin_load_row(xn + c * plane, y0 + 1, gx0, H, W, nxt[c]);
-      }
-#pragma unroll 4
-      for (int r = 0; r < kThinRows; ++r) {
-#pragma unroll
-        for (int c = 0; c < AT; ++c) {
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            win[c][0][kx] = win[c][1][kx];
-            win[c][1][kx] = win[c][2][kx];
-            win[c][2][kx] = nxt[c][kx];
-          }
-          thin_load_row(xn + c * plane, y0 + r + 2, gx0, H, W, nxt[c]);
+        for (int kx = 0; kx < 3; ++kx) {
+          win[c][0][kx] = win[c][1][kx];
+          win[c][1][kx] = win[c][2][kx];
+          win[c][2][kx] = cur[(c * (R + 2) + r + 2) * kThinPC + lane + kx - 1];
         }
-        cf acc = half == 0 ? mk(0.0f, 0.0f) : part[warp][r][lane];
+      cf acc = mk(0.0f, 0.0f);
 #pragma unroll
-        for (int c = 0; c < AT; ++c)
+      for (int c = 0; c < AT; ++c)
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-              acc = f2fma(wp[c][ky * 3 + kx], mk(win[c][ky][kx], win[c][ky][kx]), acc);
-        part[warp][r][lane] = acc;
-      }
+          for (int kx = 0; kx < 3; ++kx)
+            acc = f2fma(wp[c][ky * 3 + kx], mk(win[c][ky][kx], win[c][ky][kx]), acc);
+      part[(warp * R + r) * 32 + lane] = acc;
     }
-    __syncthreads();
-    float* yn = y + (size_t)n * 2 * plane + (size_t)y0 * W + tx * 32;
+    __syncthreads();   // partial sums complete; everyone is done reading the tile
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    float* yn = y + (size_t)t.n * 2 * plane + (size_t)t.y0 * W + t.x0;
+    {
+      const int r = threadIdx.x >> 5;                 // 8 rows x 32 pixels = 256 threads
+      cf sum = bp;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int pix = threadIdx.x + 256 * k;          // 512 pixels of the tile
-      const int r = pix >> 5, xx = pix & 31;
-      cf s = bp;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) s = f2add(s, part[g][r][xx]);
-      yn[(size_t)r * W + xx] = s.x;
-      yn[plane + (size_t)r * W + xx] = s.y;
+      for (int g = 0; g < 8; ++g) sum = f2add(sum, part[(g * R + r) * 32 + lane]);
+      yn[(size_t)r * W + lane] = sum.x;
+      yn[plane + (size_t)r * W + lane] = sum.y;
     }
-    __syncthreads();
   }
 }
 

@@ -43,7 +43,92 @@ __device__ __forceinline__ void wg_copy4(float* dst, const float* src, bool vali
                : "memory");
 }
 
-// grid: (CTAs sharing the pixel tiles, CO / 32, CI / 32); block: 256
+// Stage one tile: warp w copies input channels 4w .. 4w+3 (6 patch rows each) and
+// dY channels 4w .. 4w+3 (4 rows each), lanes along x.  Everything but the per-tile
+// base pointers and the edge predicates is a compile-time offset (the first version
+// recomputed (channel, row) from a loop counter and spent 28 % of the kernel's
+// instructions, on the same pipe as the FFMA2s, on address arithmetic).  Column /
+// row indices are clamped into the image so that every source address is valid;
+// out-of-image elements are copies of size 0 (zero fill).
+__device__ __forceinline__ void wg_stage(float* X_s, float* D_s, const float* __restrict__ x,
+                                         const float* __restrict__ dy, int tile, int tiles_x,
+                                         int tiles_y, int CI, int CO, int ci0, int co0, int H, int W,
+                                         int HI, int WI, int pad, int lane, int warp) {
+  const int n = tile / (tiles_x * tiles_y);
+  const int rem = tile - n * tiles_x * tiles_y;
+  const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+  const int y0 = ty * kWgTH, x0 = tx * kWgTW;
+  const int gx = x0 + lane - pad, gx2 = gx + kWgTW;
+  const bool ok0 = gx >= 0 && gx < WI;
+  const bool ok1 = gx2 >= 0 && gx2 < WI;
+  const int cx0 = min(max(gx, 0), WI - 1), cx1 = min(max(gx2, 0), WI - 1);
+  const size_t chs = (size_t)HI * WI;
+  const float* src_c = x + ((size_t)n * CI + ci0 + warp * 4) * chs;
+  float* dst_c = X_s + lane * kWgXS + warp * 4;
+#pragma unroll
+  for (int r = 0; r < kWgPR; ++r) {
+    const int gy = y0 + r - pad;
+    const bool row_ok = gy >= 0 && gy < HI;
+    const float* src = src_c + (size_t)min(max(gy, 0), HI - 1) * WI;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float* dst = dst_c + r * kWgPC * kWgXS + c;
+      wg_copy4(dst, src + cx0, row_ok && ok0);
+      if (lane < 2) wg_copy4(dst + kWgTW * kWgXS, src + cx1, row_ok && ok1);
+      src += chs;
+    }
+  }
+  const size_t ohs = (size_t)H * W;
+  const float* dsrc = dy + (((size_t)n * CO + co0 + warp * 4) * H + y0) * W + x0 + lane;
+  float* ddst = D_s + lane * kWgDS + warp * 4;
+#pragma unroll
+  for (int r = 0; r < kWgTH; ++r) {
+    const float* src = dsrc + (size_t)r * W;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      wg_copy4(ddst + r * kWgTW * kWgDS + c, src, true);
+      src += ohs;
+    }
+  }
+}
+
+// one staged tile into the thread's 36 accumulators: 18 FFMA2 per pixel
+__device__ __forceinline__ void wg_compute(const float* X_s, const float* D_s, cf (&acc)[9][2],
+                                           int lane, int warp) {
+#pragma unroll 1
+  for (int r = 0; r < kWgTH; ++r) {
+    float w[3][3];   // sliding window
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      w[ky][1] = X_s[((r + ky) * kWgPC + 0) * kWgXS + lane];
+      w[ky][2] = X_s[((r + ky) * kWgPC + 1) * kWgXS + lane];
+    }
+#pragma unroll
+    for (int xx = 0; xx < kWgTW; ++xx) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        w[ky][0] = w[ky][1];
+        w[ky][1] = w[ky][2];
+        w[ky][2] = X_s[((r + ky) * kWgPC + xx + 2) * kWgXS + lane];
+      }
+      const float4 d = *reinterpret_cast<const float4*>(&D_s[(r * kWgTW + xx) * kWgDS + warp * 4]);
+      const cf d01 = mk(d.x, d.y), d23 = mk(d.z, d.w);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          // packed FFMA2 with a scalar-broadcast operand: two output channels per
+          // instruction (scalar FFMAs measured 15 % slower: issue-bound)
+          acc[ky * 3 + kx][0] = f2fma(d01, mk(w[ky][kx], w[ky][kx]), acc[ky * 3 + kx][0]);
+          acc[ky * 3 + kx][1] = f2fma(d23, mk(w[ky][kx], w[ky][kx]), acc[ky * 3 + kx][1]);
+        }
+    }
+  }
+}
+
+// grid: (CTAs sharing the pixel tiles, CO / 32, CI / 32); block: 256.  One tile
+// buffer per CTA; four resident CTAs hide each other's staging (a double-buffered
+// variant with two CTAs per SM measured the same: profiles/README.md).
 __global__ void __launch_bounds__(256, 4)
     conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                          float* __restrict__ partial, int CI, int CO, int H, int W, int HI, int WI,
@@ -60,84 +145,12 @@ __global__ void __launch_bounds__(256, 4)
   for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = mk(0.0f, 0.0f);
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int n = tile / (tiles_x * tiles_y);
-    const int rem = tile - n * tiles_x * tiles_y;
-    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-    const int y0 = ty * kWgTH, x0 = tx * kWgTW;
     __syncthreads();   // everyone is done with the previous tile
-    // Warp w stages input channels 4w .. 4w+3 (6 patch rows each) and dY channels
-    // 4w .. 4w+3 (4 rows each), lanes along x.  Everything but the per-tile base
-    // pointer and the edge predicates is a compile-time offset: the first version
-    // recomputed (channel, row) from a loop counter and spent 28 % of the kernel's
-    // instructions (on the same pipe as the FFMA2s) on address arithmetic.
-    {
-      // column / row indices are clamped into the image so that every source
-      // address is valid; out-of-image elements are copies of size 0 (zero fill)
-      const int gx = x0 + lane - pad, gx2 = gx + kWgTW;
-      const bool ok0 = gx >= 0 && gx < WI;
-      const bool ok1 = gx2 >= 0 && gx2 < WI;
-      const int cx0 = min(max(gx, 0), WI - 1), cx1 = min(max(gx2, 0), WI - 1);
-      const size_t chs = (size_t)HI * WI;
-      const float* src_c = x + ((size_t)n * CI + ci0 + warp * 4) * chs;
-      float* dst_c = X_s + lane * kWgXS + warp * 4;
-#pragma unroll
-      for (int r = 0; r < kWgPR; ++r) {
-        const int gy = y0 + r - pad;
-        const bool row_ok = gy >= 0 && gy < HI;
-        const float* src = src_c + (size_t)min(max(gy, 0), HI - 1) * WI;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float* dst = dst_c + r * kWgPC * kWgXS + c;
-          wg_copy4(dst, src + cx0, row_ok && ok0);
-          if (lane < 2) wg_copy4(dst + kWgTW * kWgXS, src + cx1, row_ok && ok1);
-          src += chs;
-        }
-      }
-      const size_t ohs = (size_t)H * W;
-      const float* dsrc = dy + (((size_t)n * CO + co0 + warp * 4) * H + y0) * W + x0 + lane;
-      float* ddst = D_s + lane * kWgDS + warp * 4;
-#pragma unroll
-      for (int r = 0; r < kWgTH; ++r) {
-        const float* src = dsrc + (size_t)r * W;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          wg_copy4(ddst + r * kWgTW * kWgDS + c, src, true);
-          src += ohs;
-        }
-      }
-    }
+    wg_stage(X_s, D_s, x, dy, tile, tiles_x, tiles_y, CI, CO, ci0, co0, H, W, HI, WI, pad, lane,
+             warp);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-#pragma unroll 1
-    for (int r = 0; r < kWgTH; ++r) {
-      cf w[3][3];   // sliding window, every value duplicated into both halves of a pair
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const float a = X_s[((r + ky) * kWgPC + 0) * kWgXS + lane];
-        const float b = X_s[((r + ky) * kWgPC + 1) * kWgXS + lane];
-        w[ky][1] = mk(a, a);
-        w[ky][2] = mk(b, b);
-      }
-#pragma unroll
-      for (int xx = 0; xx < kWgTW; ++xx) {
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const float c = X_s[((r + ky) * kWgPC + xx + 2) * kWgXS + lane];
-          w[ky][0] = w[ky][1];
-          w[ky][1] = w[ky][2];
-          w[ky][2] = mk(c, c);
-        }
-        const float4 d = *reinterpret_cast<const float4*>(&D_s[(r * kWgTW + xx) * kWgDS + warp * 4]);
-        const cf d01 = mk(d.x, d.y), d23 = mk(d.z, d.w);
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            acc[ky * 3 + kx][0] = f2fma(d01, w[ky][kx], acc[ky * 3 + kx][0]);
-            acc[ky * 3 + kx][1] = f2fma(d23, w[ky][kx], acc[ky * 3 + kx][1]);
-          }
-      }
-    }
+    wg_compute(X_s, D_s, acc, lane, warp);
   }
   // partial block in dW order: [co][ci][tap]
   float* dst = partial +

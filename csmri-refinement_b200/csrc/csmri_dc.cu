@@ -640,6 +640,12 @@ static int check_ptr(const void* p, const char* name) {
     if (rc_ != CSMRI_OK) return rc_; \
   } while (0)
 
+static int check_ptr16(const void* p, const char* name) {
+  CSMRI_TRY(check_ptr(p, name));
+  if (((uintptr_t)p & 15u) != 0) return fail(CSMRI_E_ALIGN, "%s is not 16-byte aligned", name);
+  return CSMRI_OK;
+}
+
 // cudaFuncSetAttribute is issued once per (kernel, device), never on the hot
 // path: per-launch calls showed up as a ~9 us bubble between back-to-back
 // launches in the per-CTA timeline (tools/gpu_trace.py).
@@ -1468,8 +1474,8 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
     return CSMRI_OK;
   }
   constexpr int smem = kWgSmemFloats * (int)sizeof(float);
-  CSMRI_TRY(set_smem(conv3x3_wgrad_kernel, smem));
   const dim3 grid(parts, CO / kWgC, CI / kWgC);
+  CSMRI_TRY(set_smem(conv3x3_wgrad_kernel, smem));
   conv3x3_wgrad_kernel<<<grid, 256, smem, s>>>(x, dy, (float*)workspace, CI, CO, H, W,
                                                H + 2 - 2 * pad, W + 2 - 2 * pad, pad, tiles_x,
                                                tiles_y, ntiles);
@@ -1483,28 +1489,30 @@ int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float*
                        int B, int H, int W, float slope, void* stream) {
   if (!wgrad_thin(A, B))
     return fail(CSMRI_E_SHAPE, "conv3x3_thin handles 2 -> 32 and 32 -> 2 channels (got %d -> %d)", A, B);
-  if (N <= 0 || H <= 0 || W <= 0 || H % kThinRows != 0 || W % 32 != 0)
+  if (N <= 0 || H <= 0 || W <= 0 || H % kThinOutRows != 0 || W % 32 != 0)
     return fail(CSMRI_E_SHAPE, "conv3x3_thin needs H %% %d == 0 and W %% 32 == 0 (got %dx%dx%d)",
-                kThinRows, N, H, W);
+                kThinOutRows, N, H, W);
   if (!(slope >= 0.0f)) return fail(CSMRI_E_ARG, "slope must be >= 0 (got %g)", slope);
   if (A == 32 && slope != 0.0f)
     return fail(CSMRI_E_ARG, "the 32 -> 2 layer has no activation (models/recnet.py:48)");
-  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr16(x, "x"));
   CSMRI_TRY(check_ptr(w, "w"));
   CSMRI_TRY(check_ptr(y, "y"));
   if (x == y) return fail(CSMRI_E_ARG, "y must not alias x");
-  const int tiles_x = W / 32, tiles_y = H / kThinRows;
+  const int tiles_x = W / 32, tiles_y = H / (A == 2 ? kThinOutRows : kThinInRows);
   const long long ntiles_ll = (long long)N * tiles_x * tiles_y;
   if (ntiles_ll > 0x7fffffffLL) return fail(CSMRI_E_SHAPE, "too many tiles");
   int ctas = sm_count() * 2;
   if (ctas > ntiles_ll) ctas = (int)ntiles_ll;
   cudaStream_t s = (cudaStream_t)stream;
-  if (A == 2)
+  if (A == 2) {
     conv3x3_thin_out_kernel<<<ctas, 256, 0, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
                                                  (int)ntiles_ll, slope);
-  else
-    conv3x3_thin_in_kernel<<<ctas, 256, 0, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
-                                                (int)ntiles_ll);
+  } else {
+    CSMRI_TRY(set_smem(conv3x3_thin_in_kernel, kThinInSmem));
+    conv3x3_thin_in_kernel<<<ctas, 256, kThinInSmem, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
+                                                          (int)ntiles_ll);
+  }
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }
@@ -1516,11 +1524,6 @@ static int check_epilogue(int N, int C, int H, int W, float slope) {
     return fail(CSMRI_E_SHAPE, "bias_lrelu: bad shape %dx%dx%dx%d (H*W %% 4, N*C <= 65535)", N, C,
                 H, W);
   if (!(slope > 0.0f)) return fail(CSMRI_E_ARG, "bias_lrelu: slope must be > 0 (got %g)", slope);
-  return CSMRI_OK;
-}
-static int check_ptr16(const void* p, const char* name) {
-  CSMRI_TRY(check_ptr(p, name));
-  if (((uintptr_t)p & 15u) != 0) return fail(CSMRI_E_ALIGN, "%s is not 16-byte aligned", name);
   return CSMRI_OK;
 }
 
