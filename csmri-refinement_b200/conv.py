@@ -44,6 +44,8 @@ def conv3x3_wgrad(x, grad_out, pad):
 def _eligible(x, weight, stride, padding, dilation, groups):
     if not (_ENABLED and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32):
         return False
+    if x.dim() != 4 or not x.is_contiguous() or not weight.is_contiguous():
+        return False          # e.g. channels_last: the kernels address plain NCHW
     if tuple(weight.shape[2:]) != (3, 3) or groups != 1:
         return False
     if tuple(stride) != (1, 1) or tuple(dilation) != (1, 1) or tuple(padding) not in ((0, 0), (1, 1)):
@@ -173,9 +175,17 @@ class Conv2d(nn.Conv2d):
         slope = self.fused_slope
         if self.padding_mode == 'zeros' and not isinstance(self.padding, str) and \
                 _eligible(x, self.weight, self.stride, self.padding, self.dilation, self.groups) \
-                and torch.is_grad_enabled() and self.weight.requires_grad \
                 and (slope is None or (self.bias is not None and slope > 0)):
-            return _Conv3x3.apply(x, self.weight, self.bias, int(self.padding[0]), slope)
+            pad = int(self.padding[0])
+            if torch.is_grad_enabled() and (self.weight.requires_grad or x.requires_grad):
+                return _Conv3x3.apply(x, self.weight, self.bias, pad, slope)
+            # inference: same kernels, nothing saved
+            if _is_thin(self.weight, pad) and (slope is None or self.weight.shape[1] == 2):
+                return conv3x3_thin(x, self.weight, self.bias, slope or 0.0)
+            if slope is not None:
+                y = torch.ops.aten.convolution(x, self.weight, None, [1, 1], [pad, pad], [1, 1],
+                                               False, [0, 0], 1)
+                return bias_lrelu_(y, self.bias, slope)
         out = super(Conv2d, self).forward(x)
         if slope is not None:
             out = nn.functional.leaky_relu(out, slope, inplace=True)

@@ -678,3 +678,34 @@ def test_conv3x3_thin_matches_torch(shape):
         assert orc.rel_l2(gx.cpu().numpy(), x64.grad.cpu().numpy()) < 1e-6
     with pytest.raises(RuntimeError):
         conv.conv3x3_thin(x[:, :, :8], wt, bias, slope)      # H % 16 != 0
+
+
+def test_conv_module_falls_back_for_layouts_the_kernels_do_not_cover():
+    """channels_last / half inputs and grad-free calls keep torch's own path and
+    still apply the fused activation's semantics."""
+    from csmri_refinement_b200 import conv
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(3)
+    m = conv.Conv2d(32, 32, 3, padding=1).cuda()
+    m.fused_slope = 0.01
+    x = torch.randn(2, 32, 16, 32, device='cuda')
+    ref = torch.nn.functional.leaky_relu(
+        torch.nn.functional.conv2d(x, m.weight, m.bias, 1, 1), 0.01)
+    for inp in (x, x.to(memory_format=torch.channels_last)):
+        got = m(inp)
+        assert (got - ref).norm().item() < 1e-5 * ref.norm().item()
+    with torch.no_grad():
+        assert (m(x) - ref).norm().item() < 1e-5 * ref.norm().item()
+    # the fused path and torch's agree on input / bias gradients too
+    xg = x.clone().requires_grad_(True)
+    m(xg).square().sum().backward()
+    gx, gb = xg.grad.clone(), m.bias.grad.clone()
+    conv.set_fast_wgrad(False)
+    try:
+        m.zero_grad()
+        xr = x.clone().requires_grad_(True)
+        m(xr).square().sum().backward()
+    finally:
+        conv.set_fast_wgrad(True)
+    assert (gx - xr.grad).norm().item() < 1e-5 * xr.grad.norm().item()
+    assert (gb - m.bias.grad).norm().item() < 1e-5 * m.bias.grad.norm().item()
