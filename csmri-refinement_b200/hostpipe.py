@@ -9,7 +9,7 @@ adjoint, device->host - so that, after the first chunk, the step costs what the
 (full-duplex) PCIe link costs and nothing else.
 
 It is the same public operator underneath
-(:func:`csmri_refinement_b200.myfft.data_consistency` semantics,
+(:func:`csmri_refinement_b200.myfft.dc_perform` semantics,
 myfft.py:131-163 forward and :92-128 backward); masks are *assumed*
 row-constant while streaming and the assumption is verified for every chunk at
 the end with a single device->host read - if any chunk fails it, the step is

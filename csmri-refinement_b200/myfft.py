@@ -1,4 +1,11 @@
-"""Drop-in for data/reconstruction/deep_med_lib/my_pytorch/myfft.py:145-163.
+"""Drop-in for data/reconstruction/deep_med_lib/my_pytorch/myfft.py.
+
+Public names of the reference module that sit on the DC path keep their name and
+argument meaning: ``make_contiguous``, ``contiguous_clone`` (:10-18), ``Fft2d`` /
+``Ifft2d`` (:78-128, two-tensor real / imaginary calling convention, autograd
+included), ``data_consistency(k, k0, mask, noise_lvl)`` (:131-142, the k-space
+blend alone) and ``DataConsistencyInKspace`` (:145-163).  The 1-D ``Fft`` / ``Ifft``
+(:21-75) are not on the path and are not provided.
 
 ``DataConsistencyInKspace(noise_lvl=None, norm='ortho').perform(x, k0, mask)``
 keeps the reference's name, arguments and semantics; the work is done by the
@@ -115,8 +122,84 @@ def clear_plan_cache():
     _PLAN_CACHE.clear()
 
 
-def data_consistency(x, k0, mask, noise_lvl=None, residual=None, plan=None):
-    """iFFT2o(blend(FFT2o(x [+ residual]), k0, mask)) - myfft.py:131-163 in one op."""
+def make_contiguous(*Xs):
+    """myfft.py:10-11."""
+    return tuple(X if X.is_contiguous() else X.contiguous() for X in Xs)
+
+
+def contiguous_clone(X):
+    """myfft.py:14-18."""
+    return X.clone() if X.is_contiguous() else X.contiguous()
+
+
+class _Fft2Planar(torch.autograd.Function):
+    """scale * (i)FFT2_ortho of a planar (B,2,H,W) tensor.  The adjoint of a unitary
+    transform is its inverse, which is what the reference's swapped-plane
+    backward (myfft.py:92-102, 119-128) evaluates."""
+
+    @staticmethod
+    def forward(ctx, x, inverse, scale):
+        ctx.inverse, ctx.scale = inverse, scale
+        out = ops.fft2_planar(x, inverse=inverse)
+        return out if scale == 1.0 else out * scale
+
+    @staticmethod
+    def backward(ctx, grad):
+        g = ops.fft2_planar(grad.contiguous(), inverse=not ctx.inverse)
+        return (g if ctx.scale == 1.0 else g * ctx.scale), None, None
+
+
+class _Fft2dBase(object):
+    _inverse = False
+
+    def __init__(self, norm=None):
+        if norm not in (None, 'ortho'):
+            raise ValueError("norm must be None or 'ortho', got %r" % (norm,))
+        self.norm = norm
+
+    def __call__(self, X_re, X_im):
+        if X_re.shape != X_im.shape or X_re.dim() < 2:
+            raise ValueError('real and imaginary parts must have the same (..., H, W) shape')
+        h, w = X_re.shape[-2], X_re.shape[-1]
+        lead = X_re.shape[:-2]
+        x = torch.stack((X_re.reshape(-1, h, w), X_im.reshape(-1, h, w)), dim=1)
+        # pytorch_fft: fft2 un-normalised, ifft2 divides by H*W (myfft.py:85,112)
+        n = float(h * w) ** 0.5
+        scale = 1.0 if self.norm == 'ortho' else (1.0 / n if self._inverse else n)
+        out = _Fft2Planar.apply(x, self._inverse, scale)
+        return out[:, 0].reshape(*lead, h, w), out[:, 1].reshape(*lead, h, w)
+
+    forward = __call__
+
+
+class Fft2d(_Fft2dBase):
+    """myfft.py:78-102: ``k_re, k_im = Fft2d(norm)(X_re, X_im)`` over the last two axes."""
+    _inverse = False
+
+
+class Ifft2d(_Fft2dBase):
+    """myfft.py:105-128: ``x_re, x_im = Ifft2d(norm)(k_re, k_im)``."""
+    _inverse = True
+
+
+def data_consistency(k, k0, mask, noise_lvl=None):
+    """myfft.py:131-142, the blend alone, for callers that hold k-space already
+    (same tensor expression as the reference, hence bit-identical; inside
+    :meth:`DataConsistencyInKspace.perform` it is fused into the strip kernel).
+    k    - input in k-space
+    k0   - initially sampled elements in k-space
+    mask - corresponding nonzero location
+    """
+    v = noise_lvl
+    if v:  # noisy case
+        out = (1 - mask) * k + mask * (k + v * k0) / (1 + v)
+    else:  # noiseless case
+        out = (1 - mask) * k + k0
+    return out
+
+
+def dc_perform(x, k0, mask, noise_lvl=None, residual=None, plan=None):
+    """iFFT2o(blend(FFT2o(x [+ residual]), k0, mask)) - myfft.py:153-163 in one op."""
     if not x.is_cuda:
         raise RuntimeError('DataConsistencyInKspace needs CUDA tensors: the B200 DC path has '
                            'no CPU fallback (use oracle/ for CPU checks)')
@@ -145,4 +228,4 @@ class DataConsistencyInKspace(object):
         residual - optional extension: added to x before the transform
                    (the `x + block_input` of models/recnet.py:147-148)
         """
-        return data_consistency(x, k0, mask, self.noise_lvl, residual)
+        return dc_perform(x, k0, mask, self.noise_lvl, residual)

@@ -106,10 +106,10 @@ def test_cartesian_equals_general_path():
     myfft, ops, _, _ = _mods()
     x, k0, mask = _problem(4, 256, 256, acc=8, seed=3)
     xd, k0d, md = _cuda(x, k0, mask)
-    a = myfft.data_consistency(xd, k0d, md, None)
+    a = myfft.dc_perform(xd, k0d, md, None)
     b = ops.dc_general(xd, None, k0d, md, 0.0)
     assert orc.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
-    a = myfft.data_consistency(xd, k0d, md, 0.1)
+    a = myfft.dc_perform(xd, k0d, md, 0.1)
     b = ops.dc_general(xd, None, k0d, md, 0.1)
     assert orc.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
 
@@ -303,7 +303,7 @@ def test_plan_cache_and_errors():
     k0d.mul_(2.0)                          # in-place edit -> version bump -> new plan
     p2 = myfft.get_plan(k0d, md)
     assert p2 is not p1
-    out = myfft.data_consistency(xd, k0d, md)
+    out = myfft.dc_perform(xd, k0d, md)
     assert orc.rel_l2(out.cpu().numpy(), orc.dc_perform_np(x, 2 * k0, mask)) < TOL
     with pytest.raises(RuntimeError):
         myfft.DataConsistencyInKspace().perform(xd.cpu(), k0d.cpu(), md.cpu())
@@ -314,7 +314,7 @@ def test_plan_cache_and_errors():
         myfft.DataConsistencyInKspace(norm=None)
     # non-contiguous input is accepted like the reference (.contiguous() inside)
     xn = torch.randn(2, 64, 64, 2, device='cuda').permute(0, 3, 1, 2)
-    o = myfft.data_consistency(xn, k0d, md)
+    o = myfft.dc_perform(xn, k0d, md)
     ref = orc.dc_perform_np(xn.cpu().numpy(), 2 * k0, mask)
     assert orc.rel_l2(o.cpu().numpy(), ref) < TOL
 
@@ -326,7 +326,7 @@ def test_mask_zero_and_one_edge_cases():
     for fill in (0.0, 1.0):
         m = np.full_like(mask, fill)
         (md,) = _cuda(m)
-        out = myfft.data_consistency(xd, k0d, md)
+        out = myfft.dc_perform(xd, k0d, md)
         assert orc.rel_l2(out.cpu().numpy(), orc.dc_perform_np(x, k0, m)) < TOL
 
 
@@ -532,7 +532,7 @@ def test_loader_hands_over_the_dc_plan(monkeypatch):
     x = torch.randn(B, 2, n, n, device='cuda')
     handed = myfft.get_plan(batch['kspace'], batch['mask'])
     assert handed.row_constant
-    out_handed = myfft.data_consistency(x, batch['kspace'], batch['mask'])
+    out_handed = myfft.dc_perform(x, batch['kspace'], batch['mask'])
     fresh = myfft.DCPlan(batch['kspace'], batch['mask'], 0.0)
     assert fresh.row_constant
     assert torch.equal(handed.dtab, fresh.dtab)
@@ -709,3 +709,44 @@ def test_conv_module_falls_back_for_layouts_the_kernels_do_not_cover():
         conv.set_fast_wgrad(True)
     assert (gx - xr.grad).norm().item() < 1e-5 * xr.grad.norm().item()
     assert (gb - m.bias.grad).norm().item() < 1e-5 * m.bias.grad.norm().item()
+
+
+@pytest.mark.parametrize('norm', [None, 'ortho'])
+def test_fft2d_ifft2d_mirror_reference_conventions(norm):
+    """Fft2d / Ifft2d with the reference's two-tensor calling convention against
+    np.fft (what myfft.py:186-243 asserts), their autograd adjoints, and the
+    reference's own chain Fft2d -> data_consistency -> Ifft2d against perform()."""
+    myfft, ops, _, us = _mods()
+    rs = np.random.RandomState(7)
+    xr = rs.normal(size=(3, 1, 64, 128)).astype(np.float32)
+    xi = rs.normal(size=(3, 1, 64, 128)).astype(np.float32)
+    tr, ti = torch.from_numpy(xr).cuda().requires_grad_(True), torch.from_numpy(xi).cuda().requires_grad_(True)
+    kr, ki = myfft.Fft2d(norm)(tr, ti)
+    ref = np.fft.fft2(xr.astype(np.float64) + 1j * xi, norm=norm)
+    assert orc.rel_l2(kr.detach().cpu().numpy(), ref.real) < 2e-6
+    assert orc.rel_l2(ki.detach().cpu().numpy(), ref.imag) < 2e-6
+    br, bi = myfft.Ifft2d(norm)(kr, ki)
+    assert orc.rel_l2(br.detach().cpu().numpy(), xr) < 2e-6
+    assert orc.rel_l2(bi.detach().cpu().numpy(), xi) < 2e-6
+    # adjoint: d/dx <F x, w> = F^H w
+    wr = torch.from_numpy(rs.normal(size=xr.shape).astype(np.float32)).cuda()
+    wi = torch.from_numpy(rs.normal(size=xr.shape).astype(np.float32)).cuda()
+    gr, gi = torch.autograd.grad((kr * wr).sum() + (ki * wi).sum(), (tr, ti))
+    n = 64 * 128
+    adj = np.fft.ifft2(wr.cpu().numpy().astype(np.float64) + 1j * wi.cpu().numpy(),
+                       norm=norm) * (1.0 if norm == 'ortho' else n)
+    assert orc.rel_l2(gr.cpu().numpy(), adj.real) < 2e-6
+    assert orc.rel_l2(gi.cpu().numpy(), adj.imag) < 2e-6
+    if norm == 'ortho':
+        B, m = 3, 64
+        img = torch.rand(B, m, m, device='cuda')
+        batch = us.undersample(img, us.cartesian_rows((B, m, m), 4, 8, False,
+                                                      np.random.RandomState(1)))
+        x = torch.randn(B, 2, m, m, device='cuda')
+        for v in (None, 0.1):
+            k = torch.cat(myfft.Fft2d('ortho')(x[:, 0:1], x[:, 1:2]), 1)
+            out = myfft.data_consistency(k, batch['kspace'], batch['mask'], v)
+            chain = torch.cat(myfft.Ifft2d('ortho')(out[:, 0:1], out[:, 1:2]), 1)
+            fused = myfft.DataConsistencyInKspace(noise_lvl=v).perform(x, batch['kspace'],
+                                                                         batch['mask'])
+            assert (chain - fused).norm().item() < 2e-6 * fused.norm().item()
