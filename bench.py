@@ -15,6 +15,9 @@ Prints ONE JSON line (rank 0).  `value` = slices/s with inputs resident in HBM;
 with HOST (pinned) buffers, copies inside the timed region; `roofline` = the
 strip kernel's algorithmic bytes / its CUDA-event time against the measured
 HBM peak; `cpu_baseline` = the oracle port on the host cores (bounded sample).
+Extra keys: `noisy_lambda` (the same microbench with noise_lvl = 0.1) and
+`recnet_train` (BASELINE configs[2]: RecNet D5C5 fp32 training step, batch 32 per
+GPU, with `tf32_convs` as a context number).
 """
 import argparse
 import json
@@ -437,7 +440,7 @@ def main():
                          'x/k0/mask/grad-seed in, out/grad_x back, copies and compute in sequence; '
                          'includes the per-batch prepare'}
 
-    # same work through the streamed public API: chunks of 32 slices on three
+    # same work through the streamed public API: chunks of 64 slices on three
     # streams (H2D / DC forward+adjoint incl. prepare / D2H), full-duplex PCIe
     from csmri_refinement_b200 import hostpipe
     pipe = hostpipe.HostDCPipeline(dev, chunk=64, depth=3)
