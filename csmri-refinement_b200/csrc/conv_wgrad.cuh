@@ -9,11 +9,11 @@
 //
 // The product is a (CO x 9*CI) GEMM with a huge reduction dimension (all
 // pixels), so the CTAs split the pixels: each one accumulates the complete
-// 32 x 32 x 9 block of weight gradients for its tiles in registers (36 per
-// thread: lane = input channel, warp = group of 4 output channels, 9 taps) and
+// 32 x 32 x 9 block of weight gradients for its tiles in registers (72 per
+// thread: lane = input channel, warp = group of 8 output channels, 9 taps) and
 // the partial blocks are summed by a second kernel in a fixed order
-// (deterministic, no atomics).  Per pixel a thread issues 18 packed FFMA2
-// (two output channels per instruction), fed by one broadcast LDS.128 of dY and
+// (deterministic, no atomics).  Per pixel a thread issues 36 packed FFMA2
+// (two output channels per instruction), fed by two broadcast LDS.128 of dY and
 // three conflict-free LDS of the sliding 3x3 input window: the FP32 pipe is the
 // bound, shared memory and issue slots stay below it.
 #pragma once
@@ -50,10 +50,12 @@ __device__ __forceinline__ void wg_copy4(float* dst, const float* src, bool vali
 // instructions, on the same pipe as the FFMA2s, on address arithmetic).  Column /
 // row indices are clamped into the image so that every source address is valid;
 // out-of-image elements are copies of size 0 (zero fill).
+template <int NW>   // NW warps stage the tile: warp w takes channels w*(32/NW) .. of x and of dY
 __device__ __forceinline__ void wg_stage(float* X_s, float* D_s, const float* __restrict__ x,
                                          const float* __restrict__ dy, int tile, int tiles_x,
                                          int tiles_y, int CI, int CO, int ci0, int co0, int H, int W,
                                          int HI, int WI, int pad, int lane, int warp) {
+  constexpr int CPW = kWgC / NW;   // channels per warp
   const int n = tile / (tiles_x * tiles_y);
   const int rem = tile - n * tiles_x * tiles_y;
   const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
@@ -63,15 +65,15 @@ __device__ __forceinline__ void wg_stage(float* X_s, float* D_s, const float* __
   const bool ok1 = gx2 >= 0 && gx2 < WI;
   const int cx0 = min(max(gx, 0), WI - 1), cx1 = min(max(gx2, 0), WI - 1);
   const size_t chs = (size_t)HI * WI;
-  const float* src_c = x + ((size_t)n * CI + ci0 + warp * 4) * chs;
-  float* dst_c = X_s + lane * kWgXS + warp * 4;
+  const float* src_c = x + ((size_t)n * CI + ci0 + warp * CPW) * chs;
+  float* dst_c = X_s + lane * kWgXS + warp * CPW;
 #pragma unroll
   for (int r = 0; r < kWgPR; ++r) {
     const int gy = y0 + r - pad;
     const bool row_ok = gy >= 0 && gy < HI;
     const float* src = src_c + (size_t)min(max(gy, 0), HI - 1) * WI;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < CPW; ++c) {
       float* dst = dst_c + r * kWgPC * kWgXS + c;
       wg_copy4(dst, src + cx0, row_ok && ok0);
       if (lane < 2) wg_copy4(dst + kWgTW * kWgXS, src + cx1, row_ok && ok1);
@@ -79,22 +81,23 @@ __device__ __forceinline__ void wg_stage(float* X_s, float* D_s, const float* __
     }
   }
   const size_t ohs = (size_t)H * W;
-  const float* dsrc = dy + (((size_t)n * CO + co0 + warp * 4) * H + y0) * W + x0 + lane;
-  float* ddst = D_s + lane * kWgDS + warp * 4;
+  const float* dsrc = dy + (((size_t)n * CO + co0 + warp * CPW) * H + y0) * W + x0 + lane;
+  float* ddst = D_s + lane * kWgDS + warp * CPW;
 #pragma unroll
   for (int r = 0; r < kWgTH; ++r) {
     const float* src = dsrc + (size_t)r * W;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < CPW; ++c) {
       wg_copy4(ddst + r * kWgTW * kWgDS + c, src, true);
       src += ohs;
     }
   }
 }
 
-// one staged tile into the thread's 36 accumulators: 18 FFMA2 per pixel
-__device__ __forceinline__ void wg_compute(const float* X_s, const float* D_s, cf (&acc)[9][2],
-                                           int lane, int warp) {
+// one staged tile into the thread's 9*COT accumulators: 9*COT/2 FFMA2 per pixel
+template <int COT>
+__device__ __forceinline__ void wg_compute(const float* X_s, const float* D_s,
+                                           cf (&acc)[9][COT / 2], int lane, int warp) {
 #pragma unroll 1
   for (int r = 0; r < kWgTH; ++r) {
     float w[3][3];   // sliding window
@@ -111,25 +114,34 @@ __device__ __forceinline__ void wg_compute(const float* X_s, const float* D_s, c
         w[ky][1] = w[ky][2];
         w[ky][2] = X_s[((r + ky) * kWgPC + xx + 2) * kWgXS + lane];
       }
-      const float4 d = *reinterpret_cast<const float4*>(&D_s[(r * kWgTW + xx) * kWgDS + warp * 4]);
-      const cf d01 = mk(d.x, d.y), d23 = mk(d.z, d.w);
+      cf dp[COT / 2];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+      for (int q = 0; q < COT / 4; ++q) {
+        const float4 d = *reinterpret_cast<const float4*>(
+            &D_s[(r * kWgTW + xx) * kWgDS + warp * COT + 4 * q]);
+        dp[2 * q] = mk(d.x, d.y);
+        dp[2 * q + 1] = mk(d.z, d.w);
+      }
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          // packed FFMA2 with a scalar-broadcast operand: two output channels per
-          // instruction (scalar FFMAs measured 15 % slower: issue-bound)
-          acc[ky * 3 + kx][0] = f2fma(d01, mk(w[ky][kx], w[ky][kx]), acc[ky * 3 + kx][0]);
-          acc[ky * 3 + kx][1] = f2fma(d23, mk(w[ky][kx], w[ky][kx]), acc[ky * 3 + kx][1]);
-        }
+      for (int o = 0; o < COT / 2; ++o)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            // packed FFMA2 with a scalar-broadcast operand: two output channels per
+            // instruction (scalar FFMAs measured 15 % slower: issue-bound)
+            acc[ky * 3 + kx][o] = f2fma(dp[o], mk(w[ky][kx], w[ky][kx]), acc[ky * 3 + kx][o]);
     }
   }
 }
 
-// grid: (CTAs sharing the pixel tiles, CO / 32, CI / 32); block: 256.  One tile
-// buffer per CTA; four resident CTAs hide each other's staging (a double-buffered
-// variant with two CTAs per SM measured the same: profiles/README.md).
-__global__ void __launch_bounds__(256, 4)
+// grid: (CTAs sharing the pixel tiles, CO / 32, CI / 32); block: 32 * (32 / COT).
+// One tile buffer per CTA; four resident CTAs hide each other's staging (a
+// double-buffered variant with two CTAs per SM measured the same).
+// COT = output channels per thread: 4 (256 threads, 36 accumulators) or
+// 8 (128 threads, 72 accumulators, half the shared-memory loads per FFMA2).
+template <int COT>
+__global__ void __launch_bounds__(32 * (kWgC / COT), 4)
     conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                          float* __restrict__ partial, int CI, int CO, int H, int W, int HI, int WI,
                          int pad, int tiles_x, int tiles_y, int ntiles) {
@@ -137,31 +149,33 @@ __global__ void __launch_bounds__(256, 4)
   float* X_s = wg_smem;
   float* D_s = wg_smem + kWgPR * kWgPC * kWgXS;
   const int lane = threadIdx.x & 31;        // input channel within the block
-  const int warp = threadIdx.x >> 5;        // group of four output channels
+  const int warp = threadIdx.x >> 5;        // group of COT output channels
   const int co0 = blockIdx.y * kWgC, ci0 = blockIdx.z * kWgC;
 
-  cf acc[9][2];
+  cf acc[9][COT / 2];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = mk(0.0f, 0.0f);
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int o = 0; o < COT / 2; ++o) acc[t][o] = mk(0.0f, 0.0f);
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     __syncthreads();   // everyone is done with the previous tile
-    wg_stage(X_s, D_s, x, dy, tile, tiles_x, tiles_y, CI, CO, ci0, co0, H, W, HI, WI, pad, lane,
-             warp);
+    wg_stage<kWgC / COT>(X_s, D_s, x, dy, tile, tiles_x, tiles_y, CI, CO, ci0, co0, H, W, HI, WI,
+                         pad, lane, warp);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    wg_compute(X_s, D_s, acc, lane, warp);
+    wg_compute<COT>(X_s, D_s, acc, lane, warp);
   }
   // partial block in dW order: [co][ci][tap]
   float* dst = partial +
                ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kWgBlock;
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    dst[((warp * 4 + 0) * kWgC + lane) * 9 + t] = acc[t][0].x;
-    dst[((warp * 4 + 1) * kWgC + lane) * 9 + t] = acc[t][0].y;
-    dst[((warp * 4 + 2) * kWgC + lane) * 9 + t] = acc[t][1].x;
-    dst[((warp * 4 + 3) * kWgC + lane) * 9 + t] = acc[t][1].y;
-  }
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int o = 0; o < COT / 2; ++o) {
+      dst[((warp * COT + 2 * o) * kWgC + lane) * 9 + t] = acc[t][o].x;
+      dst[((warp * COT + 2 * o + 1) * kWgC + lane) * 9 + t] = acc[t][o].y;
+    }
 }
 
 // dw[co][ci][tap] = sum over the `nparts` partial blocks of its channel-block pair

@@ -675,6 +675,7 @@ static int set_smem(K kernel, int bytes) {
 __device__ unsigned g_sched[128];     // 64 x (tiles handed out, retired CTAs), zero = armed
 static std::atomic<unsigned> g_sched_next{0};   // launches may come from several host threads
 static int g_use_pdl = 1;             // programmatic dependent launch for the strip kernels
+static int g_wgrad_cot = 8;      // output channels per thread of conv3x3_wgrad_kernel (8; 4 = A/B baseline)
 static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_set_tuning
 static long long* g_trace = nullptr;  // tuning probe: per-CTA timeline buffers (2 x 1024 x 40)
 static int g_trace_launch = 0;
@@ -1111,6 +1112,7 @@ int csmri_set_trace(void* device_buffer) {
 int csmri_set_tuning(int key, int value) {
   if (key == 0) g_strip_variant = value;
   else if (key == 4) g_use_pdl = value;
+  else if (key == 5) g_wgrad_cot = value == 8 ? 8 : 4;
   else return fail(CSMRI_E_ARG, "unknown tuning key %d", key);
   return CSMRI_OK;
 }
@@ -1475,10 +1477,17 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
   }
   constexpr int smem = kWgSmemFloats * (int)sizeof(float);
   const dim3 grid(parts, CO / kWgC, CI / kWgC);
-  CSMRI_TRY(set_smem(conv3x3_wgrad_kernel, smem));
-  conv3x3_wgrad_kernel<<<grid, 256, smem, s>>>(x, dy, (float*)workspace, CI, CO, H, W,
-                                               H + 2 - 2 * pad, W + 2 - 2 * pad, pad, tiles_x,
-                                               tiles_y, ntiles);
+  if (g_wgrad_cot == 8) {
+    CSMRI_TRY(set_smem(conv3x3_wgrad_kernel<8>, smem));
+    conv3x3_wgrad_kernel<8><<<grid, 128, smem, s>>>(x, dy, (float*)workspace, CI, CO, H, W,
+                                                    H + 2 - 2 * pad, W + 2 - 2 * pad, pad, tiles_x,
+                                                    tiles_y, ntiles);
+  } else {
+    CSMRI_TRY(set_smem(conv3x3_wgrad_kernel<4>, smem));
+    conv3x3_wgrad_kernel<4><<<grid, 256, smem, s>>>(x, dy, (float*)workspace, CI, CO, H, W,
+                                                    H + 2 - 2 * pad, W + 2 - 2 * pad, pad, tiles_x,
+                                                    tiles_y, ntiles);
+  }
   conv3x3_wgrad_reduce_kernel<<<dim3(kWgBlock / 256, CO / kWgC, CI / kWgC), 256, 0, s>>>(
       (const float*)workspace, dw, CI, parts);
   CSMRI_CUDA(cudaGetLastError());

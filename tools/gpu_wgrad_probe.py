@@ -6,7 +6,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from csmri_refinement_b200 import conv  # noqa: E402
+from csmri_refinement_b200 import _lib, conv  # noqa: E402
+
+_lib.lib().csmri_set_tuning(5, int(os.environ.get('WGRAD_COT', '8')))
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cudnn.benchmark = True
