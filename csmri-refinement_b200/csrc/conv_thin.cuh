@@ -260,4 +260,105 @@ __global__ void __launch_bounds__(256, 2)
   }
 }
 
+// ---------------------------------------------------------------------------
+// Weight gradient of the 32 -> 2 layer with the input tile staged like thin_in
+// (zero padding 1).  dw[o][c][tap] = sum dy[n][o][y][x] * x[n][c][y+ky-1][x+kx-1]:
+// warp g owns input channels 4g .. 4g+3, lanes own pixels, 4 x 9 accumulator
+// pairs (o = 0, 1) per thread; dY (2 channels) comes straight from global memory.
+// The direct-from-global version (conv3x3_wgrad_thin_kernel) spent most of its
+// 130 M instructions on predicated loads and waited on them (ncu: long_scoreboard
+// 3.1 cycles per issue, FP32 pipe 20 %).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+    conv3x3_wgrad_thin_staged_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                     float* __restrict__ partial, int H, int W, int tiles_x,
+                                     int tiles_y, int ntiles) {
+  constexpr int A = 32, AT = 4, R = kThinInRows;
+  extern __shared__ __align__(16) float thin_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int cib = warp * AT;
+  cf acc[AT][9];
+#pragma unroll
+  for (int c = 0; c < AT; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[c][t] = mk(0.0f, 0.0f);
+  const size_t plane = (size_t)H * W;
+  auto stage_tile = [&](int tile, float* buf) {
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    const float* xc = x + ((size_t)t.n * A + cib) * plane;
+#pragma unroll 2
+    for (int pair = lane >> 3; pair < AT * (R + 2); pair += 4) {
+      const int c = pair / (R + 2), r = pair - c * (R + 2);
+      thin_stage_row4(buf + kThinLead + (cib * (R + 2) + pair) * kThinPC, xc + c * plane,
+                      t.y0 - 1 + r, t.x0, H, W, lane);
+    }
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) stage_tile(tile, thin_smem);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const float* cur = thin_smem + (it & 1) * kThinInBuf + kThinLead + cib * (R + 2) * kThinPC;
+    const int next = tile + gridDim.x;
+    if (next < ntiles) stage_tile(next, thin_smem + ((it + 1) & 1) * kThinInBuf);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    const float* dn = dy + ((size_t)t.n * 2 * H + t.y0) * W + t.x0 + lane;
+    float d0[R], d1[R];   // this tile's dY column: in flight while the tile lands
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      d0[r] = __ldg(dn + (size_t)r * W);
+      d1[r] = __ldg(dn + plane + (size_t)r * W);
+    }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    float win[AT][3][3];
+#pragma unroll
+    for (int c = 0; c < AT; ++c)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        win[c][1][kx] = cur[(c * (R + 2) + 0) * kThinPC + lane + kx - 1];
+        win[c][2][kx] = cur[(c * (R + 2) + 1) * kThinPC + lane + kx - 1];
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int c = 0; c < AT; ++c)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          win[c][0][kx] = win[c][1][kx];
+          win[c][1][kx] = win[c][2][kx];
+          win[c][2][kx] = cur[(c * (R + 2) + r + 2) * kThinPC + lane + kx - 1];
+        }
+      const cf d = mk(d0[r], d1[r]);
+#pragma unroll
+      for (int c = 0; c < AT; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            acc[c][ky * 3 + kx] =
+                f2fma(d, mk(win[c][ky][kx], win[c][ky][kx]), acc[c][ky * 3 + kx]);
+    }
+    __syncthreads();   // `cur` is the staging target of the next iteration
+  }
+  // fold the 32 pixel-lanes; lane 0 writes the warp's sums in dW order [o][c][tap]
+  float* dst = partial + (size_t)blockIdx.x * (A * 2 * 9);
+#pragma unroll
+  for (int c = 0; c < AT; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float a = acc[c][t].x, b = acc[c][t].y;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, m);
+        b += __shfl_xor_sync(0xffffffffu, b, m);
+      }
+      if (lane == 0) {
+        dst[(0 * A + cib + c) * 9 + t] = a;
+        dst[(1 * A + cib + c) * 9 + t] = b;
+      }
+    }
+}
+
 }  // namespace csmri

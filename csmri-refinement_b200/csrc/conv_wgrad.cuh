@@ -178,27 +178,33 @@ __global__ void __launch_bounds__(32 * (kWgC / COT), 4)
     }
 }
 
-// dw[co][ci][tap] = sum over the `nparts` partial blocks of its channel-block pair
-// grid: (36, CO / 32, CI / 32); block 256
-__global__ void __launch_bounds__(256)
+// dw[co][ci][tap] = sum over the `nparts` partial blocks of its channel-block pair.
+// grid: (kWgBlock / 64, CO / 32, CI / 32); block (64, 8): eight threads share an
+// element (partials p = g, g + 8, ...) and meet in shared memory in a fixed order.
+__global__ void __launch_bounds__(512)
     conv3x3_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int CI,
                                 int nparts) {
-  const int e = blockIdx.x * 256 + threadIdx.x;         // element of the 32 x 32 x 9 block
+  __shared__ float s_part[8][64];
+  const int e = blockIdx.x * 64 + threadIdx.x;          // element of the 32 x 32 x 9 block
   const float* src = partial + (size_t)(blockIdx.z * gridDim.y + blockIdx.y) * nparts * kWgBlock + e;
-  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-  int p = 0;
-  for (; p + 4 <= nparts; p += 4) {
+  float s0 = 0.0f, s1 = 0.0f;
+  int p = threadIdx.y;
+  for (; p + 8 < nparts; p += 16) {
     s0 += src[(size_t)p * kWgBlock];
-    s1 += src[(size_t)(p + 1) * kWgBlock];
-    s2 += src[(size_t)(p + 2) * kWgBlock];
-    s3 += src[(size_t)(p + 3) * kWgBlock];
+    s1 += src[(size_t)(p + 8) * kWgBlock];
   }
-  for (; p < nparts; ++p) s0 += src[(size_t)p * kWgBlock];
-  const int co = e / (kWgC * 9), r = e - co * (kWgC * 9);
-  const int ci = r / 9, t = r - ci * 9;
-  dw[((size_t)(blockIdx.y * kWgC + co) * CI + blockIdx.z * kWgC + ci) * 9 + t] = (s0 + s1) + (s2 + s3);
+  if (p < nparts) s0 += src[(size_t)p * kWgBlock];
+  s_part[threadIdx.y][threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float s = 0.0f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += s_part[g][threadIdx.x];
+    const int co = e / (kWgC * 9), r = e - co * (kWgC * 9);
+    const int ci = r / 9, t = r - ci * 9;
+    dw[((size_t)(blockIdx.y * kWgC + co) * CI + blockIdx.z * kWgC + ci) * 9 + t] = s;
+  }
 }
-
 
 // ---------------------------------------------------------------------------
 // Thin layers: RecNet's first (2 -> 32) and last (32 -> 2) convolution of every

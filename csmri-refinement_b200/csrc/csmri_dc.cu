@@ -1464,12 +1464,23 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
     if (ctas > kWgMaxCtas) ctas = kWgMaxCtas;
     if (ctas > ntiles) ctas = ntiles;
     const int HI = H + 2 - 2 * pad, WI = W + 2 - 2 * pad;
-    if (CI == 2)
+    if (CI == 2) {
       conv3x3_wgrad_thin_kernel<2, 4, true><<<ctas, 256, 0, s>>>(
           x, dy, (float*)workspace, H, W, HI, WI, pad, tiles_x, tiles_y, ntiles);
-    else
+    } else if (pad == 1 && ((uintptr_t)x & 15u) == 0) {
+      // input tile staged through shared memory (tiles of 8 rows)
+      const int ty8 = H / kThinInRows, nt8 = N * tiles_x * ty8;
+      ctas = sm_count() * 2;
+      if (ctas > kWgMaxCtas) ctas = kWgMaxCtas;
+      if (ctas > nt8) ctas = nt8;
+      constexpr int smem_staged = 2 * kThinInBuf * (int)sizeof(float);
+      CSMRI_TRY(set_smem(conv3x3_wgrad_thin_staged_kernel, smem_staged));
+      conv3x3_wgrad_thin_staged_kernel<<<ctas, 256, smem_staged, s>>>(x, dy, (float*)workspace, H, W,
+                                                                      tiles_x, ty8, nt8);
+    } else {
       conv3x3_wgrad_thin_kernel<4, 2, false><<<ctas, 256, 0, s>>>(
           x, dy, (float*)workspace, H, W, HI, WI, pad, tiles_x, tiles_y, ntiles);
+    }
     wgrad_thin_reduce_kernel<<<(CI * CO * 9 + 63) / 64, 64, 0, s>>>((const float*)workspace, dw,
                                                                     CI * CO * 9, ctas);
     CSMRI_CUDA(cudaGetLastError());
@@ -1488,7 +1499,7 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
                                                     H + 2 - 2 * pad, W + 2 - 2 * pad, pad, tiles_x,
                                                     tiles_y, ntiles);
   }
-  conv3x3_wgrad_reduce_kernel<<<dim3(kWgBlock / 256, CO / kWgC, CI / kWgC), 256, 0, s>>>(
+  conv3x3_wgrad_reduce_kernel<<<dim3(kWgBlock / 64, CO / kWgC, CI / kWgC), dim3(64, 8), 0, s>>>(
       (const float*)workspace, dw, CI, parts);
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
