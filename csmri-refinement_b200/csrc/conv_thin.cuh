@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256, 2)
         win[c][1][kx] = cur[(c * (R + 2) + 0) * kThinPC + lane + kx - 1];
         win[c][2][kx] = cur[(c * (R + 2) + 1) * kThinPC + lane + kx - 1];
       }
-#pragma unroll 4
+#pragma unroll 8
     for (int r = 0; r < R; ++r) {
 #pragma unroll
       for (int c = 0; c < A; ++c)
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256, 2)
         win[c][1][kx] = cur[(c * (R + 2) + 0) * kThinPC + lane + kx - 1];
         win[c][2][kx] = cur[(c * (R + 2) + 1) * kThinPC + lane + kx - 1];
       }
-#pragma unroll 2
+#pragma unroll
     for (int r = 0; r < R; ++r) {
 #pragma unroll
       for (int c = 0; c < AT; ++c)
