@@ -361,4 +361,104 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// Weight gradient of the 2 -> 32 layer, same idea: the (tiny) 2-channel input tile
+// is staged one tile ahead, warp g owns output channels 4g .. 4g+3 and streams its
+// four dY rows straight from global memory (all 8 rows of a tile requested before
+// the tile is multiplied).  dw[o][c][tap], o < 32, c < 2.
+__global__ void __launch_bounds__(256, 2)
+    conv3x3_wgrad_thin_out_staged_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                         float* __restrict__ partial, int H, int W, int tiles_x,
+                                         int tiles_y, int ntiles) {
+  constexpr int A = 2, B = 32, BT = 4, R = kThinInRows;
+  constexpr int kBuf = kThinLead + A * (R + 2) * kThinPC;
+  __shared__ __align__(16) float stage[2][kBuf];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int cob = warp * BT;
+  cf acc[A][9][BT / 2];
+#pragma unroll
+  for (int c = 0; c < A; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int o = 0; o < BT / 2; ++o) acc[c][t][o] = mk(0.0f, 0.0f);
+  const size_t plane = (size_t)H * W;
+  auto stage_tile = [&](int tile, float* buf) {
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    static_assert(A * (R + 2) % 4 == 0, "rows are staged four at a time");
+    for (int pair = warp * 4 + (lane >> 3); pair < A * (R + 2); pair += 32) {
+      const int c = pair / (R + 2), r = pair - c * (R + 2);
+      thin_stage_row4(buf + kThinLead + pair * kThinPC, x + ((size_t)t.n * A + c) * plane,
+                      t.y0 - 1 + r, t.x0, H, W, lane);
+    }
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) stage_tile(tile, stage[0]);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const float* cur = stage[it & 1] + kThinLead;
+    const int next = tile + gridDim.x;
+    if (next < ntiles) stage_tile(next, stage[(it + 1) & 1]);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    const float* dn = dy + (((size_t)t.n * B + cob) * H + t.y0) * W + t.x0 + lane;
+    float d[R][BT];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int o = 0; o < BT; ++o) d[r][o] = __ldg(dn + (size_t)o * plane + (size_t)r * W);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    float win[A][3][3];
+#pragma unroll
+    for (int c = 0; c < A; ++c)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        win[c][1][kx] = cur[(c * (R + 2) + 0) * kThinPC + lane + kx - 1];
+        win[c][2][kx] = cur[(c * (R + 2) + 1) * kThinPC + lane + kx - 1];
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int c = 0; c < A; ++c)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          win[c][0][kx] = win[c][1][kx];
+          win[c][1][kx] = win[c][2][kx];
+          win[c][2][kx] = cur[(c * (R + 2) + r + 2) * kThinPC + lane + kx - 1];
+        }
+#pragma unroll
+      for (int c = 0; c < A; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int o = 0; o < BT / 2; ++o)
+              acc[c][ky * 3 + kx][o] = f2fma(mk(d[r][2 * o], d[r][2 * o + 1]),
+                                             mk(win[c][ky][kx], win[c][ky][kx]),
+                                             acc[c][ky * 3 + kx][o]);
+    }
+    __syncthreads();   // `cur` is the staging target of the next iteration
+  }
+  float* dst = partial + (size_t)blockIdx.x * (A * B * 9);
+#pragma unroll
+  for (int c = 0; c < A; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int o = 0; o < BT / 2; ++o) {
+        float a = acc[c][t][o].x, b = acc[c][t][o].y;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, m);
+          b += __shfl_xor_sync(0xffffffffu, b, m);
+        }
+        if (lane == 0) {
+          dst[((cob + 2 * o) * A + c) * 9 + t] = a;
+          dst[((cob + 2 * o + 1) * A + c) * 9 + t] = b;
+        }
+      }
+}
+
 }  // namespace csmri

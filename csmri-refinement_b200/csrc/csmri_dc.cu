@@ -1464,7 +1464,14 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
     if (ctas > kWgMaxCtas) ctas = kWgMaxCtas;
     if (ctas > ntiles) ctas = ntiles;
     const int HI = H + 2 - 2 * pad, WI = W + 2 - 2 * pad;
-    if (CI == 2) {
+    if (CI == 2 && pad == 1 && ((uintptr_t)x & 15u) == 0) {
+      const int ty8 = H / kThinInRows, nt8 = N * tiles_x * ty8;
+      ctas = sm_count() * 2;
+      if (ctas > kWgMaxCtas) ctas = kWgMaxCtas;
+      if (ctas > nt8) ctas = nt8;
+      conv3x3_wgrad_thin_out_staged_kernel<<<ctas, 256, 0, s>>>(x, dy, (float*)workspace, H, W,
+                                                                tiles_x, ty8, nt8);
+    } else if (CI == 2) {
       conv3x3_wgrad_thin_kernel<2, 4, true><<<ctas, 256, 0, s>>>(
           x, dy, (float*)workspace, H, W, HI, WI, pad, tiles_x, tiles_y, ntiles);
     } else if (pad == 1 && ((uintptr_t)x & 15u) == 0) {
