@@ -55,6 +55,8 @@ def _eligible(x, weight, stride, padding, dilation, groups):
     w = x.shape[3] - 2 + 2 * padding[1]
     if h <= 0 or w <= 0 or w % 32 != 0:
         return False
+    if x.shape[0] * max(ci, co) > 65535:        # grid.y of the epilogue kernels
+        return False
     if (ci, co) in ((2, 32), (32, 2)):          # RecNet's first / last layer of a block
         return h % 16 == 0
     return ci % 32 == 0 and co % 32 == 0 and h % 4 == 0
