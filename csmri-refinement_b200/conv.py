@@ -24,9 +24,17 @@ def set_fast_wgrad(flag):
     _ENABLED = bool(flag)
 
 
+def _require_cuda_f32(*tensors):
+    for t in tensors:
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise RuntimeError('the convolution kernels of libcsmri_dc need float32 CUDA tensors '
+                               '(got %s on %s); there is no CPU implementation' % (t.dtype, t.device))
+
+
 def conv3x3_wgrad(x, grad_out, pad):
     """dW (CO,CI,3,3) of a stride-1 3x3 convolution; x (N,CI,H+2-2*pad,W+2-2*pad),
     grad_out (N,CO,H,W), float32 CUDA."""
+    _require_cuda_f32(x, grad_out)
     x, grad_out = x.contiguous(), grad_out.contiguous()
     n, ci = x.shape[0], x.shape[1]
     co, h, w = grad_out.shape[1], grad_out.shape[2], grad_out.shape[3]
@@ -68,6 +76,7 @@ def _aligned16(t):
 
 def bias_lrelu_(z, bias, slope):
     """z <- leaky_relu(z + bias[c], slope) in one pass, in place (z contiguous NCHW)."""
+    _require_cuda_f32(z, bias)
     n, c, h, w = z.shape
     with torch.cuda.device(z.device):
         _lib.check(_lib.lib().csmri_bias_lrelu(z.data_ptr(), bias.data_ptr(), n, c, h, w,
@@ -77,6 +86,7 @@ def bias_lrelu_(z, bias, slope):
 
 def bias_lrelu_backward(grad_y, y, slope):
     """-> (grad_z, grad_bias) from the forward OUTPUT y, one pass over grad_y and y."""
+    _require_cuda_f32(grad_y, y)
     grad_y = _aligned16(grad_y.contiguous())
     n, c, h, w = y.shape
     with torch.cuda.device(y.device):
@@ -92,6 +102,7 @@ def bias_lrelu_backward(grad_y, y, slope):
 def conv3x3_thin(x, weight, bias, slope=0.0):
     """RecNet's thin layers (2 -> 32 or 32 -> 2 channels, zero padding 1) through
     ``csmri_conv3x3_thin``: act(conv(x, weight) + bias), slope 0 = no activation."""
+    _require_cuda_f32(x, weight, bias)
     x, weight = x.contiguous(), weight.contiguous()
     n, a, h, w = x.shape
     b = weight.shape[0]

@@ -180,3 +180,24 @@ def test_product_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, f
+
+
+def test_conv_module_is_a_plain_conv2d_on_cpu():
+    """csmri_refinement_b200.conv.Conv2d keeps nn.Conv2d's parameters, keys and
+    values; on tensors the kernels do not cover (CPU here) it is torch's own path
+    plus the activation it was asked to apply."""
+    from csmri_refinement_b200 import conv
+    torch.manual_seed(0)
+    m = conv.Conv2d(32, 32, 3, padding=1)
+    ref = torch.nn.Conv2d(32, 32, 3, padding=1)
+    assert list(m.state_dict().keys()) == list(ref.state_dict().keys())
+    ref.load_state_dict(m.state_dict())
+    x = torch.randn(2, 32, 16, 32, requires_grad=True)
+    assert torch.equal(m(x), ref(x))
+    m.fused_slope = 0.01
+    out = m(x)
+    assert torch.equal(out, torch.nn.functional.leaky_relu(ref(x), 0.01))
+    out.sum().backward()
+    assert m.weight.grad is not None and x.grad is not None
+    with pytest.raises(RuntimeError):
+        conv.conv3x3_wgrad(x.detach(), out.detach(), 1)     # no CPU implementation
