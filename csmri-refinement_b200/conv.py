@@ -16,6 +16,17 @@ from torch import nn
 from . import _lib
 
 _ENABLED = True
+# experimental: weight gradient on a side stream, concurrently with the data gradient
+import os as _os
+_WGRAD_STREAM = _os.environ.get('CSMRI_WGRAD_STREAM', '0') == '1'
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    s = _SIDE_STREAMS.get(device.index)
+    if s is None:
+        s = _SIDE_STREAMS[device.index] = torch.cuda.Stream(device)
+    return s
 
 
 def set_fast_wgrad(flag):
@@ -157,6 +168,15 @@ class _Conv3x3(torch.autograd.Function):
             grad_out, gb = bias_lrelu_backward(grad_out, y, ctx.slope)
             if not need_b:
                 gb = None
+        fork = None
+        if need_w and _WGRAD_STREAM and not ctx.thin:
+            # fork here, before the data gradient is launched on the current stream
+            cur = torch.cuda.current_stream(x.device)
+            side = _side_stream(x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                gw = conv3x3_wgrad(x, grad_out, pad)
+            fork = (cur, side)
         if ctx.thin:
             if need_b and gb is None:
                 gb = grad_out.sum(dim=(0, 2, 3))
@@ -171,7 +191,12 @@ class _Conv3x3(torch.autograd.Function):
             gx = torch.ops.aten.convolution_backward(
                 grad_out, x, weight, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
                 [True, False, False])[0]
-        if need_w:
+        if fork is not None:
+            cur, side = fork
+            cur.wait_stream(side)
+            gw.record_stream(cur)
+            grad_out.record_stream(side)
+        elif need_w:
             gw = conv3x3_wgrad(x, grad_out, pad)
         return gx, gw, gb, None, None
 
