@@ -15,9 +15,17 @@ Prints ONE JSON line (rank 0).  `value` = slices/s with inputs resident in HBM;
 with HOST (pinned) buffers, copies inside the timed region; `roofline` = the
 strip kernel's algorithmic bytes / its CUDA-event time against the measured
 HBM peak; `cpu_baseline` = the oracle port on the host cores (bounded sample).
-Extra keys: `noisy_lambda` (the same microbench with noise_lvl = 0.1) and
-`recnet_train` (BASELINE configs[2]: RecNet D5C5 fp32 training step, batch 32 per
-GPU, with `tf32_convs` as a context number).
+The timed region of `value` is ONE CUDA graph holding the K steps (2K launches
+of the csmri::dc_cartesian custom op), so it measures the GPU and not the Python
+dispatch of a 50-60 us kernel; `roofline.frac` is derived from that same region
+(`roofline.kernel_frac` / `forward` / `adjoint` are the per-launch figures from
+raw C-ABI loops).
+Extra keys: `gpu_baseline_torch_fft` (cuFFT + pointwise, the reference's
+structure, on the same GPU and tensors), `noisy_lambda` (the same microbench
+with noise_lvl = 0.1), `recnet_train` (BASELINE configs[2]: RecNet D5C5 fp32
+training step, batch 32 per GPU, with `tf32_convs` as a context number),
+`recnet_1json` (configs/1-recnet.json unchanged: D3C3-nf32, GLOBAL batch 20,
+512^2, 8x; strong scaling) and `refinement_train` (BASELINE configs[4]).
 """
 import argparse
 import json
@@ -253,6 +261,99 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def pin_rank_to_cores(local_rank, local_world):
+    """Give every rank its own contiguous slice of the host cores this process
+    may use (8 ranks + their NVML / autograd threads otherwise migrate over the
+    same 32 cores).  Returns the core list, or None if affinity is unavailable."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if local_world <= 1 or len(cores) < local_world:
+            return cores
+        per = len(cores) // local_world
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return mine
+    except (AttributeError, OSError):
+        return None
+
+
+def torch_fft_dc(x, k0, mask):
+    """The reference's structure on this GPU: library FFT (cuFFT through
+    torch.fft) + separate pointwise kernels, myfft.py:153-163 noiseless branch.
+    Only a same-box comparison number ('beat the cuFFT+pointwise
+    restatement'); never on the product path."""
+    kc = torch.fft.fft2(torch.complex(x[:, 0], x[:, 1]), norm='ortho')
+    k = torch.stack((kc.real, kc.imag), 1)
+    out = (1 - mask) * k + k0
+    oc = torch.fft.ifft2(torch.complex(out[:, 0], out[:, 1]), norm='ortho')
+    return torch.stack((oc.real, oc.imag), 1)
+
+
+def event_ms(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def rank_stats(ms, dev, world):
+    """(max over ranks, {'min','median','max'} over ranks) of a per-rank time."""
+    if world <= 1:
+        return ms, {'min': ms, 'median': ms, 'max': ms}
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    all_t = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(all_t, t)
+    v = sorted(float(x.item()) for x in all_t)
+    return v[-1], {'min': v[0], 'median': float(np.median(v)), 'max': v[-1]}
+
+
+def recnet_1json_bench(dev, rank, world, steps=6, warmup=3):
+    """configs/1-recnet.json UNCHANGED: D3C3-nf32, global batch 20, 512x512,
+    8x Cartesian undersampling, MSE + Adam(2e-4).  The JSON's
+    batch_size is the GLOBAL batch (DataParallel splits it), so this leg is
+    strong scaling: 20 slices per step over however many GPUs there are."""
+    import torch.distributed as dist
+    from csmri_refinement_b200 import harness
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    conf = harness.load_config(harness.config_path('1-recnet.json'))
+    trainer, local_b = harness.recnet_trainer(conf, dev, rank, world, cuda_graph=True)
+    batches = [harness.synthetic_batch(conf, local_b, dev, seed=1000 + 16 * rank + i)
+               for i in range(2)]
+    for i in range(warmup):
+        trainer.step(batches[i % 2])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        loss = trainer.step(batches[i % 2])
+    b.record()
+    torch.cuda.synchronize()
+    ms, stats = rank_stats(a.elapsed_time(b) / steps, dev, world)
+    n_img = batches[0]['inp'].shape[-1]
+    return {'metric': 'recnet_train_slices_per_s', 'value': int(conf.batch_size) / (ms * 1e-3),
+            'unit': UNIT, 'ms_per_step': ms, 'ms_per_step_ranks': stats, 'steps': steps,
+            'scaling': 'strong', 'global_batch': int(conf.batch_size), 'local_batch': local_b,
+            'config': 'configs/1-recnet.json unchanged: RecNet D%dC%d nf=%d, global batch %d '
+                      '(this rank: %d), %dx%d, %dx Cartesian, MSE + Adam(%g), fp32 (TF32 off), '
+                      'CUDA-graph step, gradient weighted by shard size, flat-bucket allreduce '
+                      '(%d bytes)' % (conf.model['num_blocks'], conf.model['num_convs'],
+                                      conf.model['num_filters'], conf.batch_size, local_b, n_img,
+                                      n_img, conf.undersampling['acceleration_factor'],
+                                      conf.optimizer['learning_rate'], trainer.bucket.nbytes()),
+            'loss': float(loss.item())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -261,7 +362,11 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--variant', type=int, default=None, help='kernel tuning variant (debug)')
-    ap.add_argument('--no-recnet', action='store_true', help='skip the RecNet training leg')
+    ap.add_argument('--no-recnet', action='store_true', help='skip the RecNet training legs')
+    ap.add_argument('--no-refinement', action='store_true', help='skip the config-5 leg')
+    ap.add_argument('--eager', action='store_true',
+                    help='time the headline through per-step Python dispatch instead of one '
+                         'CUDA graph (debug)')
     args = ap.parse_args()
     capture_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -269,6 +374,7 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    local_world = int(os.environ.get('LOCAL_WORLD_SIZE', str(world)))
 
     if args.impl == 'reference':
         run_reference(args, rank, world)
@@ -276,8 +382,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback for the DC path)')
+    cores = pin_rank_to_cores(local_rank, local_world)
     import torch.distributed as dist
-    from csmri_refinement_b200 import _lib, myfft, ops
+    from csmri_refinement_b200 import _lib, hostpipe, myfft, ops, undersampling
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -306,83 +413,115 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- headline: W warm-up steps, then EXACTLY K steps in the timed region ----
+    # The K steps (2K launches of the product's custom op) are captured into ONE
+    # CUDA graph, so the timed region is a single host call: a 50-60 us kernel
+    # issued step by step from Python measures the host (8 ranks share 32 cores)
+    # as much as the GPU.
     for i in range(args.warmup):
         step(i)
     barrier()
-    sampler = ClockSampler(local_rank, period=0.002)
+    graph = None
+    if not args.eager:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(args.steps):
+                step(i)
+        graph.replay()            # untimed: first replay uploads the graph
+    sampler = ClockSampler(local_rank, period=0.05)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for i in range(args.steps):
-        step(i)
+    if graph is not None:
+        graph.replay()
+    else:
+        for i in range(args.steps):
+            step(i)
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms_local = ev0.elapsed_time(ev1)
+    ms, ms_ranks = rank_stats(ms_local, dev, world)
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---- per-kernel roofline: forward and adjoint launches timed separately ----
-    def time_kernel(fn, reps):
-        for i in range(3):
-            fn(i)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for i in range(reps):
-            fn(i)
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps
-
+    # ---- per-kernel figures: forward and adjoint launches timed separately -------
     lib = _lib.lib()
     stream = torch.cuda.current_stream().cuda_stream
+    it = [0]
 
-    def raw_fwd(i):
+    def raw_fwd():
+        i = it[0] = it[0] + 1
         x, _, _, _ = sets[i % nbuf]
         p = plans[i % nbuf]
         lib.csmri_dc_forward_cartesian(x.data_ptr(), None, p.dtab.data_ptr(), p.addend.data_ptr(),
                                        outs[0].data_ptr(), B, N, N, stream)
 
-    def raw_adj(i):
+    def raw_adj():
+        i = it[0] = it[0] + 1
         _, w, _, _ = sets[i % nbuf]
         p = plans[i % nbuf]
         lib.csmri_dc_adjoint_cartesian(w.data_ptr(), p.dtab.data_ptr(), outs[1].data_ptr(),
                                        B, N, N, stream)
 
-    reps = max(args.steps, 20)
-    ms_fwd = time_kernel(raw_fwd, reps)
-    ms_adj = time_kernel(raw_adj, reps)
-    clocks = sampler.stop()   # sampled over the timed region and the per-kernel timing loops
+    reps = max(args.steps, 50)
+    ms_fwd = event_ms(raw_fwd, reps, warm=3)
+    ms_adj = event_ms(raw_adj, reps, warm=3)
     peak, peak_src = measured_peak()
     bytes_fwd, bytes_adj = 24 * N * N * B, 16 * N * N * B
+    bytes_step = bytes_fwd + bytes_adj
     gbs_fwd = bytes_fwd / (ms_fwd * 1e-3) / 1e9
     gbs_adj = bytes_adj / (ms_adj * 1e-3) / 1e9
-    gbs_pair = (bytes_fwd + bytes_adj) / ((ms_fwd + ms_adj) * 1e-3) / 1e9
+    gbs_step = bytes_step / (ms_per_step * 1e-3) / 1e9       # same region as `value`
+    gbs_kernels = bytes_step / ((ms_fwd + ms_adj) * 1e-3) / 1e9
     traffic = None
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r1_dram_traffic.json')) as f:
-            traffic = json.load(f).get('bytes_per_fwd_adj_pair')
-    except Exception:
-        pass
+    for name in ('r2_dram_traffic.json', 'r1_dram_traffic.json'):
+        try:
+            with open(os.path.join(ROOT, 'profiles', name)) as f:
+                traffic = json.load(f).get('bytes_per_fwd_adj_pair')
+            break
+        except Exception:
+            pass
     roofline = {
         'bound': 'hbm', 'kernel': 'dc_strip_pipev_kernel<256,16,16,...> (forward + adjoint launches)',
-        'achieved': gbs_pair, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_pair / peak,
+        'achieved': gbs_step, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_step / peak,
         'traffic': traffic, 'peak_source': peak_src,
+        'derived_from': 'the timed region of `value`: (24+16)*N^2*B bytes / ms_per_step',
+        'bytes_per_step': bytes_step,
         'bytes_per_launch': {'forward': bytes_fwd, 'adjoint': bytes_adj},
+        'kernel_frac': gbs_kernels / peak,
         'forward': {'ms': ms_fwd, 'GBps': gbs_fwd, 'frac': gbs_fwd / peak},
         'adjoint': {'ms': ms_adj, 'GBps': gbs_adj, 'frac': gbs_adj / peak},
-        'frac_of_nominal_8000': gbs_pair / 8000.0,
+        'frac_of_nominal_8000': gbs_step / 8000.0,
     }
+
+    # ---- the reference's structure on the same GPU and tensors (cuFFT + pointwise) ----
+    gpu_baseline = None
+    if rank == 0:
+        try:
+            xs = sets[0][0].detach().clone().requires_grad_(True)
+            wseed, k0d, md = sets[0][1], sets[0][2], sets[0][3]
+
+            def tf_step():
+                out = torch_fft_dc(xs, k0d, md)
+                torch.autograd.grad(out, xs, wseed)
+
+            ms_tf = event_ms(tf_step, 5, warm=2)
+            gpu_baseline = {'value': B / (ms_tf * 1e-3), 'unit': UNIT, 'ms_per_step': ms_tf,
+                            'frac': bytes_step / (ms_tf * 1e-3) / 1e9 / peak,
+                            'what': 'torch.fft.fft2 -> blend -> torch.fft.ifft2 + autograd backward '
+                                    '(cuFFT + pointwise kernels, the reference\'s structure) on '
+                                    'the same GPU, tensors and batch; 1 GPU'}
+            del xs
+        except Exception as e:
+            gpu_baseline = {'error': repr(e)[:200]}
+        torch.cuda.empty_cache()
 
     # ---- noisy-lambda variant of configs[1] (myfft.py:139): same kernels, other plan ---
     nplans = [myfft.DCPlan(k0, mask, 0.1) for (_, _, k0, mask) in sets]
 
-    def noisy_step(i):
+    def noisy_step():
+        i = it[0] = it[0] + 1
         x, w, _, _ = sets[i % nbuf]
         p = nplans[i % nbuf]
         lib.csmri_dc_forward_cartesian(x.data_ptr(), None, p.dtab.data_ptr(), p.addend.data_ptr(),
@@ -390,96 +529,108 @@ def main():
         lib.csmri_dc_adjoint_cartesian(w.data_ptr(), p.dtab.data_ptr(), outs[1].data_ptr(),
                                        B, N, N, stream)
 
-    ms_noisy = time_kernel(noisy_step, reps)
-    if world > 1:
-        t = torch.tensor([ms_noisy], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_noisy = float(t.item())
+    ms_noisy, _ = rank_stats(event_ms(noisy_step, reps, warm=3), dev, world)
     noisy = {'noise_lvl': 0.1, 'value': world * B / (ms_noisy * 1e-3), 'unit': UNIT,
-             'ms_per_step': ms_noisy,
-             'frac': (bytes_fwd + bytes_adj) / (ms_noisy * 1e-3) / 1e9 / peak}
+             'ms_per_step': ms_noisy, 'frac': bytes_step / (ms_noisy * 1e-3) / 1e9 / peak}
     del nplans
 
-    # ---- e2e: public API, host buffers, copies inside the timed region ---------
+    # ---- e2e: public API, HOST buffers, copies inside the timed region -----------
     x0, w0, k00, m0 = sets[0]
-    hx, hk0, hm, hw = (t.cpu().pin_memory() for t in (x0, k00, m0, w0))
+    rows0 = (m0[:, 0, :, 0] != 0).to(torch.uint8)
+    k0l = undersampling.compact_lines(k00, rows0)
+    hx, hk0, hm, hw, hk0l, hrows = (t.cpu().pin_memory() for t in (x0, k00, m0, w0, k0l, rows0))
     h_out = torch.empty_like(hx).pin_memory()
     h_gx = torch.empty_like(hx).pin_memory()
-    dc = myfft.DataConsistencyInKspace()
-
-    def e2e_step():
-        x = hx.to(dev, non_blocking=True).requires_grad_(True)
-        k0 = hk0.to(dev, non_blocking=True)
-        m = hm.to(dev, non_blocking=True)
-        w = hw.to(dev, non_blocking=True)
-        out = dc.perform(x, k0, m)
-        (gx,) = torch.autograd.grad(out, x, w)
-        h_out.copy_(out.detach(), non_blocking=True)
-        h_gx.copy_(gx, non_blocking=True)
-
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    b.record()
-    barrier()
-    e2e_ms = a.elapsed_time(b)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
     tensor_bytes = hx.numel() * 4
-    e2e_simple = {'value': world * B * e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT,
-                  'h2d_bytes_per_step': 4 * tensor_bytes, 'd2h_bytes_per_step': 2 * tensor_bytes,
-                  'steps': e2e_steps, 'ms_per_step': e2e_ms / e2e_steps,
-                  'api': 'DataConsistencyInKspace.perform + autograd backward, pinned host '
-                         'x/k0/mask/grad-seed in, out/grad_x back, copies and compute in sequence; '
-                         'includes the per-batch prepare'}
+    e2e_steps = max(3, min(args.steps, 10))
 
-    # same work through the streamed public API: chunks of 64 slices on three
-    # streams (H2D / DC forward+adjoint incl. prepare / D2H), full-duplex PCIe
-    from csmri_refinement_b200 import hostpipe
+    def timed_e2e(fn):
+        for _ in range(2):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e2e_steps):
+            fn()
+        b.record()
+        barrier()
+        return rank_stats(a.elapsed_time(b) / e2e_steps, dev, world)
+
     pipe = hostpipe.HostDCPipeline(dev, chunk=64, depth=3)
-    for _ in range(2):
-        pipe.forward_backward(hx, hk0, hm, hw, h_out, h_gx)
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(e2e_steps):
-        pipe.forward_backward(hx, hk0, hm, hw, h_out, h_gx)
-    b.record()
-    barrier()
-    e2e_ms = a.elapsed_time(b)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e = {'value': world * B * e2e_steps / (e2e_ms * 1e-3), 'unit': UNIT,
-           'h2d_bytes_per_step': 4 * tensor_bytes, 'd2h_bytes_per_step': 2 * tensor_bytes,
-           'steps': e2e_steps, 'ms_per_step': e2e_ms / e2e_steps,
-           'api': 'hostpipe.HostDCPipeline.forward_backward: pinned host x/k0/mask/grad-seed in, '
-                  'out/grad_x back to pinned host, 64-slice chunks on 3 streams; includes the '
-                  'per-chunk prepare and the row-constancy verification read',
-           'unpipelined': e2e_simple}
+    h2d_lines = 2 * tensor_bytes + hk0l.numel() * 4 + hrows.numel()
+    d2h = 2 * tensor_bytes
+    ms_lines, st_lines = timed_e2e(
+        lambda: pipe.forward_backward_lines(hx, hk0l, hrows, hw, h_out, h_gx))
+    ms_dense, st_dense = timed_e2e(
+        lambda: pipe.forward_backward(hx, hk0, hm, hw, h_out, h_gx))
+
+    # the PCIe floor of the same step: the copies alone, both directions at once
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    d_in = [torch.empty_like(t, device=dev) for t in (hx, hk0l, hrows, hw)]
+
+    def copies_only():
+        cur = torch.cuda.current_stream()
+        s_up.wait_stream(cur)
+        s_dn.wait_stream(cur)
+        with torch.cuda.stream(s_up):
+            for d, h in zip(d_in, (hx, hk0l, hrows, hw)):
+                d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_out.copy_(outs[0], non_blocking=True)
+            h_gx.copy_(outs[1], non_blocking=True)
+        cur.wait_stream(s_up)
+        cur.wait_stream(s_dn)
+
+    ms_copy, _ = timed_e2e(copies_only)
+    del d_in
+    clocks = sampler.stop()   # sampled from the timed region to the end of the e2e legs
+
+    e2e = {'value': world * B / (ms_lines * 1e-3), 'unit': UNIT,
+           'h2d_bytes_per_step': h2d_lines, 'd2h_bytes_per_step': d2h,
+           'steps': e2e_steps, 'ms_per_step': ms_lines, 'ms_per_step_ranks': st_lines,
+           'h2d_GBps_per_gpu': h2d_lines / (ms_lines * 1e-3) / 1e9,
+           'd2h_GBps_per_gpu': d2h / (ms_lines * 1e-3) / 1e9,
+           'copies_only_ms_per_step': ms_copy,
+           'frac_of_copy_floor': ms_copy / ms_lines,
+           'api': 'hostpipe.HostDCPipeline.forward_backward_lines: pinned host x / grad-seed / '
+                  'sampled k0 lines (B,2,L,W) / line table (B,H) uint8 in, out / grad_x back to '
+                  'pinned host, 64-slice chunks on 3 streams; includes the per-chunk '
+                  'csmri_dc_prepare_lines and the consistency read. copies_only = the same '
+                  'bytes moved with no kernel in between (the PCIe floor of this step)',
+           'dense_interface': {
+               'value': world * B / (ms_dense * 1e-3), 'unit': UNIT, 'ms_per_step': ms_dense,
+               'ms_per_step_ranks': st_dense,
+               'h2d_bytes_per_step': 4 * tensor_bytes, 'd2h_bytes_per_step': d2h,
+               'api': 'HostDCPipeline.forward_backward: the reference loader\'s dense k0 and dense '
+                      '2-channel mask cross PCIe too (4 tensors in); includes csmri_dc_prepare and '
+                      'the row-constancy verification read'}}
+    del hx, hk0, hm, hw, hk0l, hrows, h_out, h_gx, pipe
+    torch.cuda.empty_cache()
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'warmup': args.warmup, 'ms_per_step': ms_per_step,
+        'ms_per_step_ranks': {k: v / args.steps for k, v in ms_ranks.items()},
+        'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'DC operator microbench (BASELINE configs[1]): batch %d/GPU of '
                                '%dx%d fp32 slices, 4x Cartesian mask, noiseless, fwd+adjoint'
                                % (B, N, N),
                    'l2': 'inputs larger than L2: one step streams 640 MiB over 2 rotating '
                          'buffer sets (L2 = 126 MB)',
-                   'sharding': 'batch-sharded, one rank per GPU, no data-path collective'},
+                   'sharding': 'batch-sharded, one rank per GPU, no data-path collective',
+                   'timed_region': ('the K steps are 2K launches of the csmri::dc_cartesian custom '
+                                    'op captured in ONE CUDA graph (replayed once untimed, then '
+                                    'once timed)') if graph is not None else
+                                   'K steps issued one by one from Python (--eager)',
+                   'host_cores_this_rank': len(cores) if cores else None},
         'roofline': roofline, 'e2e': e2e, 'gpu_launches': 2 * args.steps, 'clocks': clocks,
-        'hbm_GBps_fwd_adj': value / world * 40 * N * N / 1e9,
+        'hbm_GBps_fwd_adj': gbs_step,
+        'gpu_baseline_torch_fft': gpu_baseline,
         'noisy_lambda': noisy,
     }
+    del sets, plans, outs, graph
+    torch.cuda.empty_cache()
     if not args.no_recnet:
         try:
             line['recnet_train'] = recnet_train_bench(dev, rank, world)
@@ -487,6 +638,19 @@ def main():
         except Exception as e:  # secondary leg: never lose the headline line
             line.setdefault('recnet_train', {})['error'] = repr(e)[:300]
         torch.backends.cudnn.allow_tf32 = False
+        torch.cuda.empty_cache()
+        try:
+            line['recnet_1json'] = recnet_1json_bench(dev, rank, world)
+        except Exception as e:
+            line['recnet_1json'] = {'error': repr(e)[:300]}
+        torch.cuda.empty_cache()
+    if not args.no_refinement:
+        try:
+            from csmri_refinement_b200 import refinement_harness
+            line['refinement_train'] = refinement_harness.bench_leg(dev, rank, world)
+        except Exception as e:
+            line['refinement_train'] = {'error': repr(e)[:300]}
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline()
     elif rank == 0:

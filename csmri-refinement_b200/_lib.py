@@ -4,6 +4,7 @@ There is no fallback: if the shared library has not been built, importing any
 op raises immediately with the build command.
 """
 import ctypes
+import glob
 import os
 import subprocess
 import sys
@@ -11,7 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libcsmri_dc.so')
-SOURCES = ['csmri_dc.cu', 'dc_core.cuh', 'fft_regs.cuh']
+MAIN_SOURCE = 'csmri_dc.cu'
 NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-lineinfo', '-Xcompiler', '-fPIC', '-shared']
 
@@ -19,16 +20,27 @@ _c_float_p = ctypes.c_void_p   # device pointers travel as integers
 _lib = None
 
 
+def sources():
+    """Everything the library is compiled from: every .cu / .cuh under csrc/
+    (csmri_dc.cu includes all the headers) plus the public ABI header."""
+    srcs = sorted(glob.glob(os.path.join(CSRC, '*.cu')) + glob.glob(os.path.join(CSRC, '*.cuh')))
+    srcs.append(os.path.join(os.path.dirname(_HERE), 'include', 'csmri_dc.h'))
+    return srcs
+
+
+def is_stale():
+    """True when the .so is missing or older than any of its sources."""
+    if not os.path.exists(LIB_PATH):
+        return True
+    return os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in sources())
+
+
 def build(force=False, verbose=False):
     """Compile csrc/csmri_dc.cu for sm_100a into csrc/libcsmri_dc.so."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    srcs.append(os.path.join(os.path.dirname(_HERE), 'include', 'csmri_dc.h'))
-    if not force and os.path.exists(LIB_PATH):
-        newest = max(os.path.getmtime(s) for s in srcs)
-        if os.path.getmtime(LIB_PATH) >= newest:
-            return LIB_PATH
+    if not force and not is_stale():
+        return LIB_PATH
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH, os.path.join(CSRC, 'csmri_dc.cu')]
+    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH, os.path.join(CSRC, MAIN_SOURCE)]
     if verbose:
         cmd += ['-Xptxas', '-v']
         print(' '.join(cmd), file=sys.stderr)
@@ -44,6 +56,9 @@ _SIGNATURES = {
     'csmri_dc_prepare': (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_float, _c_float_p, _c_float_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'csmri_dc_prepare_lines': (ctypes.c_int, [_c_float_p, ctypes.c_void_p] + [ctypes.c_int] * 4 +
+                               [ctypes.c_float, _c_float_p, _c_float_p, ctypes.c_void_p,
+                                ctypes.c_void_p]),
     'csmri_dc_forward_cartesian': (ctypes.c_int, [_c_float_p] * 5 + [ctypes.c_int] * 3 +
                                    [ctypes.c_void_p]),
     'csmri_dc_adjoint_cartesian': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 3 +
@@ -100,9 +115,8 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 'libcsmri_dc.so is missing (%s). Build it with '
-                '`python -c "import __graft_entry__ as g; g.build()"` or '
-                '`python -m csmri_refinement_b200.build`. There is no CPU/PyTorch '
-                'fallback for the DC path.' % LIB_PATH)
+                '`python -c "import __graft_entry__ as g; g.build()"`. There is no '
+                'CPU/PyTorch fallback for the DC path.' % LIB_PATH)
         handle = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)

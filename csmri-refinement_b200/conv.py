@@ -63,6 +63,8 @@ def conv3x3_wgrad(x, grad_out, pad):
 def _eligible(x, weight, stride, padding, dilation, groups):
     if not (_ENABLED and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32):
         return False
+    if torch.is_autocast_enabled():
+        return False          # fp16 / bf16 autocast: the kernels are fp32-only, torch handles it
     if x.dim() != 4 or not x.is_contiguous() or not weight.is_contiguous():
         return False          # e.g. channels_last: the kernels address plain NCHW
     if tuple(weight.shape[2:]) != (3, 3) or groups != 1:

@@ -356,6 +356,9 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
 //        4 sampled rows only: rows with rowsel[b, h] == 0 are neither read nor
 //          transformed, their output is zero; the dense 2-channel mask
 //          (dnn_io.py:56-59) is written alongside into mask_out
+//        5 sampled rows only, COMPACT input: `in` is (B,2,L,W) and holds just the
+//          L sampled lines of each slice in ascending row order (L travels in
+//          cmulv); row h reads line #(sampled rows before h); no mask output
 // ---------------------------------------------------------------------------
 template <int W, int E, int R, bool INV, int PRE>
 __global__ void __launch_bounds__(R*(W / E))
@@ -392,16 +395,29 @@ __global__ void __launch_bounds__(R*(W / E))
   const int b = blockIdx.x / tiles_per_slice;
   const int row = (blockIdx.x - b * tiles_per_slice) * R + r;
   const size_t plane = (size_t)H * W;
-  const size_t off_in = (PRE == 3 ? (size_t)b * plane : (size_t)b * 2 * plane) + (size_t)row * W + j;
+  size_t off_in = (PRE == 3 ? (size_t)b * plane : (size_t)b * 2 * plane) + (size_t)row * W + j;
+  size_t plane_in = plane;
   const size_t off = (size_t)b * 2 * plane + (size_t)row * W + j;
 
-  // PRE == 4: uniform over the T threads (adjacent lanes) that share a row
-  const bool on = (PRE != 4) || rowsel[(size_t)b * H + row] != 0;
+  // PRE == 4 / 5: uniform over the T threads (adjacent lanes) that share a row
+  const bool on = (PRE != 4 && PRE != 5) || rowsel[(size_t)b * H + row] != 0;
+  if (PRE == 5) {
+    // position of this row among the sampled lines of its slice: the T threads
+    // of the row count disjoint parts of rowsel[b, 0..row) and fold in the lanes
+    const int L = (int)cmulv;
+    int cnt = 0;
+    for (int h = j; h < row; h += T) cnt += rowsel[(size_t)b * H + h] != 0;
+#pragma unroll
+    for (int sft = T / 2; sft > 0; sft >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, sft);
+    if (cnt > L - 1) cnt = L - 1;   // malformed table (reported through lines_ok): stay in bounds
+    plane_in = (size_t)L * W;
+    off_in = (size_t)b * 2 * plane_in + (size_t)cnt * W + j;
+  }
   cf v[E];
 #pragma unroll
   for (int i = 0; i < E; ++i) {
     float re = on ? ld_stream(in + off_in + T * i) : 0.0f;
-    float im = (PRE == 3 || !on) ? 0.0f : ld_stream(in + off_in + plane + T * i);
+    float im = (PRE == 3 || !on) ? 0.0f : ld_stream(in + off_in + plane_in + T * i);
     if (PRE == 1) {
       re += ld_stream(aux + off + T * i);
       im += ld_stream(aux + off + plane + T * i);
@@ -435,8 +451,17 @@ __global__ void __launch_bounds__(R*(W / E))
 #pragma unroll
   for (int rr = 0; rr < E; ++rr) {
     const int k0i = (rr / T) * T + E * (rr % T);          // + j
+    float im = v[rr].y * scale;
+    if (PRE == 4) {
+      // csmri_undersample transforms REAL images: the four self-conjugate bins
+      // (k_H in {0, H/2}) x (k_W in {0, W/2}) are real.  numpy leaves an exact 0.0
+      // there (compressed_sensing.py:509); the radix-5 butterflies of 320 leave
+      // rounding noise, so pin them - the k-space support must be bit-exact.
+      const int kw = k0i + j;
+      if ((row == 0 || 2 * row == H) && (kw == 0 || 2 * kw == W)) im = 0.0f;
+    }
     st_stream(out + off + k0i, v[rr].x * scale);
-    st_stream(out + off + plane + k0i, v[rr].y * scale);
+    st_stream(out + off + plane + k0i, im);
     if (PRE == 4) {
       const float m = on ? 1.0f : 0.0f;
       st_stream(mask_out + off + k0i, m);
@@ -495,6 +520,29 @@ __global__ void dtab_from_rows_kernel(const unsigned char* __restrict__ rows, in
   const int k1 = h % E, k2 = h / E;
   const float m = rows[i] ? 1.0f : 0.0f;
   dtab[(size_t)b * H + (k1 % T) * E + (k1 / T) * T + k2] = (1.0f - m) / (float)H;
+}
+
+// The same for a compact plan request (csmri_dc_prepare_lines): one CTA per
+// slice, D = 1-m or (1-m) + m/(1+v) as in mask_rows_kernel, and the number of
+// sampled rows of every slice is checked against L (lines_ok <- 0 on mismatch).
+__global__ void dtab_from_rows_checked_kernel(const unsigned char* __restrict__ rows, int H, int E,
+                                              int L, float nv, int noisy,
+                                              float* __restrict__ dtab, int* __restrict__ lines_ok) {
+  const int b = blockIdx.x, T = H / E;
+  int cnt = 0;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    const float m = rows[(size_t)b * H + h] ? 1.0f : 0.0f;
+    cnt += m != 0.0f;
+    const float d = noisy ? (1.0f - m) + m / (1.0f + nv) : (1.0f - m);
+    const int k1 = h % E, k2 = h / E;
+    dtab[(size_t)b * H + (k1 % T) * E + (k1 / T) * T + k2] = d / (float)H;
+  }
+  __shared__ int total;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  if (cnt) atomicAdd(&total, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0 && total != L) atomicExch(lines_ok, 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -672,8 +720,24 @@ static int set_smem(K kernel, int bytes) {
   return CSMRI_OK;
 }
 
-__device__ unsigned g_sched[128];     // 64 x (tiles handed out, retired CTAs), zero = armed
-static std::atomic<unsigned> g_sched_next{0};   // launches may come from several host threads
+// Dynamic tile scheduler state: (tiles handed out, retired CTAs) pairs, zero =
+// armed; the last CTA of a launch re-arms its pair, so a pair may be reused as
+// soon as that launch has finished.  Two launches that can be in flight at the
+// same time must not share a pair.  Launches on ONE stream are ordered (with
+// programmatic dependent launch only neighbours overlap), so each stream - and
+// each CUDA-graph capture, whose baked-in pair is replayed later on any stream -
+// owns a range of kSchedPerRange pairs and walks it round-robin.  Ranges are
+// handed out first come first served and recycled oldest-first once more than
+// kSchedRanges distinct streams / captures have been seen.
+constexpr int kSchedRanges = 64, kSchedPerRange = 64;
+__device__ unsigned g_sched[2 * kSchedRanges * kSchedPerRange];
+struct SchedRange {
+  unsigned long long key;
+  unsigned next;
+  bool used;
+};
+static SchedRange g_sched_ranges[kSchedRanges];
+static unsigned g_sched_victim = 0;
 static int g_use_pdl = 1;             // programmatic dependent launch for the strip kernels
 static int g_wgrad_cot = 8;      // output channels per thread of conv3x3_wgrad_kernel (8; 4 = A/B baseline)
 static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_set_tuning
@@ -727,14 +791,64 @@ static int make_tile_map(CUtensorMap* m, const float* ptr, int B, int H, int W, 
   return CSMRI_OK;
 }
 
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev < 0 || dev >= 64) ? 0 : dev;
+}
+
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  static std::atomic<int> n[64];
+  const int dev = current_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
+}
+
+// resident CTAs per SM of a persistent kernel, cached per (instantiation, device)
+template <typename K>
+static int resident_blocks(K kernel, int threads, int smem_bytes, std::atomic<int>* cache) {
+  const int dev = current_device();
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, smem_bytes) !=
+        cudaSuccess)
+      v = -1;
+    if (v < 1) v = -1;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+// scheduler pair for a launch on stream s (see g_sched)
+static int sched_slot(cudaStream_t s, unsigned** out) {
+  static unsigned* base[64] = {nullptr};
+  const int dev = current_device();
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  CSMRI_CUDA(cudaStreamGetCaptureInfo(s, &st, &id));
+  const unsigned long long key = st == cudaStreamCaptureStatusActive
+                                     ? (0x8000000000000000ULL | id)
+                                     : ((unsigned long long)(uintptr_t)s & 0x7fffffffffffffffULL);
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  if (base[dev] == nullptr) CSMRI_CUDA(cudaGetSymbolAddress((void**)&base[dev], g_sched));
+  int r = -1;
+  for (int i = 0; i < kSchedRanges; ++i)
+    if (g_sched_ranges[i].used && g_sched_ranges[i].key == key) { r = i; break; }
+  if (r < 0) {
+    for (int i = 0; i < kSchedRanges && r < 0; ++i)
+      if (!g_sched_ranges[i].used) r = i;
+    if (r < 0) r = (int)(g_sched_victim++ % kSchedRanges);
+    g_sched_ranges[r].key = key;
+    g_sched_ranges[r].next = 0;
+    g_sched_ranges[r].used = true;
+  }
+  const unsigned slot = g_sched_ranges[r].next++ % kSchedPerRange;
+  *out = base[dev] + 2 * ((size_t)r * kSchedPerRange + slot);
+  return CSMRI_OK;
 }
 
 template <int H, int E, int CW, int MINB, int WT, bool ADD, bool INPL>
@@ -744,12 +858,9 @@ static int launch_strip_pipe_wt(const float* x, const float* residual, const flo
   typedef PipeSmem<H, E, CW, ADD, INPL> S;
   auto kern = dc_strip_pipe_kernel<H, E, CW, MINB, WT, ADD, INPL>;
   CSMRI_TRY(set_smem(kern, S::kBytes));
-  static int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    CSMRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, CW * L::T,
-                                                             S::kBytes));
-    if (blocks_per_sm < 1) return fail(CSMRI_E_CUDA, "pipelined strip kernel does not fit an SM");
-  }
+  static std::atomic<int> occ[64];
+  const int blocks_per_sm = resident_blocks(kern, CW * L::T, S::kBytes, occ);
+  if (blocks_per_sm < 1) return fail(CSMRI_E_CUDA, "pipelined strip kernel does not fit an SM");
   alignas(64) CUtensorMap tm_x, tm_a;
   CSMRI_TRY(make_tile_map(&tm_x, x, B, H, W, CW));
   if (ADD) CSMRI_TRY(make_tile_map(&tm_a, addend, B, H, W, CW));
@@ -759,8 +870,7 @@ static int launch_strip_pipe_wt(const float* x, const float* residual, const flo
   int grid = sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
   unsigned* sched = nullptr;
-  CSMRI_CUDA(cudaGetSymbolAddress((void**)&sched, g_sched));
-  sched += 2 * (g_sched_next.fetch_add(1u) & 63u);
+  CSMRI_TRY(sched_slot(s, &sched));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(CW * L::T);
@@ -805,12 +915,9 @@ static int launch_strip_pipev_wt(const float* x, const float* residual, const fl
   constexpr int threads = (CW / 2) * (H / E);
   auto kern = dc_strip_pipev_kernel<H, E, CW, MINB, WT, ADD>;
   CSMRI_TRY(set_smem(kern, S::kBytes));
-  static int blocks_per_sm = 0;
-  if (blocks_per_sm == 0) {
-    CSMRI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads,
-                                                             S::kBytes));
-    if (blocks_per_sm < 1) return fail(CSMRI_E_CUDA, "two-column strip kernel does not fit an SM");
-  }
+  static std::atomic<int> occ[64];
+  const int blocks_per_sm = resident_blocks(kern, threads, S::kBytes, occ);
+  if (blocks_per_sm < 1) return fail(CSMRI_E_CUDA, "two-column strip kernel does not fit an SM");
   alignas(64) CUtensorMap tm_x, tm_a;
   CSMRI_TRY(make_tile_map(&tm_x, x, B, H, W, CW));
   if (ADD) CSMRI_TRY(make_tile_map(&tm_a, addend, B, H, W, CW));
@@ -819,11 +926,8 @@ static int launch_strip_pipev_wt(const float* x, const float* residual, const fl
   const int ntiles = B * nstrips;
   int grid = sm_count() * blocks_per_sm;
   if (grid > ntiles) grid = ntiles;
-  // scheduler slot: a ring of 64 (tile counter, retired counter) pairs, so up
-  // to 64 launches may be in flight on different streams at once
   unsigned* sched = nullptr;
-  CSMRI_CUDA(cudaGetSymbolAddress((void**)&sched, g_sched));
-  sched += 2 * (g_sched_next.fetch_add(1u) & 63u);
+  CSMRI_TRY(sched_slot(s, &sched));
   long long* trace =
       g_trace ? g_trace + (size_t)((g_trace_launch++) & 1) * 1024 * 40 : nullptr;
   cudaLaunchConfig_t cfg = {};
@@ -1064,6 +1168,7 @@ static int launch_fft_rows_cfg(const float* in, const float* aux, float* out, in
   else if (!inv && pre == 4) CSMRI_ROWS(false, 4)
   else if (inv && pre == 0) CSMRI_ROWS(true, 0)
   else if (inv && pre == 2) CSMRI_ROWS(true, 2)
+  else if (inv && pre == 5) CSMRI_ROWS(true, 5)
   else return fail(CSMRI_E_ARG, "row kernel variant inv=%d pre=%d not instantiated", (int)inv, pre);
 #undef CSMRI_ROWS
   CSMRI_CUDA(cudaGetLastError());
@@ -1073,8 +1178,10 @@ static int launch_fft_rows_cfg(const float* in, const float* aux, float* out, in
 static int launch_fft_rows(const float* in, const float* aux, float* out, int B, int H, int W,
                            float scale, float cmulv, bool inv, int pre, cudaStream_t s,
                            const unsigned char* rowsel = nullptr, float* mask_out = nullptr) {
-  if ((pre == 4) != (rowsel != nullptr && mask_out != nullptr))
+  if ((pre == 4) != (rowsel != nullptr && mask_out != nullptr) && pre != 5)
     return fail(CSMRI_E_ARG, "row selection needs pre == 4, a row table and a mask destination");
+  if (pre == 5 && (rowsel == nullptr || mask_out != nullptr))
+    return fail(CSMRI_E_ARG, "compact input needs a row table and no mask destination");
   switch (W) {
     case 32: return launch_fft_rows_cfg<32, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s, rowsel, mask_out);   // T=4
     case 64: return launch_fft_rows_cfg<64, 8, 32>(in, aux, out, B, H, scale, cmulv, inv, pre, s, rowsel, mask_out);   // T=8
@@ -1154,6 +1261,32 @@ int csmri_dc_prepare(const float* k0, const float* mask, int B, int H, int W, fl
   }
   (void)scratch;
   return CSMRI_OK;
+}
+
+int csmri_dc_prepare_lines(const float* k0_lines, const unsigned char* rows, int B, int H, int W,
+                           int L, float noise_lvl, float* dtab, float* addend, int* lines_ok,
+                           void* stream) {
+  CSMRI_TRY(check_shape(B, H, W));
+  if (L <= 0 || L > H) return fail(CSMRI_E_SHAPE, "L must be in [1, H], got %d", L);
+  CSMRI_TRY(check_ptr(k0_lines, "k0_lines"));
+  if (rows == nullptr) return fail(CSMRI_E_NULLPTR, "rows is NULL");
+  CSMRI_TRY(check_ptr(dtab, "dtab"));
+  CSMRI_TRY(check_ptr(addend, "addend"));
+  CSMRI_TRY(check_ptr(lines_ok, "lines_ok"));
+  CSMRI_TRY(ensure_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool noisy = noise_lvl != 0.0f;
+  set_flag_kernel<<<1, 1, 0, s>>>(lines_ok, 1);
+  dtab_from_rows_checked_kernel<<<B, H < 256 ? H : 256, 0, s>>>(rows, H, strip_radix(H), L,
+                                                               noise_lvl, noisy ? 1 : 0, dtab,
+                                                               lines_ok);
+  CSMRI_CUDA(cudaGetLastError());
+  // addend = iFFT_W(c * k0) / sqrt(H*W) on the sampled rows, zero elsewhere; on a
+  // sampled row c = 1 (noiseless) or v/(1+v) (noisy, m = 1), see csmri_dc_prepare
+  float sc = 1.0f / sqrtf((float)H * (float)W);
+  if (noisy) sc *= noise_lvl / (1.0f + noise_lvl);
+  return launch_fft_rows(k0_lines, nullptr, addend, B, H, W, sc, (float)L, true, 5, s, rows,
+                         nullptr);
 }
 
 int csmri_dc_forward_cartesian(const float* x, const float* residual, const float* dtab,

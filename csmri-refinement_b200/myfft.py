@@ -22,6 +22,7 @@ cached here.
 """
 import collections
 import contextlib
+import threading
 
 import torch
 
@@ -29,29 +30,44 @@ from . import ops
 
 
 class DCPlan(object):
-    """Per-batch constants of the DC operator (see csmri_dc_prepare)."""
+    """Per-batch constants of the DC operator (see csmri_dc_prepare).
 
-    __slots__ = ('k0', 'mask', 'noise_lvl', 'dtab', 'addend', 'row_constant', 'key')
+    ``flag`` is the device int32 the prepare pass wrote (1 = every mask row is
+    constant / the line table is consistent); it is only *read* here when the
+    caller did not state ``assume_row_constant``.
+    """
+
+    __slots__ = ('k0', 'mask', 'noise_lvl', 'dtab', 'addend', 'row_constant', 'key', 'flag')
 
     def __init__(self, k0, mask, noise_lvl, assume_row_constant=None, prepared=None):
         v = float(noise_lvl) if noise_lvl else 0.0   # `if v:` of myfft.py:137
         self.k0, self.mask, self.noise_lvl = k0, mask, v
+        self.flag = None
+        self.key = None
         if prepared is not None:
-            # handed over by the loader (undersampling.undersample): the mask is
-            # row-constant by construction and (dtab, addend) already exist
+            # handed over by the loader (undersampling.undersample) or built from
+            # a line table (plan_from_lines): row-constant by construction and
+            # (dtab, addend) already exist
             self.dtab, self.addend = prepared
             self.row_constant = True
-            self.key = None
             return
-        dtab, addend, flag = ops.dc_prepare(k0.detach(), mask.detach(), v)
-        self.dtab, self.addend = dtab, addend
+        if assume_row_constant is not None and not assume_row_constant:
+            # general path stated by the caller: the k0 row transform is not needed
+            dtab, _, flag = ops.dc_prepare(k0.detach(), mask.detach(), v, False)
+            self.dtab, self.addend, self.flag, self.row_constant = dtab, None, flag, False
+            return
+        dtab, addend, flag = ops.dc_prepare(k0.detach(), mask.detach(), v, True)
+        self.dtab, self.addend, self.flag = dtab, addend, flag
         if assume_row_constant is None:
             # one 4-byte device->host read per batch
             self.row_constant = bool(flag.item())
+            if not self.row_constant:
+                self.addend = None
         else:
-            self.row_constant = bool(assume_row_constant)
-        if not self.row_constant:
-            self.addend = None
+            self.row_constant = True
+            rec = _ASSUMPTION_RECORDER
+            if rec is not None:
+                rec.flags.append(flag)     # checked later by whoever made the assumption
 
 
 def _tensor_key(t):
@@ -61,7 +77,25 @@ def _tensor_key(t):
 
 _PLAN_CACHE = collections.OrderedDict()
 _PLAN_CACHE_SIZE = 4     # keys; an entry pins k0, mask and the prepared k0 term of one batch
+_PLAN_LOCK = threading.RLock()   # DataParallel-style callers reach the cache from several threads
 _ASSUME_ROW_CONSTANT = None     # process-wide default, see assume_row_constant()
+_ASSUMPTION_RECORDER = None
+
+
+class _Assumption(object):
+    """What ``assume_row_constant`` yields: the device flags of every plan that
+    was built on the assumption inside the block.  ``violations()`` returns a
+    0-dim int64 tensor (number of batches whose mask was NOT row-constant)
+    without synchronising, so it can be evaluated inside a CUDA graph."""
+
+    def __init__(self, value):
+        self.value = value
+        self.flags = []
+
+    def violations(self):
+        if not self.flags:
+            return None
+        return (1 - torch.stack([f.reshape(()) for f in self.flags])).sum()
 
 
 @contextlib.contextmanager
@@ -69,37 +103,48 @@ def assume_row_constant(value):
     """Within the block, skip the per-batch device->host read that proves the
     mask is row-constant and take ``value`` (True: Cartesian strip kernel,
     False: general path, None: check) instead.  Needed under CUDA-graph
-    capture, where a host read is illegal."""
-    global _ASSUME_ROW_CONSTANT
-    prev = _ASSUME_ROW_CONSTANT
+    capture, where a host read is illegal.  With ``True`` the proof is still
+    computed on the device; the yielded object collects those flags so the
+    caller can verify the assumption after the fact (ShardedTrainer does)."""
+    global _ASSUME_ROW_CONSTANT, _ASSUMPTION_RECORDER
+    prev, prev_rec = _ASSUME_ROW_CONSTANT, _ASSUMPTION_RECORDER
+    rec = _Assumption(value)
     _ASSUME_ROW_CONSTANT = value
+    _ASSUMPTION_RECORDER = rec if value else None
     try:
-        yield
+        yield rec
     finally:
-        _ASSUME_ROW_CONSTANT = prev
-
+        _ASSUME_ROW_CONSTANT, _ASSUMPTION_RECORDER = prev, prev_rec
 
 
 def get_plan(k0, mask, noise_lvl=None, assume_row_constant=None):
     """Cached :class:`DCPlan` for this (k0, mask, noise_lvl).
 
     The cache keeps the two tensors alive, so their storage cannot be handed
-    to another batch while an entry exists; in-place writes bump ``_version``
-    and miss.  Entries are evicted LRU (4 keys = 2-4 batches).
+    to another batch while an entry exists; in-place writes through torch bump
+    ``_version`` and miss.  Writes torch cannot see (a CUDA-graph replay filling
+    static input buffers, ``.data`` writes, raw C-ABI writes) do NOT miss: such
+    callers must bypass the cache - pass ``plan=`` to :func:`dc_perform` or call
+    :func:`clear_plan_cache` (ShardedTrainer rebuilds the plan inside its graph).
+    Entries are evicted LRU (4 keys = 2-4 batches).
     """
     v = float(noise_lvl) if noise_lvl else 0.0
     if assume_row_constant is None:
         assume_row_constant = _ASSUME_ROW_CONSTANT
     key = (_tensor_key(k0), _tensor_key(mask), v, assume_row_constant)
-    plan = _PLAN_CACHE.get(key)
-    if plan is not None:
-        _PLAN_CACHE.move_to_end(key)
-        return plan
+    with _PLAN_LOCK:
+        plan = _PLAN_CACHE.get(key)
+        if plan is not None:
+            _PLAN_CACHE.move_to_end(key)
+            if plan.flag is not None and assume_row_constant and _ASSUMPTION_RECORDER is not None:
+                _ASSUMPTION_RECORDER.flags.append(plan.flag)
+            return plan
     plan = DCPlan(k0, mask, v, assume_row_constant)
     plan.key = key
-    _PLAN_CACHE[key] = plan
-    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
-        _PLAN_CACHE.popitem(last=False)
+    with _PLAN_LOCK:
+        _PLAN_CACHE[key] = plan
+        while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+            _PLAN_CACHE.popitem(last=False)
     return plan
 
 
@@ -108,18 +153,38 @@ def register_plan(k0, mask, dtab, addend):
     (``ops.undersample(..., with_plan=True)``): the first DC layer then needs no
     prepare pass and no device->host read for this batch."""
     plan = DCPlan(k0, mask, 0.0, prepared=(dtab, addend))
-    for arc in (None, True):
-        key = (_tensor_key(k0), _tensor_key(mask), 0.0, arc)
-        _PLAN_CACHE[key] = plan
-        _PLAN_CACHE.move_to_end(key)
-    plan.key = key
-    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
-        _PLAN_CACHE.popitem(last=False)
+    with _PLAN_LOCK:
+        for arc in (None, True):
+            key = (_tensor_key(k0), _tensor_key(mask), 0.0, arc)
+            _PLAN_CACHE[key] = plan
+            _PLAN_CACHE.move_to_end(key)
+        plan.key = key
+        while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+            _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def plan_from_lines(k0_lines, rows, noise_lvl=None, check=True):
+    """:class:`DCPlan` from the compact description of a Cartesian acquisition:
+    ``rows`` (B,H) uint8 sampled-line table and ``k0_lines`` (B,2,L,W) =
+    ``kspace[b][:, rows[b] != 0, :]`` (k0 is zero off the sampled lines by
+    construction, compressed_sensing.py:510).  Nothing dense has to exist on
+    the host or cross PCIe.  ``check`` reads the 4-byte consistency flag (every
+    slice has exactly L sampled rows); pass False under graph capture / in a
+    pipeline and look at ``plan.flag`` later.  Not cached: the caller owns it."""
+    v = float(noise_lvl) if noise_lvl else 0.0
+    dtab, addend, ok = ops.dc_prepare_lines(k0_lines, rows, v, k0_lines.shape[-1])
+    if check and not bool(ok.item()):
+        raise ValueError('rows / k0_lines are inconsistent: every slice must have exactly '
+                         '%d sampled rows' % k0_lines.shape[2])
+    plan = DCPlan(None, None, v, prepared=(dtab, addend))
+    plan.flag = ok
     return plan
 
 
 def clear_plan_cache():
-    _PLAN_CACHE.clear()
+    with _PLAN_LOCK:
+        _PLAN_CACHE.clear()
 
 
 def make_contiguous(*Xs):
@@ -229,3 +294,11 @@ class DataConsistencyInKspace(object):
                    (the `x + block_input` of models/recnet.py:147-148)
         """
         return dc_perform(x, k0, mask, self.noise_lvl, residual)
+
+    def perform_lines(self, x, k0_lines, rows, residual=None, plan=None):
+        """Same operator for a Cartesian acquisition given compactly (extension,
+        see :func:`plan_from_lines`): ``rows`` (B,H) uint8 line table and
+        ``k0_lines`` (B,2,L,W), the sampled lines of k0 only."""
+        if plan is None:
+            plan = plan_from_lines(k0_lines, rows, self.noise_lvl)
+        return dc_perform(x, None, None, self.noise_lvl, residual, plan=plan)

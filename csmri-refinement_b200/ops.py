@@ -40,9 +40,11 @@ def _check_planar(name, t, like=None):
 # csmri::dc_prepare - once per batch (k0 and mask are constant over the cascade)
 # ---------------------------------------------------------------------------
 @torch.library.custom_op('csmri::dc_prepare', mutates_args=(), device_types='cuda')
-def dc_prepare(k0: torch.Tensor, mask: torch.Tensor,
-               noise_lvl: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """-> (dtab (B,H), addend (B,2,H,W), row_constant int32[1])."""
+def dc_prepare(k0: torch.Tensor, mask: torch.Tensor, noise_lvl: float,
+               with_addend: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (dtab (B,H), addend (B,2,H,W), row_constant int32[1]).  ``with_addend``
+    False skips the row transform of k0 (addend comes back empty): the mask
+    analysis alone, for callers that first want to know which path applies."""
     _check_planar('k0', k0)
     _check_planar('mask', mask, k0)
     k0 = k0.contiguous()
@@ -50,19 +52,57 @@ def dc_prepare(k0: torch.Tensor, mask: torch.Tensor,
     B, _, H, W = k0.shape
     with torch.cuda.device(k0.device):
         dtab = torch.empty((B, H), dtype=torch.float32, device=k0.device)
-        addend = torch.empty_like(k0)
+        addend = torch.empty_like(k0) if with_addend else k0.new_empty((0,))
         flag = torch.empty((1,), dtype=torch.int32, device=k0.device)
         _lib.check(_lib.lib().csmri_dc_prepare(
-            _ptr(k0), _ptr(mask), B, H, W, float(noise_lvl), _ptr(dtab), _ptr(addend),
-            _ptr(flag), None, _stream()))
+            _ptr(k0), _ptr(mask), B, H, W, float(noise_lvl), _ptr(dtab),
+            _ptr(addend) if with_addend else None, _ptr(flag), None, _stream()))
     return dtab, addend, flag
 
 
 @dc_prepare.register_fake
-def _(k0, mask, noise_lvl):
+def _(k0, mask, noise_lvl, with_addend=True):
     B, _, H, W = k0.shape
-    return (k0.new_empty((B, H)), torch.empty_like(k0),
+    return (k0.new_empty((B, H)), torch.empty_like(k0) if with_addend else k0.new_empty((0,)),
             k0.new_empty((1,), dtype=torch.int32))
+
+
+# ---------------------------------------------------------------------------
+# csmri::dc_prepare_lines - the same plan from a compact Cartesian description
+# ---------------------------------------------------------------------------
+@torch.library.custom_op('csmri::dc_prepare_lines', mutates_args=(), device_types='cuda')
+def dc_prepare_lines(k0_lines: torch.Tensor, rows: torch.Tensor, noise_lvl: float,
+                     width: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """k0_lines (B,2,L,W) = kspace[b][:, rows[b] != 0, :], rows (B,H) uint8
+    -> (dtab (B,H), addend (B,2,H,W), lines_ok int32[1])."""
+    if k0_lines.dim() != 4 or k0_lines.size(1) != 2 or k0_lines.dtype != torch.float32:
+        raise ValueError('k0_lines must be a float32 (B,2,L,W) tensor, got %s %s'
+                         % (tuple(k0_lines.shape), k0_lines.dtype))
+    if not k0_lines.is_cuda:
+        raise RuntimeError('k0_lines must be a CUDA tensor: the DC path has no CPU fallback')
+    B, _, L, W = k0_lines.shape
+    if W != width:
+        raise ValueError('k0_lines has width %d, expected %d' % (W, width))
+    if rows.dim() != 2 or rows.size(0) != B or rows.dtype != torch.uint8 or \
+            rows.device != k0_lines.device:
+        raise ValueError('rows must be a uint8 (B,H) tensor on the same device')
+    H = rows.size(1)
+    k0_lines, rows = k0_lines.contiguous(), rows.contiguous()
+    with torch.cuda.device(k0_lines.device):
+        dtab = torch.empty((B, H), dtype=torch.float32, device=k0_lines.device)
+        addend = torch.empty((B, 2, H, W), dtype=torch.float32, device=k0_lines.device)
+        ok = torch.empty((1,), dtype=torch.int32, device=k0_lines.device)
+        _lib.check(_lib.lib().csmri_dc_prepare_lines(
+            _ptr(k0_lines), _ptr(rows), B, H, W, L, float(noise_lvl), _ptr(dtab), _ptr(addend),
+            _ptr(ok), _stream()))
+    return dtab, addend, ok
+
+
+@dc_prepare_lines.register_fake
+def _(k0_lines, rows, noise_lvl, width):
+    B, H = rows.shape
+    return (k0_lines.new_empty((B, H)), k0_lines.new_empty((B, 2, H, width)),
+            k0_lines.new_empty((1,), dtype=torch.int32))
 
 
 # ---------------------------------------------------------------------------

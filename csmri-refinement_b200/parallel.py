@@ -105,6 +105,19 @@ class ShardedTrainer(object):
     ``cuda_graph=True`` captures zero_grad + forward + loss + backward +
     allreduce + Adam into one CUDA graph replayed per step on static input
     buffers (the ~100 small kernels of a D5C5 step are launch-bound otherwise).
+
+    Uneven shards (``shard_range`` when the global batch is not a multiple of
+    the world size): every rank scales its loss by ``local_n * world / global_n``
+    before backward, so SUM-allreduce / world is the gradient of the mean loss
+    over the GLOBAL batch - what the reference's single-process DataParallel
+    computes (utils/__init__.py:59-68 scatters one batch, the loss is taken on
+    the gathered output).
+
+    ``assume_row_constant=True`` (required under a CUDA graph, where the
+    per-batch device->host read of the mask proof is illegal) is *verified*: the
+    proof is still computed on the device inside the step, accumulated into a
+    sticky counter and copied to pinned host memory asynchronously; the next
+    ``step()`` raises if any earlier batch had a mask that is not row-constant.
     """
 
     def __init__(self, model, lr=2e-4, betas=(0.9, 0.999), cuda_graph=False,
@@ -114,21 +127,54 @@ class ShardedTrainer(object):
         self.cuda_graph = bool(cuda_graph)
         self.assume_row_constant = assume_row_constant
         dev = self.bucket.flat.device
+        self.device = dev
         self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, betas=betas,
                                           capturable=self.cuda_graph and dev.type == 'cuda')
         self.criterion = torch.nn.MSELoss()
         self._graph = None
         self._static = None
         self._loss = None
+        self._loss_weight = None     # local_n * world / global_n, fixed at the first step
+        self._local_n = None
+        # verification of assume_row_constant=True
+        self._bad = None             # device int64 counter (sticky)
+        self._bad_host = None        # pinned mirror
+        self._prev_event = None
+        if assume_row_constant and dev.type == 'cuda':
+            self._bad = torch.zeros((), dtype=torch.int64, device=dev)
+            self._bad_host = torch.zeros((), dtype=torch.int64).pin_memory()
+
+    def _weight_for(self, batch):
+        n = int(batch['inp'].shape[0])
+        if self._loss_weight is None or n != self._local_n:
+            if self._graph is not None:
+                raise ValueError('the CUDA-graph step was captured for %d slices per rank, got %d'
+                                 % (self._local_n, n))
+            world = self.bucket.world
+            if world > 1:
+                t = torch.tensor([n], dtype=torch.int64, device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                total = int(t.item())
+            else:
+                total = n
+            self._local_n = n
+            self._loss_weight = float(n) * world / float(total)
+        return self._loss_weight
 
     def _step_eager(self, batch):
         from . import myfft
+        weight = self._loss_weight if self._loss_weight is not None else 1.0
         self.bucket.zero_()
-        with myfft.assume_row_constant(self.assume_row_constant):
+        with myfft.assume_row_constant(self.assume_row_constant) as assumed:
             out = self.model(batch['inp'], batch['kspace'], batch['mask'])
+        if self._bad is not None:
+            viol = assumed.violations()
+            if viol is not None:
+                self._bad.add_(viol)
+                self._bad_host.copy_(self._bad, non_blocking=True)
         pred = out['pred'] if isinstance(out, dict) else out
         loss = self.criterion(pred, batch['target'])
-        loss.backward()
+        (loss if weight == 1.0 else loss * weight).backward()
         self.bucket.allreduce_mean()
         self.optimizer.step()
         return loss.detach()
@@ -167,16 +213,39 @@ class ShardedTrainer(object):
                         else:
                             v.zero_()
 
+    def _check_assumption(self):
+        """Raise if an EARLIER step saw a mask that is not row-constant (the
+        flag of the step just launched is looked at by the next call)."""
+        if self._bad_host is None:
+            return
+        prev, self._prev_event = self._prev_event, torch.cuda.Event()
+        self._prev_event.record()
+        if prev is not None:
+            prev.synchronize()         # the step before the one just launched has finished
+            if int(self._bad_host.item()) != 0:
+                raise RuntimeError(
+                    'ShardedTrainer(assume_row_constant=True): %d batch(es) had a mask that is '
+                    'not constant along W (not a Cartesian mask, compressed_sensing.py:115-116); '
+                    'the Cartesian strip kernel gave wrong results for them. Use '
+                    'assume_row_constant=None (checked, eager) or False (general path).'
+                    % int(self._bad_host.item()))
+
     def step(self, batch):
         """One optimizer step; returns the (local-shard) loss as a 0-dim tensor."""
+        self._weight_for(batch)
         if not self.cuda_graph:
-            return self._step_eager(batch)
+            loss = self._step_eager(batch)
+            self._check_assumption()
+            return loss
         if self.assume_row_constant is None:
             raise ValueError('cuda_graph=True needs assume_row_constant=True/False: the mask '
                              'check is a device->host read, which a graph cannot contain')
         if self._graph is None:
             self._capture(batch)
+            if self._bad is not None:      # the warm-up steps ran on this batch too
+                self._bad_host.copy_(self._bad, non_blocking=True)
         for k, v in batch.items():
             self._static[k].copy_(v, non_blocking=True)
         self._graph.replay()
+        self._check_assumption()
         return self._loss

@@ -161,6 +161,14 @@ class RecNet(nn.Module):
 def construct_model(conf, model_name=None, **kwargs):
     """models/recnet.py:20-26: build from a reference ``Configuration`` (or any
     object with ``to_param_dict``) or a plain dict of the same keys."""
+    user_init = conf.get_attr('weight_init', default={}) if hasattr(conf, 'get_attr') \
+        else conf.get('weight_init', {})
+    if user_init:
+        # the reference merges these rules into the per-block init
+        # (models/recnet.py:23-24, weight_inits.py:109-114); neither shipped config
+        # sets them for RecNet, and silently ignoring them would change the weights
+        raise NotImplementedError('a RecNet `weight_init` override is not supported: %r'
+                                  % (user_init,))
     if hasattr(conf, 'to_param_dict'):
         params = conf.to_param_dict(RECNET_REQUIRED_PARAMS, RECNET_OPTIONAL_PARAMS)
     else:

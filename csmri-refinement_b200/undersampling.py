@@ -92,6 +92,26 @@ def undersample(img, rows, register_dc_plan=True):
     return batch
 
 
+def compact_lines(kspace, rows):
+    """Sampled lines of a Cartesian k-space batch, ``kspace[b][:, rows[b] != 0, :]``
+    stacked to (B,2,L,W) in ascending row order - the compact form
+    ``myfft.plan_from_lines`` / ``HostDCPipeline.forward_backward_lines`` take
+    (k0 is zero everywhere else, compressed_sensing.py:510).  Works on host and
+    device tensors; every slice must have the same number of sampled rows
+    (``cs.cartesian_mask`` always samples ``Nx // acc`` lines)."""
+    if isinstance(rows, np.ndarray):
+        rows = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.uint8))
+    rows = rows.to(kspace.device)
+    counts = (rows != 0).sum(dim=1)
+    n_lines = int(counts[0].item())
+    if n_lines == 0 or not bool((counts == n_lines).all().item()):
+        raise ValueError('every slice needs the same, non-zero number of sampled rows')
+    b, _, h, w = kspace.shape
+    idx = (rows != 0).nonzero()[:, 1].reshape(b, n_lines)          # ascending per slice
+    gather = idx[:, None, :, None].expand(b, 2, n_lines, w)
+    return torch.gather(kspace, 2, gather).contiguous()
+
+
 class Undersample(object):
     """Batch/GPU version of myImageTransformations.Undersample (:1196-1238).
 

@@ -62,12 +62,32 @@ size_t csmri_dc_workspace_bytes(int B, int H, int W);
  *                          compressed_sensing.py:115-116 that the Cartesian
  *                          strip kernel relies on), else 0
  *   scratch           unused by prepare (kept for ABI symmetry), may be NULL
- * noise_lvl <= 0 or NaN-free 0 selects the noiseless branch (`if v:`,
- * myfft.py:137-138).
+ * noise_lvl == 0 selects the noiseless branch; every other value, negative
+ * ones included, takes the noisy formula - the truthiness test `if v:` of
+ * myfft.py:137-138 (Python callers map None to 0).
  */
 int csmri_dc_prepare(const float* k0, const float* mask, int B, int H, int W,
                      float noise_lvl, float* dtab, float* addend,
                      int* row_constant, void* scratch, void* stream);
+
+/* ---- once per batch, from what a Cartesian loader actually holds -----------
+ * Same outputs as csmri_dc_prepare for a Cartesian acquisition described
+ * compactly: the sampled-line table and only the sampled lines of k0.  A host
+ * caller ships N bytes + 8*L*W bytes per slice instead of the two dense
+ * (2,H,W) tensors the reference's loader builds (dnn_io.py:47-61 expands the
+ * mask to a dense 2-channel array; compressed_sensing.py:510 leaves k0 zero off
+ * the sampled lines), e.g. 0.27 instead of 2 tensors at 4x acceleration.
+ *   k0_lines (B,2,L,W)  k0[b,c,h_j,:] for the L sampled rows h_0 < h_1 < ... of
+ *                       slice b (= kspace[b][:, rows[b] != 0, :]); k0 is taken
+ *                       to be zero off the sampled lines (k0 = mask * k0)
+ *   rows     (B,H)      uint8, 1 = sampled line, as for csmri_undersample
+ *   lines_ok            out: device int, 0 if some slice does not have exactly L
+ *                       sampled rows (the plan is then invalid), else 1
+ */
+int csmri_dc_prepare_lines(const float* k0_lines, const unsigned char* rows,
+                           int B, int H, int W, int L, float noise_lvl,
+                           float* dtab, float* addend, int* lines_ok,
+                           void* stream);
 
 /* ---- DC forward, Cartesian (row-constant) masks ---------------------------
  * Replaces DataConsistencyInKspace.perform (myfft.py:153-163) =

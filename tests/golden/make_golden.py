@@ -19,6 +19,10 @@ Everything stored here is an output of unmodified reference code imported from
 * ``_scale`` / ``_unscale`` / ``_refinement_real_penalty_add``
   models/refinement_wrapper.py:51-92,173-197 and ``magnitude_image``
   utils/tensor_transforms.py:78-99
+* ``configs/1-recnet.json`` and ``configs/2-refinement.json`` copied byte for
+  byte (they are the INPUTS north_star says must run unchanged; sha256 recorded)
+  and what ``Configuration.from_json`` + ``construct_model`` build from the
+  first one under its own seed (keys, shapes, initial weights)
 
 The fixtures are small (< 1 MB in total) and are what pins ``oracle/``.
 """
@@ -212,6 +216,43 @@ def main():
                pred=res['pred'].detach().numpy(), cot=cot.numpy(),
                grad_learn=learn.grad.numpy(), grad_scale=scale_p.grad.numpy())
     np.savez_compressed(os.path.join(HERE, 'refinement_ops.npz'), **ref)
+
+    # ---- 8. the shipped run configurations, byte for byte, and what the reference
+    #         builds from configs/1-recnet.json (utils/config.py:212-250,
+    #         training/runner.py:18-21, models/recnet.py:20-26) ---------------------
+    import hashlib
+    import shutil
+    from utils.config import Configuration
+    from models import construct_model
+    cdir = os.path.join(HERE, 'configs')
+    os.makedirs(cdir, exist_ok=True)
+    conf_fix = {}
+    for name in ('1-recnet.json', '2-refinement.json'):
+        shutil.copyfile(os.path.join(REF, 'configs', name), os.path.join(cdir, name))
+        with open(os.path.join(cdir, name), 'rb') as f:
+            conf_fix['sha256:' + name] = np.array(hashlib.sha256(f.read()).hexdigest())
+    conf = Configuration.from_json(os.path.join(REF, 'configs', '1-recnet.json'))
+    model_conf = Configuration.from_dict(conf.model, conf)
+    torch.manual_seed(conf.seed)
+    net1 = construct_model(model_conf, model_conf.name)
+    conf_fix['recnet1:seed'] = np.int64(conf.seed)
+    conf_fix['recnet1:num_params'] = np.int64(sum(p.numel() for p in net1.parameters()))
+    conf_fix['recnet1:num_dc'] = np.int64(len(net1.dc_layers))
+    conf_fix['recnet1:keys'] = np.array(list(net1.state_dict().keys()))
+    for k, v in net1.state_dict().items():
+        conf_fix['recnet1:w:' + k] = v.numpy()
+    conf_fix['recnet1:batch_size'] = np.int64(conf.batch_size)
+    conf_fix['recnet1:acc'] = np.int64(conf.undersampling['acceleration_factor'])
+    conf_fix['recnet1:lr'] = np.float64(conf.optimizer['learning_rate'])
+    conf2 = Configuration.from_json(os.path.join(REF, 'configs', '2-refinement.json'))
+    conf_fix['refine2:seed'] = np.int64(conf2.seed)
+    conf_fix['refine2:top_keys'] = np.array(sorted(k for k in conf2.__dict__
+                                                   if not k.startswith('_')))
+    gen_conf = Configuration.from_dict(conf2.generator_model, conf2)
+    conf_fix['refine2:gen_mode'] = np.array(gen_conf.mode)
+    conf_fix['refine2:disc_has_name'] = np.bool_(
+        Configuration.from_dict(conf2.discriminator_model, conf2).has_attr('name'))
+    np.savez_compressed(os.path.join(HERE, 'configs.npz'), **conf_fix)
 
     tot = sum(os.path.getsize(os.path.join(HERE, f))
               for f in os.listdir(HERE) if f.endswith('.npz'))

@@ -72,6 +72,37 @@ def test_sass_is_blackwell_native(built_lib):
                           text=True, check=True).stdout
     assert 'sm_100a' in sass or 'SM100' in sass.upper() or 'arch = sm_100' in sass
     assert 'FFMA2' in sass and 'FADD2' in sass
+    # per-kernel: the hot strip kernels are TMA-fed (UTMALDG tensor loads landing on
+    # an mbarrier = SYNCS), the thin convolutions stage with cp.async (LDGSTS)
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import sass_histogram
+    hist = sass_histogram.histogram(sass)
+    hot = [k for k in hist if 'dc_strip_pipev_kernel' in k]
+    assert hot, 'two-column strip kernel missing from the library'
+    for k in hot:
+        assert hist[k].get('UTMALDG', 0) >= 1, k
+        assert hist[k].get('SYNCS', 0) >= 1, k
+        assert hist[k].get('FFMA2', 0) + hist[k].get('FADD2', 0) + hist[k].get('FMUL2', 0) >= 300, k
+        assert hist[k].get('HMMA', 0) == 0 and hist[k].get('UTCHMMA', 0) == 0   # no tensor cores: not a contraction
+    assert any(hist[k].get('LDGSTS', 0) for k in hist if 'conv3x3' in k)
+
+
+def test_build_staleness_covers_every_source(built_lib):
+    """editing any csrc/*.cuh (not only the three files once listed)
+    must trigger a rebuild."""
+    srcs = [os.path.basename(p) for p in built_lib.sources()]
+    csrc = os.path.join(ROOT, 'csmri-refinement_b200', 'csrc')
+    on_disk = [f for f in os.listdir(csrc) if f.endswith(('.cu', '.cuh'))]
+    assert set(on_disk) <= set(srcs) and 'csmri_dc.h' in srcs
+    assert not built_lib.is_stale()
+    probe = os.path.join(csrc, 'dc_pipev.cuh')
+    st = os.stat(probe)
+    try:
+        os.utime(probe, (st.st_atime, os.path.getmtime(built_lib.LIB_PATH) + 5))
+        assert built_lib.is_stale()
+    finally:
+        os.utime(probe, (st.st_atime, st.st_mtime))
+    assert not built_lib.is_stale()
 
 
 def test_host_emulation_of_the_thread_choreography(tmp_path):
@@ -201,3 +232,80 @@ def test_conv_module_is_a_plain_conv2d_on_cpu():
     assert m.weight.grad is not None and x.grad is not None
     with pytest.raises(RuntimeError):
         conv.conv3x3_wgrad(x.detach(), out.detach(), 1)     # no CPU implementation
+
+
+def test_configuration_mirror_reads_the_shipped_configs_unchanged(golden_dir):
+    """configs/1-recnet.json and 2-refinement.json are byte-identical copies of
+    the reference's files, parse through the Configuration mirror exactly as
+    through utils/config.py:212-250, and construct_model on the first builds the
+    reference's network: same keys, same shapes, SAME initial weights under the
+    config's own seed (training/runner.py:18-21, models/recnet.py:20-26)."""
+    import hashlib
+    from csmri_refinement_b200 import harness
+    from csmri_refinement_b200.config import Configuration
+    g = np.load(os.path.join(golden_dir, 'configs.npz'))
+    for name in ('1-recnet.json', '2-refinement.json'):
+        path = harness.config_path(name)
+        with open(path, 'rb') as f:
+            data = f.read()
+        assert hashlib.sha256(data).hexdigest() == str(g['sha256:' + name])
+        ref = os.path.join('/root/reference/configs', name)
+        if os.path.exists(ref):                        # build container only
+            assert open(ref, 'rb').read() == data
+    conf = harness.load_config(harness.config_path('1-recnet.json'))
+    assert conf.seed == int(g['recnet1:seed']) and 'seed' not in conf.__dict__
+    assert conf.file.endswith('1-recnet.json')
+    assert isinstance(conf.model, dict) and conf.batch_size == int(g['recnet1:batch_size'])
+    assert conf.get_attr('nonexistent', default=7) == 7
+    assert conf.get_attr('nonexistent', alternative='batch_size') == 20
+    with pytest.raises(ValueError):
+        conf.get_attr('nonexistent', alternative='also_missing')
+    harness.set_random_seeds(conf.seed)
+    net = harness.build_recnet(conf)
+    assert sum(p.numel() for p in net.parameters()) == int(g['recnet1:num_params']) == 31302
+    assert len(net.dc_layers) == int(g['recnet1:num_dc'])
+    assert list(net.state_dict().keys()) == [str(k) for k in g['recnet1:keys']]
+    for k, v in net.state_dict().items():
+        assert np.array_equal(v.numpy(), g['recnet1:w:' + k]), k
+    assert harness.adam_args(conf.optimizer, conf) == {'lr': float(g['recnet1:lr']),
+                                                      'betas': (0.9, 0.999)}
+    assert harness.undersampling_args(conf) == {'acc': int(g['recnet1:acc']), 'variable': False}
+    conf2 = harness.load_config(harness.config_path('2-refinement.json'))
+    assert conf2.seed == int(g['refine2:seed'])
+    assert sorted(k for k in conf2.__dict__ if not k.startswith('_')) == \
+        [str(k) for k in g['refine2:top_keys']]
+    gen = Configuration.from_dict(conf2.generator_model, conf2)
+    assert gen.mode == str(g['refine2:gen_mode']) and gen.seed == conf2.seed
+    disc = Configuration.from_dict(conf2.discriminator_model, conf2)
+    assert disc.has_attr('name') == bool(g['refine2:disc_has_name'])   # SURVEY D6: it has none
+    assert harness.adam_args(conf2.generator_optimizer, conf2)['betas'] == (0.5, 0.999)
+    # --conf key=value overrides and the include mechanisms
+    conf.update({'batch_size': '8', 'seed': '3', 'tags': '[a, 1, 2.5]', 'flag': 'True'})
+    assert conf.batch_size == 8 and conf.seed == 3 and conf.tags == ['a', 1, 2.5] and conf.flag is True
+
+
+def test_configuration_includes(tmp_path):
+    """`#include` and the top-level `include` section behave as in
+    utils/config.py:10-19,236-250 (checked against the reference in the build
+    container: identical __dict__ for this input)."""
+    from csmri_refinement_b200.config import Configuration
+    (tmp_path / 'base.json').write_text('{"seed": 4, "a": 1, "model": {"x": 1, "y": 2}}')
+    (tmp_path / 'm.json').write_text('{"x": 10, "z": 30}')
+    (tmp_path / 'top.json').write_text(
+        '{"#include": "base.json", "a": 2, "include": {"model": "m.json", "opt": "m.json"}}')
+    conf = Configuration.from_json(str(tmp_path / 'top.json'))
+    assert conf.seed == 4 and conf.a == 2 and not conf.has_attr('include')
+    strip = lambda d: {k: v for k, v in d.items() if not k.startswith('_')}   # noqa: E731
+    assert strip(conf.model) == {'x': 1, 'z': 30, 'y': 2}   # own keys win over the included file
+    assert strip(conf.opt) == {'x': 10, 'z': 30}
+    assert conf.to_param_dict(['a'], ['opt', 'missing'], {'a': 'alpha'})['alpha'] == 2
+    assert conf.to_param_dict([], {'missing': 5}) == {'missing': 5}
+    if os.path.exists('/root/reference/utils/config.py'):
+        sys.path.insert(0, '/root/reference')
+        try:
+            from utils.config import Configuration as Ref
+        finally:
+            sys.path.remove('/root/reference')
+        ref = Ref.from_json(str(tmp_path / 'top.json'))
+        assert strip(ref.model) == strip(conf.model) and strip(ref.opt) == strip(conf.opt)
+        assert ref.seed == conf.seed and ref.a == conf.a

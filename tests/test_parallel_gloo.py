@@ -118,3 +118,57 @@ def test_two_rank_step_equals_single_rank_full_batch(tmp_path):
     # mean of the two shard losses == full-batch loss (equal shard sizes)
     for i in range(2):
         assert abs(0.5 * (r0['losses'][i] + r1['losses'][i]) - losses[i]) < 1e-6
+
+
+def _uneven_worker(rank, world, port, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    from csmri_refinement_b200 import parallel
+    parallel.init_distributed('gloo')
+    model = _build()
+    trainer = parallel.ShardedTrainer(model, lr=1e-3)
+    full = _make_batch(3, 32)
+    shard = parallel.shard_batch(full, rank, world)
+    assert shard['inp'].shape[0] == (2 if rank == 0 else 1)
+    trainer.step(shard)
+    torch.save({'grad1': trainer.bucket.flat.clone(), 'w': trainer._loss_weight},
+               os.path.join(out_dir, 'u%d.pt' % rank))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_uneven_shards_give_the_global_batch_gradient(tmp_path):
+    """3 slices over 2 ranks (shards of 2 and 1).  Each rank weights
+    its mean loss by local_n * world / global_n, so the allreduced mean is the
+    gradient of the mean loss over all 3 slices (what the reference's
+    single-process DataParallel step computes), not the mean of shard means."""
+    world, port = 2, _free_port()
+    mp.spawn(_uneven_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(os.path.join(str(tmp_path), 'u0.pt'))
+    r1 = torch.load(os.path.join(str(tmp_path), 'u1.pt'))
+    assert abs(r0['w'] - 4.0 / 3.0) < 1e-12 and abs(r1['w'] - 2.0 / 3.0) < 1e-12
+    assert torch.equal(r0['grad1'], r1['grad1'])
+    from csmri_refinement_b200 import parallel
+    model = _build()
+    trainer = parallel.ShardedTrainer(model, lr=1e-3)
+    trainer.step(_make_batch(3, 32))
+    assert orc.rel_l2(r0['grad1'].numpy(), trainer.bucket.flat.numpy()) < 1e-5
+
+
+def test_harness_builds_the_1recnet_step_on_cpu():
+    """configs/1-recnet.json -> model, optimizer arguments and this rank's share of
+    the GLOBAL batch 20 (strong scaling: 8 ranks get 3,3,3,3,2,2,2,2)."""
+    from csmri_refinement_b200 import harness, parallel
+    conf = harness.load_config(harness.config_path('1-recnet.json'))
+    sizes = []
+    for r in range(8):
+        lo, hi = parallel.shard_range(conf.batch_size, r, 8)
+        sizes.append(hi - lo)
+    assert sizes == [3, 3, 3, 3, 2, 2, 2, 2]
+    trainer, local_b = harness.recnet_trainer(conf, torch.device('cpu'), rank=5, world=8)
+    assert local_b == 2 and not trainer.cuda_graph
+    opt = trainer.optimizer.param_groups[0]
+    assert opt['lr'] == 2e-4 and tuple(opt['betas']) == (0.9, 0.999)
+    assert trainer.bucket.nbytes() == 31302 * 4
