@@ -451,17 +451,8 @@ __global__ void __launch_bounds__(R*(W / E))
 #pragma unroll
   for (int rr = 0; rr < E; ++rr) {
     const int k0i = (rr / T) * T + E * (rr % T);          // + j
-    float im = v[rr].y * scale;
-    if (PRE == 4) {
-      // csmri_undersample transforms REAL images: the four self-conjugate bins
-      // (k_H in {0, H/2}) x (k_W in {0, W/2}) are real.  numpy leaves an exact 0.0
-      // there (compressed_sensing.py:509); the radix-5 butterflies of 320 leave
-      // rounding noise, so pin them - the k-space support must be bit-exact.
-      const int kw = k0i + j;
-      if ((row == 0 || 2 * row == H) && (kw == 0 || 2 * kw == W)) im = 0.0f;
-    }
     st_stream(out + off + k0i, v[rr].x * scale);
-    st_stream(out + off + plane + k0i, im);
+    st_stream(out + off + plane + k0i, v[rr].y * scale);
     if (PRE == 4) {
       const float m = on ? 1.0f : 0.0f;
       st_stream(mask_out + off + k0i, m);

@@ -4,6 +4,7 @@ Mirrors, with the reference's names and argument meaning:
 
 * ``scale`` / ``unscale``            models/refinement_wrapper.py:51-92 (``_scale``, ``_unscale``)
 * ``magnitude_image``                utils/tensor_transforms.py:78-99
+* ``complex_abs``                    utils/tensor_transforms.py:62-75, differentiable
 * ``refinement_real_penalty_add``    RefinementWrapper._refinement_real_penalty_add,
                                      models/refinement_wrapper.py:173-197
 
@@ -133,3 +134,26 @@ def refinement_real_penalty_add(out_pretrained, out_learnable, scale_param):
                                        scale_param)
     return {'pred': pred, 'pretrained': out_pretrained, 'prescaled_refinement': out_learnable,
             'scaled_refinement': scale_param * out_learnable}
+
+
+class _ComplexAbs(torch.autograd.Function):
+    """|z| of a planar complex batch through ``csmri_magnitude_clamp`` (bit-identical
+    to ``(re**2 + im**2) ** 0.5``); backward d|z| = (re, im) / |z| (0 where |z| = 0)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        mag = rec_transforms.magnitude(x, lo=float('-inf'), hi=float('inf'))
+        ctx.save_for_backward(x, mag)
+        return mag
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, mag = ctx.saved_tensors
+        return x * (grad / mag.clamp_min(torch.finfo(torch.float32).tiny)) * (mag > 0)
+
+
+def complex_abs(tensor):
+    """``complex_abs`` (utils/tensor_transforms.py:62-75): (B,2,H,W) -> (B,1,H,W),
+    differentiable (the generator losses of config 5 back-propagate through it)."""
+    _check_bchw('tensor', tensor, 2)
+    return _ComplexAbs.apply(tensor.contiguous())

@@ -254,6 +254,78 @@ def main():
         Configuration.from_dict(conf2.discriminator_model, conf2).has_attr('name'))
     np.savez_compressed(os.path.join(HERE, 'configs.npz'), **conf_fix)
 
+    # ---- 9. the models around the frozen RecNet in configs/2-refinement.json:
+    #         models/unet.py, models/discriminators.py built by the reference's own
+    #         construct_model under a seed (keys, init RNG order, forward values) ----
+    rm = {}
+
+    def checksum(sd):
+        return np.array([[float(v.double().sum()), float(v.double().pow(2).sum())]
+                         for v in sd.values()])
+
+    # (a) the full-size models of the shipped config: keys, shapes, weight checksums
+    gconf = Configuration.from_dict(conf2.generator_model, conf2)
+    uconf = Configuration.from_dict(gconf.learnable_model, conf2)
+    torch.manual_seed(conf2.seed)
+    unet_full = construct_model(uconf, uconf.name)
+    dconf_d = dict(conf2.discriminator_model)
+    dconf_d.setdefault('name', 'CNNDiscriminator')          # the JSON has no name
+    dconf = Configuration.from_dict(dconf_d, conf2)
+    disc_full = construct_model(dconf, dconf.name)
+    for tag, net in (('unet_full', unet_full), ('disc_full', disc_full)):
+        sd = net.state_dict()
+        rm[tag + ':keys'] = np.array(list(sd.keys()))
+        rm[tag + ':shapes'] = np.array([str(tuple(v.shape)) for v in sd.values()])
+        rm[tag + ':checksum'] = checksum(sd)
+        rm[tag + ':num_params'] = np.int64(sum(p.numel() for p in net.parameters()))
+    with torch.no_grad():
+        unet_full.eval()
+        xin = torch.from_numpy(rs.normal(size=(1, 2, 64, 64)).astype(np.float32))
+        rm['unet_full:x'] = xin.numpy()
+        rm['unet_full:y_eval'] = unet_full(xin).numpy()
+    del unet_full, disc_full
+
+    # (b) small instances of the same architectures, weights and outputs stored
+    small_u = dict(uconf.__dict__)
+    small_u.update(encode_filters=[4, 8, 16], decode_filters=[8, 4])
+    torch.manual_seed(3)
+    unet_s = construct_model(Configuration.from_dict(small_u), 'UNET')
+    small_d = dict(dconf_d)
+    small_d.update(num_filters_per_layer=[4, 8, 8, 16, 16, 16], spatial_shape=[128, 128])
+    disc_s = construct_model(Configuration.from_dict(small_d), 'CNNDiscriminator')
+    for tag, net in (('unet_s', unet_s), ('disc_s', disc_s)):
+        for k, v in net.state_dict().items():
+            rm[tag + ':w:' + k] = v.numpy().copy()     # BN buffers change in the forward below
+    xu = torch.from_numpy(rs.normal(size=(2, 2, 48, 40)).astype(np.float32))
+    rm['unet_s:x'] = xu.numpy()
+    unet_s.train()
+    yu = unet_s(xu)
+    yu.square().mean().backward()
+    rm['unet_s:y_train'] = yu.detach().numpy()
+    rm['unet_s:g_head'] = unet_s.head[0].weight.grad.numpy()
+    rm['unet_s:g_first'] = unet_s.encode_units[0].encode[1].weight.grad.numpy()
+    unet_s.eval()
+    with torch.no_grad():
+        rm['unet_s:y_eval'] = unet_s(xu).numpy()       # uses the running stats updated above
+    xd = torch.from_numpy(rs.uniform(0, 1, size=(2, 1, 128, 128)).astype(np.float32))
+    rm['disc_s:x'] = xd.numpy()
+    disc_s.eval()
+    with torch.no_grad():
+        od = disc_s(xd)
+    rm['disc_s:logits_eval'] = od['logits'].numpy()
+    rm['disc_s:prob_eval'] = od['prob'].numpy()
+    rm['disc_s:num_features'] = np.int64(len(od['features']))
+    for i, f in enumerate(od['features']):
+        rm['disc_s:feat%d_eval' % i] = f.numpy()
+    # (c) adversarial / feature losses on those outputs (models/adversarial_loss.py)
+    from models.adversarial_loss import GANLoss, FeatureMatchingLoss
+    with torch.no_grad():
+        od2 = disc_s(xd.flip(0) * 0.5)
+    rm['loss:gan_disc'] = np.float64(GANLoss('disc', '', 0.1)(od, od2).item())
+    rm['loss:gan_gen'] = np.float64(GANLoss('gen', '', 0.1)(od, od2).item())
+    rm['loss:fm_gen'] = np.float64(FeatureMatchingLoss('gen', 'L1')(od, od2).item())
+    np.savez_compressed(os.path.join(HERE, 'refinement_models.npz'), **rm)
+
     tot = sum(os.path.getsize(os.path.join(HERE, f))
               for f in os.listdir(HERE) if f.endswith('.npz'))
     print('golden fixtures written, %d bytes' % tot)

@@ -202,10 +202,21 @@ def test_undersample_vs_oracle(N, acc):
     want = orc.to_tensor_format(x_fu)
     # index selection is bit-exact: nothing outside the sampled lines ...
     assert np.all(ks[m2 == 0] == 0)
-    # ... and exactly the reference's support on them, 320 (radix-5) included:
-    # the imaginary parts of the four self-conjugate bins of a real image are
-    # exact zeros in numpy and are pinned to zero by the row kernel
-    assert np.array_equal(ks != 0, want != 0)
+    # ... and exactly the reference's support on them.  The only entries whose
+    # zero-ness is not a property of the index selection are the imaginary parts
+    # of the three self-conjugate bins (0,W/2), (H/2,0), (H/2,W/2) of a real
+    # image: mathematically 0, and for sizes with a radix-5 factor numpy itself
+    # leaves either an exact 0.0 or ~1e-17 of float64 rounding noise there
+    # depending on the data (N=320, RandomState(320): slice 1 has 0.0 at two of
+    # them, slices 0 and 2 have noise; measured in the build container).  They
+    # are compared by magnitude instead; (0,0) is an exact 0.0 on both sides.
+    same = (ks != 0) == (want != 0)
+    if N & (N - 1):
+        for (h, w) in ((0, N // 2), (N // 2, 0), (N // 2, N // 2)):
+            assert np.all(np.abs(ks[:, 1, h, w]) <= 1e-6 * np.abs(want).max())
+            same[:, 1, h, w] = True
+    assert same.all()
+    assert np.all(ks[:, 1, 0, 0] == 0) and np.all(want[:, 1, 0, 0] == 0)
     assert orc.rel_l2(ks, orc.complex_to_planar(x_fu, np.float64)) < TOL
     assert orc.rel_l2(batch['inp'].cpu().numpy(), orc.complex_to_planar(x_u, np.float64)) < TOL
     assert np.array_equal(batch['target'].cpu().numpy(), orc.to_tensor_format(img))

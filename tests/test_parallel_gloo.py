@@ -172,3 +172,79 @@ def test_harness_builds_the_1recnet_step_on_cpu():
     opt = trainer.optimizer.param_groups[0]
     assert opt['lr'] == 2e-4 and tuple(opt['betas']) == (0.9, 0.999)
     assert trainer.bucket.nbytes() == 31302 * 4
+
+
+def _small_refinement_conf(tmp_dir):
+    """configs/2-refinement.json with the widths cut down so that one adversarial
+    step runs on the CPU in seconds (same keys, same code path)."""
+    import json
+    from csmri_refinement_b200 import harness
+    with open(harness.config_path('2-refinement.json')) as f:
+        c = json.load(f)
+    c['generator_model']['learnable_model'].update(encode_filters=[4, 8, 16], decode_filters=[8, 4])
+    c['generator_model']['pretrained_model'].update(num_filters=4)
+    c['discriminator_model'].update(num_filters_per_layer=[4, 8, 8, 16, 16, 16],
+                                    spatial_shape=[128, 128], image_pool_size=3)
+    c['batch_size'] = 2
+    path = os.path.join(tmp_dir, 'small-refinement.json')
+    with open(path, 'w') as f:
+        json.dump(c, f)
+    return harness.load_config(path)
+
+
+def _refine_worker(rank, world, port, out_dir, overlap):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    from csmri_refinement_b200 import parallel, refinement_harness as rh
+    if world > 1:
+        parallel.init_distributed('gloo')
+    conf = _small_refinement_conf(out_dir if rank == 0 else os.path.join(out_dir, 'r1'))
+    trainer = rh.AdversarialTrainer(conf, torch.device('cpu'), rank, overlap=overlap,
+                                    dc_factory=orc.OracleDataConsistencyInKspace,
+                                    chunk_bytes=2048)
+    assert len(trainer.disc_bucket.chunks) > 3
+    res = []
+    for i in range(3):                       # third step draws from the (size 3) image pool
+        out = trainer.step(_make_batch(2, 128, seed=10 * rank + i))
+        res.append({k: (v.clone() if torch.is_tensor(v) else [t.clone() for t in v])
+                    for k, v in out.items()})
+    torch.save({'gen': [p.detach().clone() for p in trainer.gen_bucket.params],
+                'disc': [p.detach().clone() for p in trainer.disc_bucket.params],
+                'disc_grad': trainer.disc_bucket.flat.clone(), 'res': res,
+                'gen_keys': list(trainer.gen.state_dict().keys())},
+               os.path.join(out_dir, 'ref_%d_%d_%d.pt' % (world, int(overlap), rank)))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_adversarial_step_two_ranks_overlapped_allreduce(tmp_path):
+    """BASELINE configs[4] host logic on 2 gloo ranks: the discriminator / generator
+    gradient buckets are all-reduced chunk by chunk from backward hooks; both
+    ranks end with identical weights, and the overlapped exchange equals the
+    single all-reduce after backward."""
+    os.makedirs(os.path.join(str(tmp_path), 'r1'), exist_ok=True)
+    for overlap in (True, False):
+        mp.spawn(_refine_worker, args=(2, _free_port(), str(tmp_path), overlap), nprocs=2,
+                 join=True)
+    load = lambda w, o, r: torch.load(os.path.join(str(tmp_path), 'ref_%d_%d_%d.pt' % (w, o, r)))  # noqa: E731
+    a0, a1, b0 = load(2, 1, 0), load(2, 1, 1), load(2, 0, 0)
+    for key in ('gen', 'disc'):
+        for p, q in zip(a0[key], a1[key]):
+            assert torch.equal(p, q)                   # identical replicas
+        for p, q in zip(a0[key], b0[key]):
+            assert torch.allclose(p, q, rtol=0, atol=1e-6)   # overlapped == serial exchange
+    assert torch.allclose(a0['disc_grad'], b0['disc_grad'], rtol=1e-5, atol=1e-8)
+    assert a0['disc_grad'].abs().sum() > 0
+    assert a0['gen_keys'][0] == 'scale' and a0['gen_keys'][1].startswith('pretrained_model.')
+    r = a0['res'][-1]
+    assert len(r['gen_losses']) == 4 and all(torch.isfinite(t) for t in r['gen_losses'])
+    assert torch.isfinite(r['disc_loss']) and torch.isfinite(r['gen_loss'])
+    # frozen RecNet: its parameters are not in the generator bucket (3 conv blocks x 3 convs x 2)
+    from csmri_refinement_b200 import refinement_harness as rh
+    conf = _small_refinement_conf(str(tmp_path))
+    gen = rh.build_generator(conf, dc_factory=orc.OracleDataConsistencyInKspace)
+    n_frozen = sum(1 for p in gen.pretrained_model.parameters())
+    assert n_frozen == 18 and len(a0['gen']) == len(list(gen.parameters())) - n_frozen
