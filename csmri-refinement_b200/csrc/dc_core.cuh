@@ -67,16 +67,26 @@ struct LineFFT {
   // ncu source pages (low-throughput, high-latency path), so each CTA keeps
   // the N values it needs as a [T][E] table in shared memory and every thread
   // reads its row with E/2 broadcast LDS.128.
-  static constexpr int kTwBytes = N * (int)sizeof(cf);
+  // Row j of the shared-memory table starts at j * kTwPitch.  With LW = 8 (or 16)
+  // lanes per line a warp holds 4 (2) different j, and rows exactly E entries
+  // (a multiple of 128 bytes for E = 16 / 32) apart put their broadcast
+  // LDS.128 on the same banks: a 4-way conflict on every twiddle load (ncu r1:
+  // 16 % of the shared-load wavefronts of the adjoint were conflicts).  Two
+  // entries (16 bytes) of padding per row spread them over disjoint banks.
+  static constexpr int kTwPitch = E + 2;
+  static constexpr int kTwBytes = T * kTwPitch * (int)sizeof(cf);
   static CSMRI_HD void fill_twiddles(cf* tw_s, int tid, int nthreads) {
 #ifdef __CUDA_ARCH__
     const cf* src = g_tw_lines + tw_lines_offset(N);
-    for (int idx = tid; idx < N; idx += nthreads) tw_s[idx] = __ldg(src + idx);
+    for (int idx = tid; idx < N; idx += nthreads) {
+      const int jj = idx / E, k1 = idx - jj * E;
+      tw_s[jj * kTwPitch + k1] = __ldg(src + idx);
+    }
 #else
     for (int idx = tid; idx < N; idx += nthreads) {
       const int jj = idx / E, k1 = idx - jj * E;
       const double a = -2.0 * 3.14159265358979323846 * (double)((jj * k1) % N) / (double)N;
-      tw_s[idx] = mk((float)__builtin_cos(a), (float)__builtin_sin(a));
+      tw_s[jj * kTwPitch + k1] = mk((float)__builtin_cos(a), (float)__builtin_sin(a));
     }
 #endif
   }
@@ -94,7 +104,7 @@ struct LineFFT {
   }
   template <bool INV>
   static CSMRI_HD void apply_twiddles(cf* v, const cf* tw_s, int j) {
-    const float4* row = reinterpret_cast<const float4*>(tw_s + j * E);
+    const float4* row = reinterpret_cast<const float4*>(tw_s + j * kTwPitch);
 #pragma unroll
     for (int p = 0; p < E / 2; ++p) {
       const float4 q = row[p];
@@ -183,7 +193,7 @@ struct LineFFTV {
 
   template <bool INV>
   static CSMRI_HD void apply_twiddles(cf2* v, const cf* tw_s, int j) {
-    const float4* row = reinterpret_cast<const float4*>(tw_s + j * E);
+    const float4* row = reinterpret_cast<const float4*>(tw_s + j * Base::kTwPitch);
 #pragma unroll
     for (int p = 0; p < E / 2; ++p) {
       const float4 q = row[p];

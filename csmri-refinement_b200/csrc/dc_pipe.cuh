@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(CW*(H / E), MINB)
   float* abuf = reinterpret_cast<float*>(smem_dyn + S::kAOff);   // absent when !ADD
   float* dbuf = reinterpret_cast<float*>(smem_dyn + S::kDOff);   // [2][H]
   cf* tw_s = reinterpret_cast<cf*>(dbuf + 2 * H);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tw_s + H);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tw_s + L::T * L::kTwPitch);
   const uint32_t bar_x = smem_u32(&bars[0]);    // x tile (+ D row) landed
   const uint32_t bar_a = smem_u32(&bars[1]);    // addend tile landed
   const uint32_t bar_ae = smem_u32(&bars[2]);   // addend tile consumed by all NT threads

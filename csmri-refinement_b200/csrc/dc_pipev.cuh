@@ -62,7 +62,7 @@ __global__ void __launch_bounds__((CW / 2) * (H / E), MINB)
   float* abuf = xbuf + S::kTileFloats;                                // absent when !ADD
   float* dbuf = xbuf + (ADD ? 2 : 1) * S::kTileFloats;                // [2][H]
   cf* tw_s = reinterpret_cast<cf*>(dbuf + 2 * H);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tw_s + H);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tw_s + L::Base::T * L::Base::kTwPitch);
   const uint32_t bar_x = smem_u32(&bars[0]);
   const uint32_t bar_a = smem_u32(&bars[1]);
   const uint32_t bar_ae = smem_u32(&bars[2]);

@@ -23,7 +23,7 @@ static double check(bool inv_first) {
   typedef LineFFT<N, E, CW> L;
   constexpr int T = L::T;
   std::vector<cf> sm(L::kSmemBytes / sizeof(cf));
-  std::vector<float4> tw4(N / 2);
+  std::vector<float4> tw4(L::kTwBytes / sizeof(float4));
   cf* tw = reinterpret_cast<cf*>(tw4.data());
   for (int t = 0; t < T; ++t) L::fill_twiddles(tw, t, T);
   std::vector<std::vector<cf>> regs(T * CW, std::vector<cf>(E));
@@ -91,7 +91,7 @@ static double check_v2() {
   typedef LineFFT<N, E, LW> B;
   constexpr int T = L::T;
   std::vector<float4> sm(N * LW);
-  std::vector<float4> tw4(N / 2);
+  std::vector<float4> tw4(B::kTwBytes / sizeof(float4));
   cf* tw = reinterpret_cast<cf*>(tw4.data());
   for (int t = 0; t < T; ++t) B::fill_twiddles(tw, t, T);
   std::vector<std::vector<cf2>> regs(T * LW, std::vector<cf2>(E));

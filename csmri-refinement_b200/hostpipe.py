@@ -28,10 +28,17 @@ of the line table is verified the same way and a violation raises.
 """
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 class HostDCPipeline(object):
+    """``chunk`` slices per pipeline step, ``depth`` chunk buffers in flight.
+    Everything a chunk needs on the device - staging inputs, the plan (D table,
+    addend), both results, the verification flag - is allocated once per
+    (shape, input form) and the kernels are enqueued through the raw C ABI: the
+    per-chunk host cost is a handful of asynchronous calls, so small chunks
+    (short pipeline fill / drain) do not turn the step host-bound."""
+
     def __init__(self, device, chunk=32, depth=3, noise_lvl=None):
         self.device = torch.device(device)
         self.chunk = int(chunk)
@@ -42,16 +49,21 @@ class HostDCPipeline(object):
         self.s_out = torch.cuda.Stream(self.device)
         self._bufs = {}
 
-    def _buffers(self, tag, shapes):
-        """``depth`` sets of device staging buffers, one per name in ``shapes``
-        ({name: (per-slice shape, dtype)})."""
-        key = (tag,) + tuple(sorted((k, tuple(v[0]), v[1]) for k, v in shapes.items()))
+    def _buffers(self, tag, shapes, n_chunks):
+        """``depth`` sets of device buffers, one tensor per name in ``shapes``
+        ({name: (per-slice shape, dtype)}), plus one flag per chunk."""
+        key = (tag, n_chunks) + tuple(sorted((k, tuple(v[0]), v[1]) for k, v in shapes.items()))
         bufs = self._bufs.get(tag)
         if bufs is None or bufs[0] != key:
-            sets = [{k: torch.empty((self.chunk,) + tuple(shp), dtype=dt, device=self.device)
-                     for k, (shp, dt) in shapes.items()} for _ in range(self.depth)]
-            bufs = self._bufs[tag] = (key, sets)
-        return bufs[1]
+            sets = []
+            for _ in range(self.depth):
+                d = {k: torch.empty((self.chunk,) + tuple(shp), dtype=dt, device=self.device)
+                     for k, (shp, dt) in shapes.items()}
+                d['e_in'], d['e_run'], d['e_out'] = (torch.cuda.Event() for _ in range(3))
+                sets.append(d)
+            flags = torch.ones((n_chunks,), dtype=torch.int32, device=self.device)
+            bufs = self._bufs[tag] = (key, sets, flags)
+        return bufs[1], bufs[2]
 
     @staticmethod
     def _check_pinned(*tensors):
@@ -59,42 +71,43 @@ class HostDCPipeline(object):
             if t.device.type != 'cpu' or not t.is_pinned():
                 raise ValueError('HostDCPipeline needs pinned host tensors')
 
-    def _run(self, B, bufs, host_in, prepare, h_out, h_gx):
+    def _run(self, B, H, W, bufs, flags, host_in, prepare, h_out, h_gx):
         """Common three-stream loop.  ``host_in``: {name: pinned host tensor};
-        ``prepare(buf, n)`` -> (dtab, addend, flag) on the compute stream."""
+        ``prepare(buf, n, flag_ptr, stream)`` enqueues the plan kernels of a chunk."""
+        lib = _lib.lib()
         cur = torch.cuda.current_stream(self.device)
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(cur)
-        flags, done = [], [None] * self.depth
+        run = self.s_run.cuda_stream
         n_chunks = (B + self.chunk - 1) // self.chunk
-        for c in range(n_chunks):
-            lo, hi = c * self.chunk, min(B, (c + 1) * self.chunk)
-            n = hi - lo
-            buf = bufs[c % self.depth]
-            with torch.cuda.stream(self.s_in):
-                if done[c % self.depth] is not None:      # buffer still feeding an older chunk
-                    self.s_in.wait_event(done[c % self.depth])
-                for k, h in host_in.items():
-                    buf[k][:n].copy_(h[lo:hi], non_blocking=True)
-                e_in = torch.cuda.Event()
-                e_in.record(self.s_in)
+        with torch.cuda.device(self.device):
+            for c in range(n_chunks):
+                lo, hi = c * self.chunk, min(B, (c + 1) * self.chunk)
+                n = hi - lo
+                buf = bufs[c % self.depth]
+                with torch.cuda.stream(self.s_in):
+                    if c >= self.depth:          # inputs of the chunk that used this set are consumed
+                        self.s_in.wait_event(buf['e_run'])
+                    for k, h in host_in.items():
+                        buf[k][:n].copy_(h[lo:hi], non_blocking=True)
+                    buf['e_in'].record(self.s_in)
+                self.s_run.wait_event(buf['e_in'])
+                if c >= self.depth:              # results of that chunk have left the device
+                    self.s_run.wait_event(buf['e_out'])
+                prepare(buf, n, flags[c:c + 1].data_ptr(), run)
+                _lib.check(lib.csmri_dc_forward_cartesian(
+                    buf['x'].data_ptr(), None, buf['dtab'].data_ptr(), buf['addend'].data_ptr(),
+                    buf['out'].data_ptr(), n, H, W, run))
+                _lib.check(lib.csmri_dc_adjoint_cartesian(
+                    buf['g'].data_ptr(), buf['dtab'].data_ptr(), buf['gx'].data_ptr(), n, H, W, run))
+                buf['e_run'].record(self.s_run)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(buf['e_run'])
+                    h_out[lo:hi].copy_(buf['out'][:n], non_blocking=True)
+                    h_gx[lo:hi].copy_(buf['gx'][:n], non_blocking=True)
+                    buf['e_out'].record(self.s_out)
             with torch.cuda.stream(self.s_run):
-                self.s_run.wait_event(e_in)
-                dtab, addend, flag = prepare(buf, n)
-                out = ops.dc_cartesian(buf['x'][:n], None, dtab, addend)
-                gx = ops.dc_cartesian(buf['g'][:n], None, dtab, None)
-                flags.append(flag)
-                e_run = torch.cuda.Event()
-                e_run.record(self.s_run)
-                done[c % self.depth] = e_run
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(e_run)
-                h_out[lo:hi].copy_(out, non_blocking=True)
-                h_gx[lo:hi].copy_(gx, non_blocking=True)
-                out.record_stream(self.s_out)
-                gx.record_stream(self.s_out)
-        with torch.cuda.stream(self.s_run):
-            ok = torch.stack(flags).min()
+                ok = flags[:n_chunks].min()
         cur.wait_stream(self.s_out)
         cur.wait_stream(self.s_run)
         self.s_out.synchronize()
@@ -105,17 +118,23 @@ class HostDCPipeline(object):
         (B,2,H,W); results are written into the pinned ``h_out`` / ``h_gx``.
         Returns after all copies have completed."""
         self._check_pinned(hx, hk0, hmask, hgrad, h_out, h_gx)
-        B = hx.shape[0]
+        B, _, H, W = hx.shape
         per = tuple(hx.shape[1:])
         f32 = torch.float32
-        bufs = self._buffers('dense', {'x': (per, f32), 'k0': (per, f32), 'mask': (per, f32),
-                                       'g': (per, f32)})
+        n_chunks = (B + self.chunk - 1) // self.chunk
+        bufs, flags = self._buffers('dense', {
+            'x': (per, f32), 'k0': (per, f32), 'mask': (per, f32), 'g': (per, f32),
+            'addend': (per, f32), 'out': (per, f32), 'gx': (per, f32), 'dtab': ((H,), f32)},
+            n_chunks)
+        lib = _lib.lib()
 
-        def prepare(buf, n):
-            return ops.dc_prepare(buf['k0'][:n], buf['mask'][:n], self.noise_lvl)
+        def prepare(buf, n, flag_ptr, stream):
+            _lib.check(lib.csmri_dc_prepare(
+                buf['k0'].data_ptr(), buf['mask'].data_ptr(), n, H, W, self.noise_lvl,
+                buf['dtab'].data_ptr(), buf['addend'].data_ptr(), flag_ptr, None, stream))
 
-        ok = self._run(B, bufs, {'x': hx, 'k0': hk0, 'mask': hmask, 'g': hgrad}, prepare,
-                       h_out, h_gx)
+        ok = self._run(B, H, W, bufs, flags, {'x': hx, 'k0': hk0, 'mask': hmask, 'g': hgrad},
+                       prepare, h_out, h_gx)
         if not ok:
             # some chunk's mask was not row-constant: redo through the general path
             self._general(hx, hk0, hmask, hgrad, h_out, h_gx)
@@ -130,22 +149,28 @@ class HostDCPipeline(object):
         if hrows.shape != (B, H) or hrows.dtype != torch.uint8:
             raise ValueError('rows must be a uint8 (B,H) tensor')
         if hk0_lines.dim() != 4 or hk0_lines.shape[0] != B or hk0_lines.shape[1] != 2 or \
-                hk0_lines.shape[3] != W:
-            raise ValueError('k0_lines must be (B,2,L,W)')
+                hk0_lines.shape[3] != W or hk0_lines.dtype != torch.float32:
+            raise ValueError('k0_lines must be a float32 (B,2,L,W) tensor')
+        L = int(hk0_lines.shape[2])
         per = tuple(hx.shape[1:])
         f32 = torch.float32
-        bufs = self._buffers('lines', {'x': (per, f32), 'g': (per, f32),
-                                       'k0l': (tuple(hk0_lines.shape[1:]), f32),
-                                       'rows': ((H,), torch.uint8)})
+        n_chunks = (B + self.chunk - 1) // self.chunk
+        bufs, flags = self._buffers('lines', {
+            'x': (per, f32), 'g': (per, f32), 'k0l': ((2, L, W), f32), 'rows': ((H,), torch.uint8),
+            'addend': (per, f32), 'out': (per, f32), 'gx': (per, f32), 'dtab': ((H,), f32)},
+            n_chunks)
+        lib = _lib.lib()
 
-        def prepare(buf, n):
-            return ops.dc_prepare_lines(buf['k0l'][:n], buf['rows'][:n], self.noise_lvl, W)
+        def prepare(buf, n, flag_ptr, stream):
+            _lib.check(lib.csmri_dc_prepare_lines(
+                buf['k0l'].data_ptr(), buf['rows'].data_ptr(), n, H, W, L, self.noise_lvl,
+                buf['dtab'].data_ptr(), buf['addend'].data_ptr(), flag_ptr, stream))
 
-        ok = self._run(B, bufs, {'x': hx, 'k0l': hk0_lines, 'rows': hrows, 'g': hgrad}, prepare,
-                       h_out, h_gx)
+        ok = self._run(B, H, W, bufs, flags, {'x': hx, 'k0l': hk0_lines, 'rows': hrows, 'g': hgrad},
+                       prepare, h_out, h_gx)
         if not ok:
             raise ValueError('rows / k0_lines are inconsistent: every slice must have exactly '
-                             '%d sampled rows' % hk0_lines.shape[2])
+                             '%d sampled rows' % L)
 
     def _general(self, hx, hk0, hmask, hgrad, h_out, h_gx):
         B = hx.shape[0]

@@ -95,7 +95,12 @@ class _Assumption(object):
     def violations(self):
         if not self.flags:
             return None
-        return (1 - torch.stack([f.reshape(()) for f in self.flags])).sum()
+        seen, uniq = set(), []
+        for f in self.flags:            # every DC layer of a cascade reports the same plan
+            if id(f) not in seen:
+                seen.add(id(f))
+                uniq.append(f.reshape(()))
+        return (1 - torch.stack(uniq)).sum()
 
 
 @contextlib.contextmanager

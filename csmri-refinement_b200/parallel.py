@@ -116,8 +116,9 @@ class ShardedTrainer(object):
     ``assume_row_constant=True`` (required under a CUDA graph, where the
     per-batch device->host read of the mask proof is illegal) is *verified*: the
     proof is still computed on the device inside the step, accumulated into a
-    sticky counter and copied to pinned host memory asynchronously; the next
-    ``step()`` raises if any earlier batch had a mask that is not row-constant.
+    sticky counter and copied to pinned host memory asynchronously; ``step()``
+    raises as soon as it sees the counter non-zero - at the latest in the call
+    after the offending batch.
     """
 
     def __init__(self, model, lr=2e-4, betas=(0.9, 0.999), cuda_graph=False,

@@ -376,6 +376,10 @@ def bench_leg(dev, rank, world, steps=4, warmup=2):
     ``batch_size`` (5) slices of 512x512 per GPU (weak scaling)."""
     conf = harness.load_config(harness.config_path('2-refinement.json'))
     b = int(conf.batch_size)
+    # U-Net / discriminator / VGG19 are not parity-gated: torch's stock convolution
+    # setting (TF32 tensor cores); the frozen RecNet path stays fp32 (RefinementWrapper.forward)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
     batches = [harness.synthetic_batch(conf, b, dev, seed=2000 + 16 * rank + i) for i in range(2)]
     res = {}
     for mode in (('overlapped', True),) + ((('serial', False),) if world > 1 else ()):
@@ -427,6 +431,7 @@ def bench_leg(dev, rank, world, steps=4, warmup=2):
                   'discriminator (27,941,697 params), losses 0.5*gan + FeatureMatching + 10*VGG19 + '
                   '2*FeaturePenalty, Adam(2e-4, beta1 0.5) x2, batch %d/GPU of 512x512, 8x Cartesian; '
                   'synthetic data, discriminator name defaulted, RecNet and VGG19 weights are '
-                  'seeded random (checkpoint / ImageNet weights do not exist offline: SURVEY D6); '
+                  'seeded random (checkpoint / ImageNet weights do not exist offline: SURVEY D6); U-Net / '
+                  'discriminator / VGG19 convolutions with torch\'s stock TF32 setting, RecNet path fp32; '
                   'discriminator gradients all-reduced in %d chunks overlapped with backward'
                   % (b, len(trainer.disc_bucket.chunks))}
