@@ -140,8 +140,15 @@ __device__ __forceinline__ void wg_compute(const float* X_s, const float* D_s,
 // double-buffered variant with two CTAs per SM measured the same).
 // COT = output channels per thread: 4 (256 threads, 36 accumulators) or
 // 8 (128 threads, 72 accumulators, half the shared-memory loads per FFMA2).
+// Accumulation is two-level: a tile's 128 products per weight go into fresh
+// registers, the tile sums into a second register set.  With one running sum per
+// weight over all ~10^3 pixels of a CTA the fp32 rounding error of the strongly
+// cancelling sum reached 1.8e-5 of |dW| at 512^2 (tests: 1-recnet.json against a
+// float64 evaluation); the error of a two-level sum grows with sqrt(128 * tiles)
+// instead of sqrt(128 * tiles^2 / 2).  The second set costs 9 * COT registers,
+// hence three instead of four resident CTAs for COT = 8.
 template <int COT>
-__global__ void __launch_bounds__(32 * (kWgC / COT), 4)
+__global__ void __launch_bounds__(32 * (kWgC / COT), COT == 8 ? 3 : 2)
     conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                          float* __restrict__ partial, int CI, int CO, int H, int W, int HI, int WI,
                          int pad, int tiles_x, int tiles_y, int ntiles) {
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(32 * (kWgC / COT), 4)
   const int warp = threadIdx.x >> 5;        // group of COT output channels
   const int co0 = blockIdx.y * kWgC, ci0 = blockIdx.z * kWgC;
 
-  cf acc[9][COT / 2];
+  cf acc[9][COT / 2];   // sum over the CTA's tiles of the per-tile sums
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
@@ -162,9 +169,18 @@ __global__ void __launch_bounds__(32 * (kWgC / COT), 4)
     __syncthreads();   // everyone is done with the previous tile
     wg_stage<kWgC / COT>(X_s, D_s, x, dy, tile, tiles_x, tiles_y, CI, CO, ci0, co0, H, W, HI, WI,
                          pad, lane, warp);
+    cf tacc[9][COT / 2];   // this tile
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int o = 0; o < COT / 2; ++o) tacc[t][o] = mk(0.0f, 0.0f);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    wg_compute<COT>(X_s, D_s, acc, lane, warp);
+    wg_compute<COT>(X_s, D_s, tacc, lane, warp);
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int o = 0; o < COT / 2; ++o) acc[t][o] = f2add(acc[t][o], tacc[t][o]);
   }
   // partial block in dW order: [co][ci][tap]
   float* dst = partial +

@@ -1580,7 +1580,7 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
   const long long ntiles_ll = (long long)N * tiles_x * tiles_y;
   if (ntiles_ll > 0x7fffffffLL) return fail(CSMRI_E_SHAPE, "too many tiles");
   const int ntiles = (int)ntiles_ll;
-  int cap = sm_count() * 4;
+  int cap = sm_count() * (g_wgrad_cot == 8 ? 3 : 2);   // resident CTAs per SM (conv_wgrad.cuh)
   if (cap > kWgMaxCtas) cap = kWgMaxCtas;
   int parts = wgrad_parts(CI, CO, cap);
   if (parts > ntiles) parts = ntiles;

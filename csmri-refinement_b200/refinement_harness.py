@@ -303,7 +303,7 @@ class AdversarialTrainer(object):
     322-389) for the loss set of the shipped config, on this rank's batch."""
 
     def __init__(self, conf, device, rank=0, overlap=True, vgg_seed=1234, dc_factory=None,
-                 chunk_bytes=16 << 20):
+                 chunk_bytes=16 << 20, channels_last=False):
         self.conf, self.device = conf, device
         harness.set_random_seeds(conf.seed)            # identical replicas on every rank
         self.gen = build_generator(conf, dc_factory).to(device)
@@ -317,6 +317,12 @@ class AdversarialTrainer(object):
             else:
                 p.data.zero_()
         self.vgg = self.vgg.to(device).eval()
+        if channels_last:
+            # library-side layout choice for the cuDNN models only (the RecNet path and every
+            # kernel of libcsmri_dc stay NCHW planar): saves cuDNN's per-layer NCHW<->NHWC
+            # transposes around its tensor-core kernels
+            for m in (self.gen.learnable_model, self.disc, self.vgg):
+                m.to(memory_format=torch.channels_last)
         random.seed(conf.seed * 1000 + rank)           # image pool draws: per rank
         dconf = Configuration.from_dict(conf.discriminator_model, conf)
         pool = dconf.get_attr('image_pool_size', default=5 * conf.batch_size) \
@@ -383,7 +389,7 @@ def bench_leg(dev, rank, world, steps=4, warmup=2):
     batches = [harness.synthetic_batch(conf, b, dev, seed=2000 + 16 * rank + i) for i in range(2)]
     res = {}
     for mode in (('overlapped', True),) + ((('serial', False),) if world > 1 else ()):
-        trainer = AdversarialTrainer(conf, dev, rank, overlap=mode[1])
+        trainer = AdversarialTrainer(conf, dev, rank, overlap=mode[1], channels_last=True)
         for i in range(warmup):
             trainer.step(batches[i % 2])
         torch.cuda.synchronize()

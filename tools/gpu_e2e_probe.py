@@ -1,4 +1,6 @@
-"""HostDCPipeline chunk-size sweep (context probe for the e2e number)."""
+"""HostDCPipeline sweep (context probe for the e2e number): chunk size, buffers in
+flight, copy streams per direction, with and without CUDA-graph replay, for the
+compact (line table + sampled k0 lines) and the dense input form."""
 import os
 import sys
 
@@ -17,8 +19,11 @@ batch = undersampling.undersample(img, rows)
 hx = torch.randn(B, 2, n, n).pin_memory()
 hg = torch.randn(B, 2, n, n).pin_memory()
 hk0, hm = batch['kspace'].cpu().pin_memory(), batch['mask'].cpu().pin_memory()
+hrows = torch.from_numpy(rows).pin_memory()
+hk0l = undersampling.compact_lines(batch['kspace'], hrows.to(dev)).cpu().pin_memory()
 ho, hgx = torch.empty_like(hx).pin_memory(), torch.empty_like(hx).pin_memory()
-# raw PCIe reference points
+prop = torch.cuda.get_device_properties(dev)
+print('async engines:', getattr(prop, 'async_engine_count', '?'))
 d = torch.empty_like(hx, device=dev)
 for name, fn in (('H2D 128MiB', lambda: d.copy_(hx, non_blocking=True)),
                  ('D2H 128MiB', lambda: ho.copy_(d, non_blocking=True))):
@@ -29,16 +34,23 @@ for name, fn in (('H2D 128MiB', lambda: d.copy_(hx, non_blocking=True)),
         fn()
     b.record(); torch.cuda.synchronize()
     print(name, '%.1f GB/s' % (5 * hx.numel() * 4 / a.elapsed_time(b) / 1e6))
-for chunk, depth in ((16, 3), (32, 3), (64, 3), (128, 2), (64, 4)):
-    pipe = hostpipe.HostDCPipeline(dev, chunk=chunk, depth=depth)
-    for _ in range(2):
-        pipe.forward_backward(hx, hk0, hm, hg, ho, hgx)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(5):
-        pipe.forward_backward(hx, hk0, hm, hg, ho, hgx)
-    b.record(); torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 5
-    print('chunk %d depth %d: %.2f ms/step  %.0f slices/s  H2D %.1f GB/s' % (
-        chunk, depth, ms, B / ms * 1e3, 4 * hx.numel() * 4 / ms / 1e6))
+for chunk, depth, cs, graph in ((64, 3, 1, True), (32, 3, 1, True), (16, 4, 1, True), (64, 3, 2, True),
+                                (32, 4, 2, True), (16, 4, 2, True), (32, 4, 2, False), (8, 6, 2, True)):
+    pipe = hostpipe.HostDCPipeline(dev, chunk=chunk, depth=depth, copy_streams=cs, use_graph=graph)
+    res = []
+    for form in ('lines', 'dense'):
+        if form == 'lines':
+            call = lambda: pipe.forward_backward_lines(hx, hk0l, hrows, hg, ho, hgx)   # noqa: E731
+        else:
+            call = lambda: pipe.forward_backward(hx, hk0, hm, hg, ho, hgx)             # noqa: E731
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            call()
+        b.record(); torch.cuda.synchronize()
+        res.append(a.elapsed_time(b) / 5)
+    print('chunk %3d depth %d copy_streams %d graph %d: lines %.2f ms (%.0f slices/s)  dense %.2f ms' % (
+        chunk, depth, cs, graph, res[0], B / res[0] * 1e3, res[1]))

@@ -18,7 +18,7 @@ torch.backends.cuda.matmul.allow_tf32 = tf32
 torch.backends.cudnn.benchmark = True
 dev = torch.device('cuda:0')
 conf = harness.load_config(harness.config_path('2-refinement.json'))
-tr = rh.AdversarialTrainer(conf, dev)
+tr = rh.AdversarialTrainer(conf, dev, channels_last=os.environ.get('REFINE_CL', '0') == '1')
 batch = harness.synthetic_batch(conf, int(conf.batch_size), dev, seed=1)
 for _ in range(3):
     tr.step(batch)
@@ -29,7 +29,7 @@ for _ in range(3):
     tr.step(batch)
 b.record()
 torch.cuda.synchronize()
-print('tf32=%d  step %.2f ms (CUDA events, 3 steps)' % (tf32, a.elapsed_time(b) / 3))
+print('tf32=%d channels_last=%s  step %.2f ms (CUDA events, 3 steps)' % (tf32, os.environ.get('REFINE_CL', '0'), a.elapsed_time(b) / 3))
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(2):
         tr.step(batch)
