@@ -556,7 +556,7 @@ def main():
         barrier()
         return rank_stats(a.elapsed_time(b) / e2e_steps, dev, world)
 
-    pipe = hostpipe.HostDCPipeline(dev, chunk=16, depth=4)   # raw-ABI pipeline: small chunks are cheap
+    pipe = hostpipe.HostDCPipeline(dev, chunk=32, depth=3)   # best of tools/gpu_e2e_probe.py
     h2d_lines = 2 * tensor_bytes + hk0l.numel() * 4 + hrows.numel()
     d2h = 2 * tensor_bytes
     ms_lines, st_lines = timed_e2e(
@@ -594,7 +594,8 @@ def main():
            'frac_of_copy_floor': ms_copy / ms_lines,
            'api': 'hostpipe.HostDCPipeline.forward_backward_lines: pinned host x / grad-seed / '
                   'sampled k0 lines (B,2,L,W) / line table (B,H) uint8 in, out / grad_x back to '
-                  'pinned host, 16-slice chunks on 3 streams; includes the per-chunk '
+                  'pinned host, 32-slice chunks on 3 streams, the whole schedule replayed as one CUDA '
+                  'graph; includes the per-chunk '
                   'csmri_dc_prepare_lines and the consistency read. copies_only = the same '
                   'bytes moved with no kernel in between (the PCIe floor of this step)',
            'dense_interface': {
