@@ -94,6 +94,8 @@ _SIGNATURES = {
                             [ctypes.c_void_p]),
     'csmri_conv3x3_thin': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 5 +
                            [ctypes.c_float, ctypes.c_void_p]),
+    'csmri_conv3x3_tc': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 4 +
+                         [ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
     'csmri_bias_lrelu': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_int] * 4 +
                          [ctypes.c_float, ctypes.c_void_p]),
     'csmri_bias_lrelu_backward': (ctypes.c_int, [_c_float_p] * 5 + [ctypes.c_int] * 4 +

@@ -16,6 +16,7 @@ from torch import nn
 from . import _lib
 
 _ENABLED = True
+_TC_ENABLED = True
 # experimental: weight gradient on a side stream, concurrently with the data gradient
 import os as _os
 _WGRAD_STREAM = _os.environ.get('CSMRI_WGRAD_STREAM', '0') == '1'
@@ -27,6 +28,13 @@ def _side_stream(device):
     if s is None:
         s = _SIDE_STREAMS[device.index] = torch.cuda.Stream(device)
     return s
+
+
+def set_tensor_core_conv(flag):
+    """Switch the tcgen05 forward / data-gradient kernel of the 32 -> 32 layers on / off
+    (off = cuDNN's fp32 kernels; A/B timing, tests)."""
+    global _TC_ENABLED
+    _TC_ENABLED = bool(flag)
 
 
 def set_fast_wgrad(flag):
@@ -127,6 +135,29 @@ def conv3x3_thin(x, weight, bias, slope=0.0):
     return y
 
 
+def conv3x3_tc(x, weight, bias, slope=0.0, transpose_flip=False):
+    """RecNet's 32 -> 32 layers (zero padding 1) through ``csmri_conv3x3_tc``
+    (tcgen05 tensor cores, error-compensated TF32 split, fp32 accumulation):
+    act(conv(x, weight) + bias); ``transpose_flip`` gives the data gradient of
+    the same layer from the same weight tensor."""
+    _require_cuda_f32(x, weight, bias)
+    x, weight = x.contiguous(), weight.contiguous()
+    n, c, h, w = x.shape
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x)
+        _lib.check(_lib.lib().csmri_conv3x3_tc(
+            x.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
+            y.data_ptr(), n, c, h, w, float(slope), int(bool(transpose_flip)),
+            torch.cuda.current_stream().cuda_stream))
+    return y
+
+
+def _is_tc(x, weight, pad):
+    """Shapes csmri_conv3x3_tc covers: 32 -> 32 channels, padding 1, H % 16 == 0, W % 128 == 0."""
+    return (_TC_ENABLED and pad == 1 and tuple(weight.shape[:2]) == (32, 32) and
+            x.shape[2] % 16 == 0 and x.shape[3] % 128 == 0)
+
+
 def _is_thin(weight, pad):
     return pad == 1 and (weight.shape[1], weight.shape[0]) in ((2, 32), (32, 2))
 
@@ -141,8 +172,11 @@ class _Conv3x3(torch.autograd.Function):
         ctx.pad, ctx.slope = pad, slope
         ctx.has_bias = bias is not None
         ctx.thin = _is_thin(weight, pad) and (slope is None or weight.shape[1] == 2)
+        ctx.tc = _is_tc(x, weight, pad)
         if ctx.thin:
             y = conv3x3_thin(x, weight, bias, slope or 0.0)
+        elif ctx.tc:
+            y = conv3x3_tc(x, weight, bias, slope or 0.0)
         elif slope is None:
             y = torch.ops.aten.convolution(x, weight, bias, [1, 1], [pad, pad], [1, 1], False,
                                            [0, 0], 1)
@@ -184,6 +218,11 @@ class _Conv3x3(torch.autograd.Function):
                 gb = grad_out.sum(dim=(0, 2, 3))
             if need_x:     # the same kernel family on flipped, transposed weights
                 gx = conv3x3_thin(grad_out, weight.flip(2, 3).transpose(0, 1), None, 0.0)
+        elif ctx.tc:
+            if need_b and gb is None:
+                gb = grad_out.sum(dim=(0, 2, 3))
+            if need_x:     # the same kernel with the operator transposed and mirrored
+                gx = conv3x3_tc(grad_out, weight, None, 0.0, transpose_flip=True)
         elif ctx.slope is None:
             if need_x or need_b:
                 gx, _, gb = torch.ops.aten.convolution_backward(
@@ -222,6 +261,8 @@ class Conv2d(nn.Conv2d):
             # inference: same kernels, nothing saved
             if _is_thin(self.weight, pad) and (slope is None or self.weight.shape[1] == 2):
                 return conv3x3_thin(x, self.weight, self.bias, slope or 0.0)
+            if _is_tc(x, self.weight, pad):
+                return conv3x3_tc(x, self.weight, self.bias, slope or 0.0)
             if slope is not None:
                 y = torch.ops.aten.convolution(x, self.weight, None, [1, 1], [pad, pad], [1, 1],
                                                False, [0, 0], 1)

@@ -49,6 +49,7 @@
 #include "conv_wgrad.cuh"
 #include "conv_epilogue.cuh"
 #include "conv_thin.cuh"
+#include "conv_tc.cuh"
 
 namespace csmri {
 
@@ -732,6 +733,7 @@ static unsigned g_sched_victim = 0;
 static int g_use_pdl = 1;             // programmatic dependent launch for the strip kernels
 static int g_wgrad_cot = 8;      // output channels per thread of conv3x3_wgrad_kernel (8; 4 = A/B baseline)
 static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_set_tuning
+static int g_tc_debug = 0;       // conv3x3_tc_kernel probe bits (tuning key 6)
 static long long* g_trace = nullptr;  // tuning probe: per-CTA timeline buffers (2 x 1024 x 40)
 static int g_trace_launch = 0;
 
@@ -1213,6 +1215,7 @@ int csmri_set_tuning(int key, int value) {
   if (key == 0) g_strip_variant = value;
   else if (key == 4) g_use_pdl = value;
   else if (key == 5) g_wgrad_cot = value == 8 ? 8 : 4;
+  else if (key == 6) g_tc_debug = value & 7;
   else return fail(CSMRI_E_ARG, "unknown tuning key %d", key);
   return CSMRI_OK;
 }
@@ -1666,6 +1669,29 @@ int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float*
     conv3x3_thin_in_kernel<<<ctas, 256, kThinInSmem, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
                                                           (int)ntiles_ll);
   }
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+// ---- 32 -> 32 convolution on the tensor cores, 3xTF32 (conv_tc.cuh) -------------
+int csmri_conv3x3_tc(const float* x, const float* w, const float* bias, float* y, int N, int C,
+                     int H, int W, float slope, int transpose_flip, void* stream) {
+  if (C != kTcC) return fail(CSMRI_E_SHAPE, "conv3x3_tc handles %d -> %d channels (got %d)", kTcC, kTcC, C);
+  if (N <= 0 || H <= 0 || W <= 0 || H % kTcRowBlock != 0 || W % kTcM != 0)
+    return fail(CSMRI_E_SHAPE, "conv3x3_tc needs H %% %d == 0 and W %% %d == 0 (got %dx%dx%d)",
+                kTcRowBlock, kTcM, N, H, W);
+  if (!(slope >= 0.0f)) return fail(CSMRI_E_ARG, "slope must be >= 0 (got %g)", slope);
+  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr(w, "w"));
+  CSMRI_TRY(check_ptr(y, "y"));
+  if (x == y) return fail(CSMRI_E_ARG, "y must not alias x");
+  const long long nitems_ll = (long long)N * (W / kTcM) * (H / kTcRowBlock);
+  if (nitems_ll > 0x7fffffffLL) return fail(CSMRI_E_SHAPE, "too many tiles");
+  CSMRI_TRY(set_smem(conv3x3_tc_kernel, kTcSmemBytes));
+  int grid = sm_count();
+  if (grid > nitems_ll) grid = (int)nitems_ll;
+  conv3x3_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(
+      x, w, bias, y, H, W, (int)nitems_ll, slope, transpose_flip != 0, g_tc_debug);
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
 }

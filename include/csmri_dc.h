@@ -246,6 +246,20 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
 int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float* y,
                        int N, int A, int B, int H, int W, float slope, void* stream);
 
+/* RecNet's 32 -> 32 channel 3x3 convolutions (the inner layers of every ConvBlock,
+ * models/recnet.py:37-44), stride 1, zero padding 1, on the tcgen05 tensor cores
+ * with an error-compensated TF32 split (fp32-level accuracy, fp32 accumulation in
+ * tensor memory):  y = act(conv(x, wq) + bias)
+ *   x (N,32,H,W), w (32,32,3,3), bias (32) or NULL, y (N,32,H,W), y must not alias x;
+ *   slope > 0 applies LeakyReLU, slope = 0 none;
+ *   transpose_flip = 0: wq = w (what nn.Conv2d.forward computes);
+ *   transpose_flip = 1: wq[co][ci][ky][kx] = w[ci][co][2-ky][2-kx], i.e. the data
+ *   gradient of the same layer (what autograd computes for its input).
+ * H % 16 == 0, W % 128 == 0; anything else is CSMRI_E_SHAPE (the caller keeps its
+ * own convolution backend for those shapes). */
+int csmri_conv3x3_tc(const float* x, const float* w, const float* bias, float* y,
+                     int N, int C, int H, int W, float slope, int transpose_flip, void* stream);
+
 /* Bias + LeakyReLU after a convolution (models/recnet.py:45-48: Conv2d(bias=True)
  * followed by nn.LeakyReLU(relu_leakiness, inplace=True)), fused into one pass:
  *   csmri_bias_lrelu:           z (N,C,H,W) <- lrelu(z + bias[c]), in place

