@@ -1,0 +1,254 @@
+// Second tcgen05 unit probe (kind::tf32): the facts the tensor-core weight gradient and the
+// TMEM-operand convolution are built on, each checked against exact small-integer references:
+//   1. A operand read from TENSOR MEMORY (lane = row m, 32-bit column = k), written there with
+//      tcgen05.st.32x32b; B from shared memory (no-swizzle K-major canonical), N = 32;
+//   2. B in the 128-byte-swizzled K-major layout a TMA box {32 floats x rows} produces
+//      (16-byte chunk c of row r stored at chunk c ^ (r % 8)), N = 96, K advanced by +32 bytes;
+//   3. what the tensor core does with the 13 low mantissa bits of an fp32 container
+//      (truncate or round), for both operand sources;
+//   4. cycles per MMA for the shapes under consideration (TS N=32/64/96/128, SS N=32/64).
+// nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/umma_probe2 tools/umma_probe2.cu
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <cuda_runtime.h>
+
+constexpr int M = 128, K = 32, NMAX = 128;
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0;"
+               " tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p; }" ::"r"(d),
+               "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+               : "memory");
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0;"
+               " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p; }" ::"r"(d),
+               "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+               : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+#define TMEM_LD32(v, addr)                                                                                      \
+  asm volatile(                                                                                                 \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, " \
+      "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"             \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),          \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),    \
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),  \
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])   \
+      : "r"(addr))
+#define TMEM_ST32(addr, v)                                                                                      \
+  asm volatile(                                                                                                 \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "   \
+      "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(   \
+          addr),                                                                                                \
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),         \
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), \
+      "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]),            \
+      "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])                                     \
+      : "memory")
+
+// mode 0: A in TMEM, B no-swizzle N = 32.   mode 1: A in TMEM, B 128B-swizzled, N = n (<= 128).
+// mode 2: A in smem (no swizzle), B 128B-swizzled N = n.
+// a: (128 x 32) row major, b: (n x 32) row major, out: (128 x n)
+__global__ void __launch_bounds__(128) probe(const float* __restrict__ a, const float* __restrict__ b,
+                                             float* __restrict__ out, int mode, int n) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  float* B_sw = reinterpret_cast<float*>(smem);                  // [n rows][32 floats], swizzled: 16 KiB max
+  float* B_ns = reinterpret_cast<float*>(smem + 16384);          // [k/4][n][4]: 16 KiB max
+  float* A_ns = reinterpret_cast<float*>(smem + 32768);          // [k/4][128][4]: 16 KiB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 49152);
+  uint32_t* tmem_base = reinterpret_cast<uint32_t*>(smem + 49152 + 16);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < n * K; i += 128) {
+    const int r = i / K, k = i % K;
+    B_ns[((k / 4) * n + r) * 4 + (k % 4)] = b[i];
+    const int chunk = (k / 4) ^ (r % 8);
+    B_sw[r * 32 + chunk * 4 + (k % 4)] = b[i];
+  }
+  for (int i = tid; i < M * K; i += 128) { const int m = i / K, k = i % K; A_ns[((k / 4) * M + m) * 4 + (k % 4)] = a[i]; }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(s32(tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_base;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const uint32_t a_col = 128;                                    // A lives in TMEM columns 128 .. 159
+  {
+    uint32_t v[32];
+    for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(a[tid * K + k]);
+    TMEM_ST32(tmem + lane_base + a_col, v);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(n);
+    for (int ks = 0; ks < K / 8; ++ks) {
+      const uint64_t db_ns = make_desc(s32(B_ns) + 2 * ks * n * 16, n * 16, 128, 0);
+      const uint64_t db_sw = make_desc(s32(B_sw) + ks * 32, 16, 1024, 2);
+      const uint64_t da_ns = make_desc(s32(A_ns) + 2 * ks * M * 16, M * 16, 128, 0);
+      if (mode == 0) mma_ts(tmem, tmem + a_col + 8 * ks, db_ns, idesc, ks > 0);
+      else if (mode == 1) mma_ts(tmem, tmem + a_col + 8 * ks, db_sw, idesc, ks > 0);
+      else mma_ss(tmem, da_ns, db_sw, idesc, ks > 0);
+    }
+    commit(s32(bar));
+  }
+  wait(s32(bar), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    uint32_t v[32];
+    TMEM_LD32(v, tmem + lane_base + c0);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int c = 0; c < 32 && c0 + c < n; ++c) out[tid * n + c0 + c] = __uint_as_float(v[c]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
+// cycles per MMA: `reps` MMAs back to back from one thread, then one commit
+// mode 0 / 1: TS (A in TMEM), B no-swizzle / swizzled;  mode 2 / 3: SS, B no-swizzle / swizzled
+__global__ void __launch_bounds__(128) timing(long long* cycles, int mode, int n, int reps) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 98304);
+  uint32_t* tmem_base = reinterpret_cast<uint32_t*>(smem + 98304 + 16);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 98304 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.0f;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(n);
+    const uint32_t sb = s32(smem), sa = s32(smem + 49152);
+    uint64_t dbs[8], das[8];
+    uint32_t ats[8];
+    for (int i = 0; i < 8; ++i) {
+      const int ks = i & 3, blk = (i >> 2) & 1;
+      dbs[i] = (mode & 1) ? make_desc(sb + blk * 16384 + ks * 32, 16, 1024, 2)
+                          : make_desc(sb + blk * 16384 + 2 * ks * n * 16, n * 16, 128, 0);
+      das[i] = make_desc(sa + blk * 16384 + 2 * ks * M * 16, M * 16, 128, 0);
+      ats[i] = tmem + 256 + blk * 32 + 8 * ks;
+    }
+    const long long t0 = clock64();
+    if (mode < 2) {
+      for (int i = 0; i < reps; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mma_ts(tmem, ats[j], dbs[j], idesc, 1u);
+      }
+    } else {
+      for (int i = 0; i < reps; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mma_ss(tmem, das[j], dbs[j], idesc, 1u);
+      }
+    }
+    commit(s32(bar));
+    wait(s32(bar), 0);
+    cycles[0] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+int main() {
+  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 50176);
+  cudaFuncSetAttribute(timing, cudaFuncAttributeMaxDynamicSharedMemorySize, 99328);
+  std::vector<float> a(M * K), b(NMAX * K), out(M * NMAX);
+  for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) a[m * K + k] = (float)((m * 7 + k * 3) % 17 - 8) * 0.125f;
+  for (int n = 0; n < NMAX; ++n) for (int k = 0; k < K; ++k) b[n * K + k] = (float)((k * 5 + n * 11) % 13 - 6) * 0.25f;
+  float *da, *db, *dout; long long* dcyc;
+  cudaMalloc(&da, a.size() * 4); cudaMalloc(&db, b.size() * 4); cudaMalloc(&dout, out.size() * 4); cudaMalloc(&dcyc, 8);
+  cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice);
+  int bad_total = 0;
+  const int tests[5][2] = {{0, 32}, {1, 32}, {1, 96}, {1, 128}, {2, 96}};
+  for (int t = 0; t < 5; ++t) {
+    const int mode = tests[t][0], n = tests[t][1];
+    cudaMemset(dout, 0xff, out.size() * 4);
+    probe<<<1, 128, 50176>>>(da, db, dout, mode, n);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost);
+    int bad = 0; double worst = 0;
+    for (int m = 0; m < M; ++m) for (int j = 0; j < n; ++j) {
+      double ref = 0;
+      for (int k = 0; k < K; ++k) ref += (double)a[m * K + k] * b[j * K + k];
+      const double d = fabs(out[m * n + j] - ref);
+      if (!(d <= worst)) worst = d;
+      if (d != 0) ++bad;
+    }
+    printf("layout test mode %d (%s, B %s) N=%3d: %s, %d / %d mismatches, worst |diff| %.3g\n", mode,
+           mode == 2 ? "A in smem" : "A in TMEM", mode == 0 ? "no swizzle" : "128B swizzle", n, cudaGetErrorString(e), bad,
+           M * n, worst);
+    bad_total += bad + (e != cudaSuccess);
+    if (e != cudaSuccess) return 2;
+  }
+  // 3. low mantissa bits: a = 1 + 2^-11 + 2^-12 (truncation -> 1, round-to-nearest -> 1 + 2^-10), b = 1 at k = 0 only
+  for (int which = 0; which < 2; ++which) {
+    std::vector<float> a2(M * K, 0.0f), b2(NMAX * K, 0.0f);
+    const float probe_v = 1.0f + ldexpf(1.0f, -11) + ldexpf(1.0f, -12);
+    for (int m = 0; m < M; ++m) a2[m * K] = which == 0 ? probe_v : 1.0f;
+    for (int n = 0; n < NMAX; ++n) b2[n * K] = which == 0 ? 1.0f : probe_v;
+    cudaMemcpy(da, a2.data(), a2.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, b2.data(), b2.size() * 4, cudaMemcpyHostToDevice);
+    for (int mode = 1; mode <= 2; ++mode) {
+      probe<<<1, 128, 50176>>>(da, db, dout, mode, 32);
+      cudaDeviceSynchronize();
+      cudaMemcpy(out.data(), dout, 128, cudaMemcpyDeviceToHost);
+      printf("low-bit test: %s operand = 1 + 2^-11 + 2^-12 (%s): product = 1 + %.6g * 2^-10  (0 = truncated, 1 = rounded, 0.75 = exact)\n",
+             which == 0 ? "A" : "B", which == 0 ? (mode == 2 ? "from smem" : "from TMEM") : "from smem",
+             (out[0] - 1.0) * 1024.0);
+    }
+  }
+  // 4. cycles per MMA
+  const int tm[14][2] = {{0, 32}, {0, 64}, {0, 96}, {0, 128}, {0, 192}, {0, 256}, {1, 32}, {1, 96}, {1, 192}, {2, 32}, {2, 64}, {2, 128}, {3, 32}, {3, 96}};
+  for (int t = 0; t < 14; ++t) {
+    const int reps = 2000;
+    timing<<<1, 128, 99328>>>(dcyc, tm[t][0], tm[t][1], reps);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long c = 0; cudaMemcpy(&c, dcyc, 8, cudaMemcpyDeviceToHost);
+    const char* names[4] = {"TS, B no swizzle", "TS, B 128B swizzle", "SS, B no swizzle", "SS, B 128B swizzle"};
+    printf("timing %-20s N=%3d: %7.1f cycles per MMA (128 x N x 8)  [%s]\n", names[tm[t][0]], tm[t][1], (double)c / reps,
+           cudaGetErrorString(e));
+  }
+  printf(bad_total ? "UMMA PROBE2 FAILED\n" : "UMMA PROBE2 OK\n");
+  return bad_total != 0;
+}
