@@ -153,9 +153,9 @@ def conv3x3_tc(x, weight, bias, slope=0.0, transpose_flip=False):
 
 
 def _is_tc(x, weight, pad):
-    """Shapes csmri_conv3x3_tc covers: 32 -> 32 channels, padding 1, H % 16 == 0, W % 128 == 0."""
+    """Shapes csmri_conv3x3_tc covers: 32 -> 32 channels, padding 1, H % 8 == 0, W % 128 == 0."""
     return (_TC_ENABLED and pad == 1 and tuple(weight.shape[:2]) == (32, 32) and
-            x.shape[2] % 16 == 0 and x.shape[3] % 128 == 0)
+            x.shape[2] % 8 == 0 and x.shape[3] % 128 == 0)
 
 
 def _is_thin(weight, pad):

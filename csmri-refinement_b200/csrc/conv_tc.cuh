@@ -13,31 +13,34 @@
 // does not beat cuDNN - so this kernel uses tcgen05.mma (kind::tf32, ~1.1 PFLOP/s
 // dense) with the accumulator in tensor memory.
 //
-// Implicit GEMM, one output row segment per tile:
-//     D[m = 128 pixels, n = 32 co] = sum_{tap} A_tap[128 x 32 ci] * B_tap[32 ci x 32 co]
+// Implicit GEMM over one staged input row segment at a time:
+//     acc[out row r+1-ky][m = 128 pixels, n = 32 co] += A_r,kx[128 x 32 ci] * B_kx,ky[32 ci x 32 co]
 // * A lives in shared memory in the NON-swizzled K-major canonical layout
 //   [ci/4][pixel][ci%4] (16-byte units, pixels contiguous).  In that layout
 //   "start one pixel further right" is "descriptor start address + 16 bytes", so the
-//   three horizontal taps read the SAME staged row at offsets 0 / 16 / 32 bytes and
-//   the three vertical taps read three different staged rows: every input row
-//   segment (130 pixels x 32 channels) is staged ONCE per output-row block and
-//   used by 9 taps x 3 output rows.  (tools/umma_probe.cu checks the shifted-start
-//   property on the hardware; swizzled layouts do not have it.)
+//   three horizontal taps read the SAME staged row at offsets 0 / 16 / 32 bytes
+//   (tools/umma_probe.cu checks the shifted-start property on the hardware;
+//   swizzled layouts do not have it).
+// * a tcgen05.mma of 128 x N x 8 costs max(44.5, N / 2) cycles whatever N is
+//   (tools/umma_probe2.cu), so an N = 32 instruction runs the tensor pipe at a third
+//   of its rate.  The three VERTICAL taps are therefore stacked along N: the B
+//   operand of a horizontal tap is [ky = 0 co | ky = 1 co | ky = 2 co] (N = 96), and
+//   the accumulators of consecutive output rows sit side by side in tensor memory in
+//   DESCENDING row order, so that one instruction adds input row r's contribution to
+//   output rows r+1, r, r-1 at once.  An input row is staged once and consumed by
+//   36 instructions (3 horizontal taps x 4 k-steps x 3 split terms).
+// * work item = 8 output rows x 128 pixels = 256 accumulator columns; the 512 TMEM
+//   columns hold two items, so the epilogue of one overlaps the MMAs of the next.
+//   At the top / bottom of an item the N window shrinks to the rows that exist.
 // * staging = 4 producer warps: coalesced fp32 loads straight from the NCHW
 //   tensor, hi / lo split in registers, two 16-byte shared stores per (pixel,
-//   4 channels), fence.proxy.async, mbarrier arrive.  A ring of 4 row slots.
-// * one thread issues the 72 MMAs of a tile (9 taps x 4 k-steps x 2), commits to
-//   mbarriers that (a) hand the accumulator to the epilogue warps and (b) return
-//   the oldest ring slot.  With both operands in shared memory a thin (N = 32)
-//   MMA is bound by operand fetch, not by the tensor pipe (measured: 108 MMAs of
-//   128 x 32 x 8 took ~68 cycles each, the pipe needs 16; A is 4 of the 5 KiB an MMA
-//   reads).  So the B operand of a tap is [B_hi | B_lo] side by side (N = 64):
-//   ONE MMA gives A_hi*B_hi in accumulator columns 0-31 and A_hi*B_lo in columns
-//   32-63, a second (N = 32) adds A_lo*B_hi to columns 0-31 - A_hi is fetched once
-//   instead of twice - and the epilogue adds the two column groups.
+//   4 channels), fence.proxy.async, mbarrier arrive.  A ring of 4 row slots, each
+//   released by a tcgen05.commit as soon as its 36 instructions have retired.
+// * the two small split terms (lo*hi, hi*lo) of a row are issued before its hi*hi
+//   term: the accumulator is rounded toward zero after every instruction, and that
+//   rounding is relative to what the accumulator holds at the time.
 // * 4 epilogue warps: tcgen05.ld (lane = pixel, columns = output channels),
-//   bias + LeakyReLU, coalesced 128-byte row stores per channel; two accumulator
-//   buffers in TMEM so the next tile's MMAs overlap the epilogue.
+//   bias + LeakyReLU, coalesced 128-byte row stores per channel.
 // * B (the 9 x 32 x 32 weights, hi and lo) is split once per CTA into shared
 //   memory; `transpose_flip` builds the data-gradient operator (ci <-> co swapped,
 //   taps mirrored) from the same weight tensor, so backward-data is this kernel too.
@@ -53,13 +56,15 @@ constexpr int kTcPA = 136;               // staged pixels per row slot (130 used
 constexpr int kTcPlane = kTcPA * 16;     // bytes between the 4-channel planes of a row slot
 constexpr int kTcSlotPart = 8 * kTcPlane;            // one row, hi or lo
 constexpr int kTcSlots = 4;
-constexpr int kTcBTap = 8 * 2 * kTcC * 16;           // one tap of B: [ci/4][hi co | lo co][ci%4] (8 KiB)
-constexpr int kTcBBytes = 9 * kTcBTap;               // 72 KiB
-constexpr int kTcAccCols = 2 * kTcC;                 // TMEM columns per accumulator buffer
+constexpr int kTcBPlane = 3 * kTcC * 16;            // B: bytes between 4-channel (ci) planes: 96 rows (ky, co)
+constexpr int kTcBPart = 8 * kTcBPlane;             // one horizontal tap, hi or lo: [ci/4][ky co][ci%4] (12 KiB)
+constexpr int kTcBBytes = 3 * 2 * kTcBPart;         // 72 KiB
+constexpr int kTcRowBlock = 8;                      // output rows per work item (10 staged rows)
+constexpr int kTcAccCols = kTcRowBlock * kTcC;      // TMEM columns per item (two items resident)
 constexpr int kTcABytes = kTcSlots * 2 * kTcSlotPart;
-constexpr int kTcSmemBytes = kTcBBytes + kTcABytes + 256;
-constexpr int kTcThreads = 288;          // 4 epilogue warps, 4 producer warps, 1 MMA warp
-constexpr int kTcRowBlock = 16;          // output rows per work item (18 staged rows)
+constexpr int kTcSmemBytes = kTcBBytes + kTcABytes + 512;
+constexpr int kTcThreads = 448;          // 4 epilogue warps, 2 x 4 producer warps, 1 halo warp, 1 MMA warp
+constexpr int kTcMmaWarp = 13;
 
 __device__ __forceinline__ uint32_t tc_s32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -104,6 +109,28 @@ __device__ __forceinline__ float tc_tf32(float v) {     // round to nearest TF32
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return __uint_as_float(r);
 }
+// The same split for the streamed operand, 4 instructions per value instead of 9:
+// hi = v rounded to nearest TF32 (integer add of half an ulp, mask; cvt.rna's Inf / NaN
+// special case is dropped - a non-finite input gives a non-finite output either way),
+// lo = v - hi exactly, rounded by the half-ulp add alone: the tensor core ignores the
+// 13 low mantissa bits of its fp32 containers (tools/umma_probe2.cu), which is the mask.
+__device__ __forceinline__ void tc_split(float v, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+  lo = __uint_as_float(__float_as_uint(v - hi) + 0x1000u);
+}
+
+// tuning probe (debug bit 7): cycles CTA 0 spent inside each kind of barrier wait
+__device__ long long tc_prof[8];
+#define TC_PROF_WAIT(slot_, bar_, par_)                                   \
+  do {                                                                    \
+    if (debug & 128) {                                                    \
+      const long long t0_ = clock64();                                    \
+      tc_mbar_wait(bar_, par_);                                           \
+      prof[slot_] += clock64() - t0_;                                     \
+    } else {                                                              \
+      tc_mbar_wait(bar_, par_);                                           \
+    }                                                                     \
+  } while (0)
 
 struct TcItem {
   int n, x0, y0;
@@ -128,37 +155,37 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                       const float* __restrict__ bias, float* __restrict__ y, int H, int W, int nitems,
                       float slope, int transpose_flip, int debug) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
-  unsigned char* B_s = tc_smem;                       // [tap][ci/4][hi co 0-31 | lo co 0-31][ci%4]
-  unsigned char* A_s = tc_smem + kTcBBytes;           // [slot][part][ci/4][pixel][ci%4]
+  unsigned char* B_s = tc_smem;                       // [kx][hi | lo][ci/4][ky co 0-95][ci%4]
+  unsigned char* A_s = tc_smem + kTcBBytes;           // [slot][hi | lo][ci/4][pixel][ci%4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + kTcBBytes + kTcABytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
   const uint32_t row_full = tc_s32(&bars[0]);         // [4] producers -> MMA
   const uint32_t row_free = tc_s32(&bars[4]);         // [4] MMA -> producers
-  const uint32_t acc_full = tc_s32(&bars[8]);         // [2] MMA -> epilogue
-  const uint32_t acc_free = tc_s32(&bars[10]);        // [2] epilogue -> MMA
+  const uint32_t acc_free = tc_s32(&bars[8]);         // [2] epilogue -> MMA (one per resident item)
+  const uint32_t acc_full = tc_s32(&bars[10]);        // [2][8] MMA -> epilogue (one per output row)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long prof[4] = {0, 0, 0, 0};
+  const long long t_start = clock64();
   const int xsegs = W / kTcM, yblocks = H / kTcRowBlock;
   const size_t plane = (size_t)H * W;
 
   // ---- one-time setup -----------------------------------------------------------
   if (tid == 0) {
     for (int i = 0; i < kTcSlots; ++i) {
-      tc_mbar_init(row_full + 8 * i, 128);
+      tc_mbar_init(row_full + 8 * i, 5);          // one arrival per producer warp of the row's group + the halo warp
       tc_mbar_init(row_free + 8 * i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      tc_mbar_init(acc_full + 8 * i, 1);
-      tc_mbar_init(acc_free + 8 * i, 128);
-    }
+    for (int i = 0; i < 2; ++i) tc_mbar_init(acc_free + 8 * i, 4);   // one arrival per epilogue warp
+    for (int i = 0; i < 2 * kTcRowBlock; ++i) tc_mbar_init(acc_full + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(
+  if (warp == kTcMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
                      tc_s32(tmem_slot))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // weights: split into hi / lo, laid out as the B operand of each tap
+  // weights: split into hi / lo, laid out as the B operand of each horizontal tap
   for (int e = tid; e < 9 * kTcC * kTcC; e += kTcThreads) {
     const int tap = e / (kTcC * kTcC), r = e - tap * (kTcC * kTcC);
     const int co = r / kTcC, ci = r - co * kTcC;       // operator element (co, ci, tap)
@@ -166,9 +193,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const float v = transpose_flip ? __ldg(w + ((ci * kTcC + co) * 3 + (2 - ky)) * 3 + (2 - kx))
                                    : __ldg(w + ((co * kTcC + ci) * 3 + ky) * 3 + kx);
     const float hi = tc_tf32(v), lo = tc_tf32(v - hi);
-    const int off = tap * kTcBTap + (ci >> 2) * (2 * kTcC * 16) + co * 16 + (ci & 3) * 4;
+    const int off = kx * (2 * kTcBPart) + (ci >> 2) * kTcBPlane + (ky * kTcC + co) * 16 + (ci & 3) * 4;
     *reinterpret_cast<float*>(B_s + off) = hi;
-    *reinterpret_cast<float*>(B_s + off + kTcC * 16) = lo;
+    *reinterpret_cast<float*>(B_s + off + kTcBPart) = lo;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -176,123 +203,177 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
-    // ===== producers: one input row segment (130 pixels x 32 channels) per ring slot =====
-    const int j = tid - 128;                       // 0 .. 127: pixel within the segment
-    uint32_t q = 0;                                // ring rows produced by this CTA so far
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const TcItem t = tc_item(item, xsegs, yblocks);
-      const float* xn = x + (size_t)t.n * kTcC * plane;
-      for (int r = 0; r < kTcRowBlock + 2; ++r, ++q) {
-        const int slot = q & 3;
-        tc_mbar_wait(row_free + 8 * slot, ((q >> 2) & 1) ^ 1);
-        const int gy = t.y0 - 1 + r;
-        unsigned char* hi_s = A_s + (size_t)slot * 2 * kTcSlotPart;
-        unsigned char* lo_s = hi_s + kTcSlotPart;
-        const bool row_ok = gy >= 0 && gy < H;
-        // pixel p of the slot is image column x0 - 1 + p; thread j stages p = j and,
-        // for j < 2, the two right-most pixels p = 128 + j
-        for (int pass = 0; pass < (j < 2 ? 2 : 1); ++pass) {
-          const int p = j + 128 * pass;
-          const int gx = t.x0 - 1 + p;
-          const bool ok = row_ok && gx >= 0 && gx < W;
-          const float* src = xn + (size_t)(ok ? gy : 0) * W + (ok ? gx : 0);
-          float v[kTcC];
+  if (warp >= 4 && warp < 12) {
+    // ===== producers: two groups of 4 warps; group g stages the ring rows q = g (mod 2),
+    // pixels 1 .. 128 of the slot (image columns x0 .. x0 + 127), one pixel per thread.
+    // The next row of the group is fetched into registers before the current one is
+    // converted, so the global-load latency hides behind the split / store work and the
+    // two groups overlap each other's barrier waits.
+    const int g = (warp - 4) >> 2;
+    const int j = (tid - 128) & 127;               // pixel within the segment
+    int item = blockIdx.x, r = g;                  // row to fetch next
+    uint32_t q = g;                                // its ring index
+    TcItem t = tc_item(item < nitems ? item : 0, xsegs, yblocks);
+    float v[kTcC], vn[kTcC];
+    auto fetch = [&](float* dst) {
+      const int gy = t.y0 - 1 + r;
+      const bool ok = item < nitems && gy >= 0 && gy < H && !(debug & 2);
+      const float* src = x + ((size_t)t.n * kTcC * H + (ok ? gy : 0)) * W + t.x0 + j;
 #pragma unroll
-          for (int c = 0; c < kTcC; ++c) v[c] = (ok && !(debug & 2)) ? __ldg(src + (size_t)c * plane) : 0.0f;
-#pragma unroll
-          for (int kc = 0; kc < 8; ++kc) {
-            float4 h, l;
-            h.x = tc_tf32(v[4 * kc]);     l.x = tc_tf32(v[4 * kc] - h.x);
-            h.y = tc_tf32(v[4 * kc + 1]); l.y = tc_tf32(v[4 * kc + 1] - h.y);
-            h.z = tc_tf32(v[4 * kc + 2]); l.z = tc_tf32(v[4 * kc + 2] - h.z);
-            h.w = tc_tf32(v[4 * kc + 3]); l.w = tc_tf32(v[4 * kc + 3] - h.w);
-            *reinterpret_cast<float4*>(hi_s + kc * kTcPlane + p * 16) = h;
-            *reinterpret_cast<float4*>(lo_s + kc * kTcPlane + p * 16) = l;
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc_mbar_arrive(row_full + 8 * slot);
+      for (int c = 0; c < kTcC; ++c) dst[c] = ok ? __ldg(src + (size_t)c * plane) : 0.0f;
+    };
+    fetch(v);
+    while (item < nitems) {
+      const uint32_t slot = q & 3;
+      // advance the fetch position by two rows and get that row on its way
+      r += 2;
+      if (r >= kTcRowBlock + 2) {
+        r -= kTcRowBlock + 2;
+        item += gridDim.x;
+        if (item < nitems) t = tc_item(item, xsegs, yblocks);
       }
+      fetch(vn);
+      TC_PROF_WAIT(0, row_free + 8 * slot, ((q >> 2) & 1) ^ 1);
+      unsigned char* hi_s = A_s + (size_t)slot * 2 * kTcSlotPart + (j + 1) * 16;
+      unsigned char* lo_s = hi_s + kTcSlotPart;
+      if (!(debug & 16)) {
+#pragma unroll
+        for (int kc = 0; kc < 8; ++kc) {
+          float4 h, l;
+          tc_split(v[4 * kc], h.x, l.x);
+          tc_split(v[4 * kc + 1], h.y, l.y);
+          tc_split(v[4 * kc + 2], h.z, l.z);
+          tc_split(v[4 * kc + 3], h.w, l.w);
+          *reinterpret_cast<float4*>(hi_s + kc * kTcPlane) = h;
+          *reinterpret_cast<float4*>(lo_s + kc * kTcPlane) = l;
+        }
+      }
+      // every thread publishes its own stores to the async proxy, then ONE lane per warp
+      // arrives (an arrival per thread is serialised on the barrier word)
+      if (!(debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(row_full + 8 * slot);
+      q += 2;
+#pragma unroll
+      for (int c = 0; c < kTcC; ++c) v[c] = vn[c];
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
+    // ===== halo warp: slot pixels 0 and 129 (image columns x0 - 1 and x0 + 128) of EVERY
+    // ring row; lane = (side, channel pair), next row fetched one step ahead =====
+    const int side = lane >> 4, c0 = (lane & 15) * 2;
+    int item = blockIdx.x, r = 0;
+    uint32_t q = 0;
+    TcItem t = tc_item(item < nitems ? item : 0, xsegs, yblocks);
+    float a0, a1, n0, n1;
+    auto fetch = [&](float& o0, float& o1) {
+      const int gy = t.y0 - 1 + r, gx = side ? t.x0 + kTcM : t.x0 - 1;
+      const bool ok = item < nitems && gy >= 0 && gy < H && gx >= 0 && gx < W && !(debug & 2);
+      const float* src = x + (((size_t)t.n * kTcC + c0) * H + (ok ? gy : 0)) * W + (ok ? gx : 0);
+      o0 = ok ? __ldg(src) : 0.0f;
+      o1 = ok ? __ldg(src + plane) : 0.0f;
+    };
+    fetch(a0, a1);
+    while (item < nitems) {
+      const uint32_t slot = q & 3;
+      if (++r >= kTcRowBlock + 2) {
+        r = 0;
+        item += gridDim.x;
+        if (item < nitems) t = tc_item(item, xsegs, yblocks);
+      }
+      fetch(n0, n1);
+      tc_mbar_wait(row_free + 8 * slot, ((q >> 2) & 1) ^ 1);
+      float* hi_s = reinterpret_cast<float*>(A_s + (size_t)slot * 2 * kTcSlotPart + (c0 >> 2) * kTcPlane +
+                                             (side ? kTcM + 1 : 0) * 16) + (c0 & 3);
+      float* lo_s = hi_s + kTcSlotPart / 4;
+      float2 h, l;
+      tc_split(a0, h.x, l.x);
+      tc_split(a1, h.y, l.y);
+      *reinterpret_cast<float2*>(hi_s) = h;
+      *reinterpret_cast<float2*>(lo_s) = l;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(row_full + 8 * slot);
+      ++q;
+      a0 = n0;
+      a1 = n1;
+    }
+  } else if (warp == kTcMmaWarp) {
     // ===== MMA issuer: one elected thread =====
     if (lane == 0) {
-      // D fp32, A / B tf32, both K-major, M = 128; N = 64 ([hi | lo] weights) and N = 32 (hi only)
-      const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcC >> 3) << 17) |
-                               ((uint32_t)(kTcM >> 4) << 24);
-      const uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * kTcC >> 3) << 17) |
-                               ((uint32_t)(kTcM >> 4) << 24);
+      // D fp32, A / B tf32, both K-major, M = 128, N = 32 x (vertical taps in the window)
+      const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcM >> 4) << 24);
       const uint64_t da_base = tc_desc(tc_s32(A_s), kTcPlane, 128);
-      const uint64_t db_base = tc_desc(tc_s32(B_s), 2 * kTcC * 16, 128);
-      uint32_t q = 0, tile = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        for (int r = 0; r < kTcRowBlock; ++r, ++q, ++tile) {
-          // input rows of output row r: ring rows q, q + 1, q + 2
-          if (r == 0) {
-            tc_mbar_wait(row_full + 8 * (q & 3), (q >> 2) & 1);
-            tc_mbar_wait(row_full + 8 * ((q + 1) & 3), ((q + 1) >> 2) & 1);
-          }
-          tc_mbar_wait(row_full + 8 * ((q + 2) & 3), ((q + 2) >> 2) & 1);
-          const uint32_t buf = tile & 1;
-          tc_mbar_wait(acc_free + 8 * buf, ((tile >> 1) & 1) ^ 1);
+      const uint64_t db_base = tc_desc(tc_s32(B_s), kTcBPlane, 128);
+      uint32_t q = 0, itemc = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++itemc) {
+        const uint32_t buf = itemc & 1;
+        TC_PROF_WAIT(1, acc_free + 8 * buf, ((itemc >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_base = tmem + buf * kTcAccCols;
+        for (int i = 0; i < kTcRowBlock + 2; ++i, ++q) {
+          // staged row i is image row y0 - 1 + i; it feeds output row y0 + i - ky, kept in
+          // column block 7 - (i - ky): vertical taps ky_lo .. ky_hi exist inside this item
+          const uint32_t slot = q & 3;
+          TC_PROF_WAIT(2, row_full + 8 * slot, (q >> 2) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t d_tmem = tmem + buf * kTcAccCols;
-          uint32_t acc = 0;
+          const int ky_lo = i > kTcRowBlock - 1 ? i - (kTcRowBlock - 1) : 0;
+          const int ky_hi = i < 2 ? i : 2;
+          const int nky = ky_hi - ky_lo + 1;
+          const uint32_t d_win = d_base + (uint32_t)(kTcRowBlock - 1 - i + ky_lo) * kTcC;
+          const uint32_t idesc_all = idesc0 | ((uint32_t)(nky * kTcC >> 3) << 17);
+          const uint64_t da_hi = da_base + (uint32_t)((slot * (2 * kTcSlotPart)) >> 4);
+          const uint64_t da_lo = da_hi + (uint32_t)(kTcSlotPart >> 4);
+          const uint64_t db_hi = db_base + (uint32_t)((ky_lo * kTcC * 16) >> 4);
+          const uint64_t db_lo = db_hi + (uint32_t)(kTcBPart >> 4);
+          bool first = ky_lo == 0;      // the ky = 0 block of this window has not been written yet
+          if (!(debug & 1)) {
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const uint64_t da_row = da_base + (uint32_t)((((q + ky) & 3) * (2 * kTcSlotPart)) >> 4);
+            for (int term = 0; term < 3; ++term) {          // lo*hi, hi*lo, hi*hi
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
+              for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                // only the 14-bit start-address field (16-byte units) changes between MMAs
-                const uint64_t dah = da_row + (uint32_t)((2 * ks * kTcPlane + kx * 16) >> 4);
-                const uint64_t dal = dah + (uint32_t)(kTcSlotPart >> 4);
-                const uint64_t db = db_base + (uint32_t)(((ky * 3 + kx) * kTcBTap + 2 * ks * (2 * kTcC * 16)) >> 4);
-                if (!(debug & 1)) {
-                  tc_mma(d_tmem, dah, db, idesc64, acc);    // cols 0-31 += hi*hi, cols 32-63 += hi*lo
-                  tc_mma(d_tmem, dal, db, idesc32, 1u);     // cols 0-31 += lo*hi
+                for (int ks = 0; ks < 4; ++ks) {
+                  // only the 14-bit start-address field (16-byte units) changes between MMAs
+                  const uint64_t da = (term == 0 ? da_lo : da_hi) + (uint32_t)((2 * ks * kTcPlane + kx * 16) >> 4);
+                  const uint64_t db = (term == 1 ? db_lo : db_hi) +
+                                      (uint32_t)((kx * (2 * kTcBPart) + 2 * ks * kTcBPlane) >> 4);
+                  if (term == 0 && kx == 0 && ks == 0 && first) {
+                    tc_mma(d_win, da, db, idesc0 | ((uint32_t)(kTcC >> 3) << 17), 0u);
+                    if (nky > 1)
+                      tc_mma(d_win + kTcC, da, db + (uint32_t)((kTcC * 16) >> 4),
+                             idesc0 | ((uint32_t)((nky - 1) * kTcC >> 3) << 17), 1u);
+                  } else {
+                    tc_mma(d_win, da, db, idesc_all, 1u);
+                  }
                 }
-                acc = 1u;
               }
             }
           }
-          tc_commit(acc_full + 8 * buf);
-          tc_commit(row_free + 8 * (q & 3));              // ring row q is not needed again
-          if (r == kTcRowBlock - 1) {                     // last output row of the block
-            tc_commit(row_free + 8 * ((q + 1) & 3));
-            tc_commit(row_free + 8 * ((q + 2) & 3));
-          }
+          tc_commit(row_free + 8 * slot);                   // the ring slot may be refilled
+          if (i >= 2) tc_commit(acc_full + 8 * (buf * kTcRowBlock + i - 2));   // output row y0 + i - 2 is complete
         }
-        q += 2;   // the block consumed kTcRowBlock + 2 ring rows
       }
     }
   } else {
-    // ===== epilogue: warp e owns TMEM lanes 32e .. 32e + 31 = pixels of the tile =====
+    // ===== epilogue: warp e owns TMEM lanes 32e .. 32e + 31 = pixels of the segment =====
     float bv[kTcC];
 #pragma unroll
     for (int c = 0; c < kTcC; ++c) bv[c] = bias != nullptr ? __ldg(bias + c) : 0.0f;
-    uint32_t tile = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    uint32_t itemc = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++itemc) {
       const TcItem t = tc_item(item, xsegs, yblocks);
+      const uint32_t buf = itemc & 1;
       float* yn = y + (size_t)t.n * kTcC * plane + t.x0 + tid;
-      for (int r = 0; r < kTcRowBlock; ++r, ++tile) {
-        const uint32_t buf = tile & 1;
-        tc_mbar_wait(acc_full + 8 * buf, (tile >> 1) & 1);
+      for (int r = 0; r < kTcRowBlock; ++r) {
+        TC_PROF_WAIT(3, acc_full + 8 * (buf * kTcRowBlock + r), (itemc >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t v[kTcC], u[kTcC];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + buf * kTcAccCols;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11,"
-            " %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28,"
-            " %29, %30, %31}, [%32];"
-            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]),
-              "=r"(u[7]), "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]),
-              "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]),
-              "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]),
-              "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-            : "r"(taddr + kTcC));
+        if (debug & 32) {
+          if (r == kTcRowBlock - 1 && lane == 0) tc_mbar_arrive(acc_free + 8 * buf);
+          continue;
+        }
+        uint32_t v[kTcC];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + buf * kTcAccCols +
+                               (uint32_t)(kTcRowBlock - 1 - r) * kTcC;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11,"
             " %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28,"
@@ -304,12 +385,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        tc_mbar_arrive(acc_free + 8 * buf);               // accumulator buffer may be overwritten
+        if (r == kTcRowBlock - 1) {                         // the item's columns may be overwritten
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive(acc_free + 8 * buf);
+        }
         float* dst = yn + (size_t)(t.y0 + r) * W;
 #pragma unroll
         for (int c = 0; c < kTcC; ++c) {
-          float o = (__uint_as_float(u[c]) + __uint_as_float(v[c])) + bv[c];   // small term first
+          float o = __uint_as_float(v[c]) + bv[c];
           if (slope > 0.0f) o = o > 0.0f ? o : o * slope;
           if (!(debug & 4))
             asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(dst + (size_t)c * plane), "f"(o)
@@ -318,11 +402,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
     }
   }
+  if ((debug & 128) && blockIdx.x == 0) {
+    if (tid == 128) tc_prof[0] = prof[0];                      // producer group 0: waiting for a free ring slot
+    if (tid == kTcMmaWarp * 32) { tc_prof[1] = prof[1]; tc_prof[2] = prof[2]; tc_prof[5] = clock64() - t_start; }
+    if (tid == 0) tc_prof[3] = prof[3];                        // epilogue: waiting for a finished row
+  }
   // ---- teardown ------------------------------------------------------------------
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+  if (warp == kTcMmaWarp)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 }  // namespace csmri

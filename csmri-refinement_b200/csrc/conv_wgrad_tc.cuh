@@ -1,0 +1,380 @@
+// Weight gradient of RecNet's 32 -> 32 channel 3x3 convolutions (the backward-weight
+// half of models/recnet.py:37-44 in Runner._train_step, training/runner.py:154-178) on
+// the tcgen05 tensor cores, with the same error-compensated TF32 split as conv_tc.cuh:
+//     dw[co][ci][ky][kx] = sum_{n,y,x} dy[n][co][y][x] * x[n][ci][y+ky-1][x+kx-1]
+// is a (32 x 288) GEMM whose reduction dimension is every pixel of the batch.
+//
+// One tensor-core instruction covers all nine taps of an 8-pixel run of one row:
+//     D[(kx, co) 96 of 128 lanes][(ky, ci) 96 columns] += A[(kx, co)][8 px] * B[(ky, ci)][8 px]^T
+// * A = the dy row, three copies shifted by 1 - kx pixels, in TENSOR MEMORY (lane =
+//   (kx, co), column = pixel; tcgen05.mma reads its A operand from TMEM): a shift
+//   along the reduction dimension cannot be expressed in a shared-memory descriptor
+//   (K advances in 32-byte steps), but the thread that writes lane (kx, co) simply
+//   starts one register further left or right.  Three staging warps (kx = 0, 1, 2)
+//   read the row from shared memory, split it into hi / lo and tcgen05.st it.
+// * B = the three input rows y-1, y, y+1, UNshifted, stacked along N: each row
+//   segment (32 channels x 32 pixels = one 128-byte-swizzled TMA box) is loaded
+//   ONCE into a ring of row slots and serves as ky = 2, 1, 0 of three consecutive
+//   steps; the three slots of a step are adjacent in shared memory, so one
+//   descriptor with N = 96 spans them.  (Ring of 6 + the first two slots mirrored
+//   behind the last, so a window never wraps.)  Image borders cost nothing: TMA
+//   zero-fills the out-of-range rows, the staging threads zero the two halo pixels.
+// * the raw fp32 box IS the hi operand (the tensor core ignores the 13 low mantissa
+//   bits, tools/umma_probe2.cu); four splitter warps write lo = x - trunc(x) next to it.
+// * 24 instructions (8 k-steps x {lo*hi, hi*lo, hi*hi}) of 128 x 96 x 8 per 64-pixel
+//   row segment; the accumulator stays in tensor memory and is drained into fp32
+//   registers every 4 rows (the tensor core rounds its accumulator toward zero after
+//   every instruction, so long chains are kept short), double buffered.
+// * per CTA one partial 96 x 96 block in the workspace; conv3x3_wgrad_tc_reduce_kernel
+//   sums the CTAs in a fixed order (deterministic) into dw's (co, ci, ky, kx) layout.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "conv_tc.cuh"
+
+namespace csmri {
+
+constexpr int kWtcC = 32;
+constexpr int kWtcPx = 64;                 // pixels per step (two 32-pixel swizzle atoms)
+constexpr int kWtcRows = 16;               // dy rows per work item (18 input rows loaded)
+constexpr int kWtcDrain = 4;               // steps per accumulator drain
+constexpr int kWtcRing = 6;                // input-row ring (+ 2 mirrored slots)
+constexpr int kWtcBox = 32 * 128;          // one TMA box: 32 channels x 32 pixels fp32 (4 KiB)
+constexpr int kWtcXAtom = (kWtcRing + 2) * kWtcBox;          // one atom column of the ring (32 KiB)
+constexpr int kWtcXPart = 2 * kWtcXAtom;                     // hi or lo (64 KiB)
+constexpr int kWtcDySlots = 3;
+constexpr int kWtcDyBytes = kWtcDySlots * 2 * kWtcBox;       // 24 KiB
+constexpr int kWtcSmemBytes = 2 * kWtcXPart + kWtcDyBytes + 1024 + 1024;   // + barriers + alignment slack
+constexpr int kWtcThreads = 416;           // 4 drain, 3 staging, 1 TMA, 4 splitter, 1 MMA warp
+constexpr int kWtcPartial = 96 * 96;       // floats per CTA in the workspace
+
+__device__ __forceinline__ void wtc_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void wtc_tma_box(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// A operand from tensor memory (TS form)
+__device__ __forceinline__ void wtc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{ .reg .pred p; setp.ne.b32 p, %4, 0;"
+      " tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p; }" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+#define WTC_ST32(addr, v)                                                                                        \
+  asm volatile(                                                                                                  \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "    \
+      "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(    \
+          addr),                                                                                                 \
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),          \
+      "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]),  \
+      "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]),             \
+      "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])                                      \
+      : "memory")
+#define WTC_LD32(v, addr)                                                                                        \
+  asm volatile(                                                                                                  \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "  \
+      "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"              \
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),           \
+        "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]),     \
+        "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),   \
+        "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])    \
+      : "r"(addr))
+
+struct WtcItem {
+  int n, x0, y0;
+};
+__device__ __forceinline__ WtcItem wtc_item(int item, int xsegs, int yblocks) {
+  WtcItem t;
+  t.n = item / (xsegs * yblocks);
+  const int rem = item - t.n * xsegs * yblocks;
+  const int yb = rem / xsegs;
+  t.y0 = yb * kWtcRows;
+  t.x0 = (rem - yb * xsegs) * kWtcPx;
+  return t;
+}
+
+// one dy row segment -> the A operand of one step: lane (KX, co) holds dy[co][x0 + p + 1 - KX], p = 0 .. 63,
+// as hi (columns 0-63 of the buffer) and lo (columns 64-127)
+template <int KX>
+__device__ __forceinline__ void wtc_stage_dy(const unsigned char* dy_slot, int co, float halo, uint32_t tmem_a) {
+  float d[kWtcPx + 2];                      // d[1 + p] = dy[x0 + p]; d[0], d[65] = halo pixels
+  d[0] = KX == 2 ? halo : 0.0f;
+  d[kWtcPx + 1] = KX == 0 ? halo : 0.0f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 q = *reinterpret_cast<const float4*>(dy_slot + a * kWtcBox + co * 128 + ((c ^ (co & 7)) << 4));
+      d[1 + 32 * a + 4 * c] = q.x;
+      d[2 + 32 * a + 4 * c] = q.y;
+      d[3 + 32 * a + 4 * c] = q.z;
+      d[4 + 32 * a + 4 * c] = q.w;
+    }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float hi[32], lo[32];
+#pragma unroll
+    for (int p = 0; p < 32; ++p) tc_split(d[32 * half + p + 2 - KX], hi[p], lo[p]);
+    WTC_ST32(tmem_a + 32 * half, hi);
+    WTC_ST32(tmem_a + kWtcPx + 32 * half, lo);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// x, dy: (N, 32, H, W) fp32 as 3-D tensor maps {W, H, N * 32}, box {32, 1, 32}, 128-byte swizzle.
+// H % kWtcRows == 0, W % kWtcPx == 0.  partial: gridDim.x blocks of 96 x 96 floats,
+// [(kx, co)][(ky, ci)].  dy_ptr: the same dy tensor, for the two halo pixels of a segment.
+__global__ void __launch_bounds__(kWtcThreads, 1)
+    conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
+                            const float* __restrict__ dy_ptr, float* __restrict__ partial, int H, int W, int nitems) {
+  extern __shared__ unsigned char wtc_smem_raw[];
+  // 128-byte-swizzled boxes are anchored at 1024-byte boundaries
+  unsigned char* smem = wtc_smem_raw + ((1024u - (tc_s32(wtc_smem_raw) & 1023u)) & 1023u);
+  unsigned char* X_hi = smem;                              // [atom 2][slot 8][32 ci][128 B]
+  unsigned char* X_lo = smem + kWtcXPart;
+  unsigned char* DY_s = smem + 2 * kWtcXPart;              // [slot 3][atom 2][32 co][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kWtcXPart + kWtcDyBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+  const uint32_t x_full = tc_s32(&bars[0]);       // [6] TMA -> splitters (hi landed)
+  const uint32_t xlo_full = tc_s32(&bars[6]);     // [6] splitters -> MMA
+  const uint32_t x_free = tc_s32(&bars[12]);      // [6] MMA -> TMA
+  const uint32_t dy_full = tc_s32(&bars[18]);     // [3] TMA -> staging
+  const uint32_t dy_free = tc_s32(&bars[21]);     // [3] staging -> TMA
+  const uint32_t a_full = tc_s32(&bars[24]);      // [2] staging -> MMA
+  const uint32_t a_free = tc_s32(&bars[26]);      // [2] MMA -> staging
+  const uint32_t d_full = tc_s32(&bars[28]);      // [2] MMA -> drain
+  const uint32_t d_free = tc_s32(&bars[30]);      // [2] drain -> MMA
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int xsegs = W / kWtcPx, yblocks = H / kWtcRows;
+
+  if (tid == 0) {
+    for (int i = 0; i < kWtcRing; ++i) {
+      tc_mbar_init(x_full + 8 * i, 1);
+      tc_mbar_init(xlo_full + 8 * i, 4);
+      tc_mbar_init(x_free + 8 * i, 1);
+    }
+    for (int i = 0; i < kWtcDySlots; ++i) {
+      tc_mbar_init(dy_full + 8 * i, 1);
+      tc_mbar_init(dy_free + 8 * i, 3);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc_mbar_init(a_full + 8 * i, 3);
+      tc_mbar_init(a_free + 8 * i, 1);
+      tc_mbar_init(d_full + 8 * i, 1);
+      tc_mbar_init(d_free + 8 * i, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dy) : "memory");
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_s32(tmem_slot))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  // tensor memory: accumulators at columns 0 and 128 (96 used each), A buffers at 256 and 384
+  // (64 hi + 64 lo columns each)
+
+  if (warp == 7) {
+    // ===== TMA producer: input rows (once each, + mirror) and dy rows, in the order the steps need them =====
+    if (lane == 0) {
+      uint32_t qx = 0, qd = 0;          // input rows / dy rows issued so far
+      auto load_x = [&](const WtcItem& t, int i) {
+        const uint32_t slot = qx % kWtcRing, use = qx / kWtcRing;
+        tc_mbar_wait(x_free + 8 * slot, (use & 1) ^ 1);
+        const bool mirror = slot < 2;
+        wtc_expect_tx(x_full + 8 * slot, (mirror ? 4 : 2) * kWtcBox);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          wtc_tma_box(tc_s32(X_hi + a * kWtcXAtom + slot * kWtcBox), &tm_x, x_full + 8 * slot, t.x0 + 32 * a,
+                      t.y0 - 1 + i, t.n * kWtcC);
+          if (mirror)
+            wtc_tma_box(tc_s32(X_hi + a * kWtcXAtom + (slot + kWtcRing) * kWtcBox), &tm_x, x_full + 8 * slot,
+                        t.x0 + 32 * a, t.y0 - 1 + i, t.n * kWtcC);
+        }
+        ++qx;
+      };
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const WtcItem t = wtc_item(item, xsegs, yblocks);
+        load_x(t, 0);
+        load_x(t, 1);
+        for (int j = 0; j < kWtcRows; ++j, ++qd) {
+          load_x(t, j + 2);
+          const uint32_t slot = qd % kWtcDySlots, use = qd / kWtcDySlots;
+          tc_mbar_wait(dy_free + 8 * slot, (use & 1) ^ 1);
+          wtc_expect_tx(dy_full + 8 * slot, 2 * kWtcBox);
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+            wtc_tma_box(tc_s32(DY_s + (slot * 2 + a) * kWtcBox), &tm_dy, dy_full + 8 * slot, t.x0 + 32 * a,
+                        t.y0 + j, t.n * kWtcC);
+        }
+      }
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // ===== splitters: lo = x - trunc_tf32(x), rounded, next to every landed input row =====
+    const int s = tid - 256;                                  // 0 .. 127
+    uint32_t qx = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      for (int i = 0; i < kWtcRows + 2; ++i, ++qx) {
+        const uint32_t slot = qx % kWtcRing, use = qx / kWtcRing;
+        tc_mbar_wait(x_full + 8 * slot, use & 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int chunk = s + 128 * k;                      // 512 16-byte chunks: 2 atoms x 256
+          const int off = (chunk >> 8) * kWtcXAtom + slot * kWtcBox + (chunk & 255) * 16;
+          const float4 v = *reinterpret_cast<const float4*>(X_hi + off);
+          float4 l;
+          l.x = __uint_as_float(__float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u)) + 0x1000u);
+          l.y = __uint_as_float(__float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)) + 0x1000u);
+          l.z = __uint_as_float(__float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u)) + 0x1000u);
+          l.w = __uint_as_float(__float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u)) + 0x1000u);
+          *reinterpret_cast<float4*>(X_lo + off) = l;
+          if (slot < 2) *reinterpret_cast<float4*>(X_lo + off + kWtcRing * kWtcBox) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(xlo_full + 8 * slot);
+      }
+    }
+  } else if (warp >= 4 && warp < 7) {
+    // ===== dy staging: warp kx writes TMEM lanes 32 kx .. 32 kx + 31 =====
+    const int kx = warp - 4, co = lane;
+    const uint32_t lane_base = (uint32_t)(kx * 32) << 16;
+    const size_t plane = (size_t)H * W;
+    uint32_t sc = 0;                                          // steps staged so far
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const WtcItem t = wtc_item(item, xsegs, yblocks);
+      for (int j = 0; j < kWtcRows; ++j, ++sc) {
+        // the one halo pixel this lane needs (kx = 0: right of the segment, kx = 2: left), fetched early
+        float halo = 0.0f;
+        const int hx = kx == 0 ? t.x0 + kWtcPx : t.x0 - 1;
+        if (kx != 1 && hx >= 0 && hx < W)
+          halo = __ldg(dy_ptr + ((size_t)t.n * kWtcC + co) * plane + (size_t)(t.y0 + j) * W + hx);
+        const uint32_t buf = sc & 1, slot = sc % kWtcDySlots;
+        tc_mbar_wait(a_free + 8 * buf, ((sc >> 1) & 1) ^ 1);
+        tc_mbar_wait(dy_full + 8 * slot, (sc / kWtcDySlots) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned char* src = DY_s + slot * 2 * kWtcBox;
+        const uint32_t ta = tmem + lane_base + 256 + buf * 128;
+        if (kx == 0) wtc_stage_dy<0>(src, co, halo, ta);
+        else if (kx == 1) wtc_stage_dy<1>(src, co, halo, ta);
+        else wtc_stage_dy<2>(src, co, halo, ta);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tc_mbar_arrive(a_full + 8 * buf);
+          tc_mbar_arrive(dy_free + 8 * slot);
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // D fp32, A / B tf32, K-major, M = 128, N = 96
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // 128-byte swizzle, 8-row groups 1024 bytes apart
+      const uint64_t db_hi0 = tc_desc(tc_s32(X_hi), 16, 1024) | ((uint64_t)2 << 61);
+      const uint64_t db_lo0 = tc_desc(tc_s32(X_lo), 16, 1024) | ((uint64_t)2 << 61);
+      uint32_t sc = 0, qbase = 0, period = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, qbase += kWtcRows + 2) {
+        for (int j = 0; j < kWtcRows; ++j, ++sc) {
+          const uint32_t dbuf = period & 1;
+          const bool first = (j % kWtcDrain) == 0, last = (j % kWtcDrain) == kWtcDrain - 1;
+          if (first) tc_mbar_wait(d_free + 8 * dbuf, ((period >> 1) & 1) ^ 1);
+          // input rows j, j + 1, j + 2 of the item: ring counters qbase + j ..
+          for (int k = (j == 0 ? 0 : 2); k < 3; ++k) {
+            const uint32_t q = qbase + j + k;
+            tc_mbar_wait(xlo_full + 8 * (q % kWtcRing), (q / kWtcRing) & 1);
+          }
+          const uint32_t abuf = sc & 1;
+          tc_mbar_wait(a_full + 8 * abuf, (sc >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t wslot = (qbase + j) % kWtcRing;      // window = slots wslot .. wslot + 2
+          const uint32_t d_tmem = tmem + dbuf * 128;
+          const uint32_t a_tmem = tmem + 256 + abuf * 128;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t boff = (uint32_t)(((ks >> 2) * kWtcXAtom + wslot * kWtcBox + (ks & 3) * 32) >> 4);
+            wtc_mma_ts(d_tmem, a_tmem + kWtcPx + 8 * ks, db_hi0 + boff, idesc, (first && ks == 0) ? 0u : 1u);   // lo * hi
+            wtc_mma_ts(d_tmem, a_tmem + 8 * ks, db_lo0 + boff, idesc, 1u);                                       // hi * lo
+            wtc_mma_ts(d_tmem, a_tmem + 8 * ks, db_hi0 + boff, idesc, 1u);                                       // hi * hi
+          }
+          tc_commit(a_free + 8 * abuf);
+          tc_commit(x_free + 8 * wslot);                       // input row j of the item is not needed again
+          if (j == kWtcRows - 1) {
+            tc_commit(x_free + 8 * ((qbase + j + 1) % kWtcRing));
+            tc_commit(x_free + 8 * ((qbase + j + 2) % kWtcRing));
+          }
+          if (last) {
+            tc_commit(d_full + 8 * dbuf);
+            ++period;
+          }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ===== drain: warp w owns TMEM lanes 32 w .. 32 w + 31; lanes 96-127 are never written =====
+    float acc[96];
+#pragma unroll
+    for (int i = 0; i < 96; ++i) acc[i] = 0.0f;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    uint32_t period = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      for (int pr = 0; pr < kWtcRows / kWtcDrain; ++pr, ++period) {
+        const uint32_t dbuf = period & 1;
+        tc_mbar_wait(d_full + 8 * dbuf, (period >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float v0[32], v1[32], v2[32];
+        WTC_LD32(v0, tmem + lane_base + dbuf * 128);
+        WTC_LD32(v1, tmem + lane_base + dbuf * 128 + 32);
+        WTC_LD32(v2, tmem + lane_base + dbuf * 128 + 64);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(d_free + 8 * dbuf);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          acc[i] += v0[i];
+          acc[32 + i] += v1[i];
+          acc[64 + i] += v2[i];
+        }
+      }
+    }
+    if (warp < 3) {
+      float* dst = partial + ((size_t)blockIdx.x * 96 + tid) * 96;
+#pragma unroll
+      for (int i = 0; i < 96; i += 4)
+        *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// dw[co][ci][ky][kx] = sum over CTAs, in CTA order, of partial[cta][(kx, co)][(ky, ci)]
+__global__ void __launch_bounds__(128)
+    conv3x3_wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nctas) {
+  const int e = blockIdx.x * 128 + threadIdx.x;                // (kx, co, ky, ci)
+  if (e >= kWtcPartial) return;
+  float s = 0.0f;
+  for (int c = 0; c < nctas; ++c) s += partial[(size_t)c * kWtcPartial + e];
+  const int row = e / 96, col = e - row * 96;
+  const int kx = row >> 5, co = row & 31, ky = col >> 5, ci = col & 31;
+  dw[((co * kWtcC + ci) * 3 + ky) * 3 + kx] = s;
+}
+
+}  // namespace csmri

@@ -255,7 +255,7 @@ int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float*
  *   transpose_flip = 0: wq = w (what nn.Conv2d.forward computes);
  *   transpose_flip = 1: wq[co][ci][ky][kx] = w[ci][co][2-ky][2-kx], i.e. the data
  *   gradient of the same layer (what autograd computes for its input).
- * H % 16 == 0, W % 128 == 0; anything else is CSMRI_E_SHAPE (the caller keeps its
+ * H % 8 == 0, W % 128 == 0; anything else is CSMRI_E_SHAPE (the caller keeps its
  * own convolution backend for those shapes). */
 int csmri_conv3x3_tc(const float* x, const float* w, const float* bias, float* y,
                      int N, int C, int H, int W, float slope, int transpose_flip, void* stream);

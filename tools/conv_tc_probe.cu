@@ -73,7 +73,9 @@ int main() {
     float *dx, *dw, *db, *dy;
     cudaMalloc(&dx, ne * 4); cudaMalloc(&dw, 9216 * 4); cudaMalloc(&db, 128); cudaMalloc(&dy, ne * 4);
     cudaMemset(dx, 0, ne * 4); cudaMemset(dw, 0, 9216 * 4); cudaMemset(db, 0, 128);
-    for (int debug = 0; debug < 8; ++debug) {
+    const int dbg_list[7] = {0, 128, 128 | 55, 128 | 50, 128 | 7, 128 | 2, 128 | 1};
+    for (int di = 0; di < 7; ++di) {
+      const int debug = dbg_list[di];
       if (ti == 1 && debug) break;
       for (int i = 0; i < 3; ++i) launch(dx, dw, db, dy, N, H, W, 0.01f, 0, debug);
       cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -83,9 +85,15 @@ int main() {
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
       const double flop = 2.0 * 9 * 32 * 32 * (double)N * H * W;
-      printf("N=%d %dx%d [skip mma %d, loads %d, stores %d]: %.3f ms per layer  %.1f TFLOP/s (fp32-equivalent)  %.0f GB/s of in+out traffic (%s)\n",
-             N, H, W, debug & 1, (debug >> 1) & 1, (debug >> 2) & 1, ms, flop / ms / 1e9, 2.0 * ne * 4 / ms / 1e6,
+      printf("N=%d %dx%d [debug %2d: skip mma %d, loads %d, stores %d]: %.3f ms per layer  %.1f TFLOP/s (fp32-equivalent)  %.0f GB/s of in+out traffic (%s)\n",
+             N, H, W, debug, debug & 1, (debug >> 1) & 1, (debug >> 2) & 1, ms, flop / ms / 1e9, 2.0 * ne * 4 / ms / 1e6,
              cudaGetErrorString(cudaGetLastError()));
+      if (debug & 128) {
+        long long pr[8]; cudaMemcpyFromSymbol(pr, tc_prof, sizeof(pr));
+        const double rows = (double)((N * (W / kTcM) * (H / kTcRowBlock) + 147) / 148) * (kTcRowBlock + 2);
+        printf("    CTA 0, cycles per staged row: producer waits slot %.0f | MMA waits item buffer %.0f, waits row %.0f | epilogue waits row %.0f | MMA thread total %.0f\n",
+               2 * pr[0] / rows, pr[1] / rows, pr[2] / rows, pr[3] / rows, pr[5] / rows);
+      }
     }
     cudaFree(dx); cudaFree(dw); cudaFree(db); cudaFree(dy);
   }

@@ -249,6 +249,12 @@ int main() {
     printf("timing %-20s N=%3d: %7.1f cycles per MMA (128 x N x 8)  [%s]\n", names[tm[t][0]], tm[t][1], (double)c / reps,
            cudaGetErrorString(e));
   }
+  for (int reps = 0; reps <= 16; reps += 8) {
+    timing<<<1, 128, 99328>>>(dcyc, 2, 96, reps);
+    cudaDeviceSynchronize();
+    long long c = 0; cudaMemcpy(&c, dcyc, 8, cudaMemcpyDeviceToHost);
+    printf("latency: %d MMAs (SS, N=96) + commit + mbarrier wait: %lld cycles\n", reps, c);
+  }
   printf(bad_total ? "UMMA PROBE2 FAILED\n" : "UMMA PROBE2 OK\n");
   return bad_total != 0;
 }
