@@ -23,8 +23,9 @@
 //   bits, tools/umma_probe2.cu); four splitter warps write lo = x - trunc(x) next to it.
 // * 24 instructions (8 k-steps x {lo*hi, hi*lo, hi*hi}) of 128 x 96 x 8 per 64-pixel
 //   row segment; the accumulator stays in tensor memory and is drained into fp32
-//   registers every 4 rows (the tensor core rounds its accumulator toward zero after
-//   every instruction, so long chains are kept short), double buffered.
+//   registers after every row segment, double buffered (the tensor core rounds its
+//   accumulator toward zero after every instruction: rel-L2 against float64 is 1.8e-6
+//   with a drain every 4 segments, 4.7e-7 with one every segment, for 4 % of the time).
 // * per CTA one partial 96 x 96 block in the workspace; conv3x3_wgrad_tc_reduce_kernel
 //   sums the CTAs in a fixed order (deterministic) into dw's (co, ci, ky, kx) layout.
 #pragma once
@@ -38,7 +39,7 @@ namespace csmri {
 constexpr int kWtcC = 32;
 constexpr int kWtcPx = 64;                 // pixels per step (two 32-pixel swizzle atoms)
 constexpr int kWtcRows = 16;               // dy rows per work item (18 input rows loaded)
-constexpr int kWtcDrain = 4;               // steps per accumulator drain
+constexpr int kWtcDrain = 1;                // steps per accumulator drain (short chains: see above)
 constexpr int kWtcRing = 6;                // input-row ring (+ 2 mirrored slots)
 constexpr int kWtcBox = 32 * 128;          // one TMA box: 32 channels x 32 pixels fp32 (4 KiB)
 constexpr int kWtcXAtom = (kWtcRing + 2) * kWtcBox;          // one atom column of the ring (32 KiB)
@@ -135,7 +136,8 @@ __device__ __forceinline__ void wtc_stage_dy(const unsigned char* dy_slot, int c
 // [(kx, co)][(ky, ci)].  dy_ptr: the same dy tensor, for the two halo pixels of a segment.
 __global__ void __launch_bounds__(kWtcThreads, 1)
     conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
-                            const float* __restrict__ dy_ptr, float* __restrict__ partial, int H, int W, int nitems) {
+                            const float* __restrict__ dy_ptr, float* __restrict__ partial, int H, int W, int nitems,
+                            int debug) {
   extern __shared__ unsigned char wtc_smem_raw[];
   // 128-byte-swizzled boxes are anchored at 1024-byte boundaries
   unsigned char* smem = wtc_smem_raw + ((1024u - (tc_s32(wtc_smem_raw) & 1023u)) & 1023u);
@@ -155,6 +157,8 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
   const uint32_t d_free = tc_s32(&bars[30]);      // [2] drain -> MMA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int xsegs = W / kWtcPx, yblocks = H / kWtcRows;
+  long long prof[4] = {0, 0, 0, 0};        // TC_PROF_WAIT (debug bit 7): cycles inside barrier waits
+  const long long t_start = clock64();
 
   if (tid == 0) {
     for (int i = 0; i < kWtcRing; ++i) {
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       for (int i = 0; i < kWtcRows + 2; ++i, ++qx) {
         const uint32_t slot = qx % kWtcRing, use = qx / kWtcRing;
-        tc_mbar_wait(x_full + 8 * slot, use & 1);
+        TC_PROF_WAIT(0, x_full + 8 * slot, use & 1);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int chunk = s + 128 * k;                      // 512 16-byte chunks: 2 atoms x 256
@@ -264,8 +268,8 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
         if (kx != 1 && hx >= 0 && hx < W)
           halo = __ldg(dy_ptr + ((size_t)t.n * kWtcC + co) * plane + (size_t)(t.y0 + j) * W + hx);
         const uint32_t buf = sc & 1, slot = sc % kWtcDySlots;
-        tc_mbar_wait(a_free + 8 * buf, ((sc >> 1) & 1) ^ 1);
-        tc_mbar_wait(dy_full + 8 * slot, (sc / kWtcDySlots) & 1);
+        TC_PROF_WAIT(0, a_free + 8 * buf, ((sc >> 1) & 1) ^ 1);
+        TC_PROF_WAIT(1, dy_full + 8 * slot, (sc / kWtcDySlots) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const unsigned char* src = DY_s + slot * 2 * kWtcBox;
         const uint32_t ta = tmem + lane_base + 256 + buf * 128;
@@ -293,14 +297,14 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
         for (int j = 0; j < kWtcRows; ++j, ++sc) {
           const uint32_t dbuf = period & 1;
           const bool first = (j % kWtcDrain) == 0, last = (j % kWtcDrain) == kWtcDrain - 1;
-          if (first) tc_mbar_wait(d_free + 8 * dbuf, ((period >> 1) & 1) ^ 1);
+          if (first) TC_PROF_WAIT(0, d_free + 8 * dbuf, ((period >> 1) & 1) ^ 1);
           // input rows j, j + 1, j + 2 of the item: ring counters qbase + j ..
           for (int k = (j == 0 ? 0 : 2); k < 3; ++k) {
             const uint32_t q = qbase + j + k;
-            tc_mbar_wait(xlo_full + 8 * (q % kWtcRing), (q / kWtcRing) & 1);
+            TC_PROF_WAIT(1, xlo_full + 8 * (q % kWtcRing), (q / kWtcRing) & 1);
           }
           const uint32_t abuf = sc & 1;
-          tc_mbar_wait(a_full + 8 * abuf, (sc >> 1) & 1);
+          TC_PROF_WAIT(2, a_full + 8 * abuf, (sc >> 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t wslot = (qbase + j) % kWtcRing;      // window = slots wslot .. wslot + 2
           const uint32_t d_tmem = tmem + dbuf * 128;
@@ -359,6 +363,11 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
       for (int i = 0; i < 96; i += 4)
         *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
     }
+  }
+  if ((debug & 128) && blockIdx.x == 0) {
+    if (tid == 128) { tc_prof[0] = prof[0]; tc_prof[1] = prof[1]; tc_prof[2] = clock64() - t_start; }   // staging warp kx = 0
+    if (tid == 384) { tc_prof[3] = prof[0]; tc_prof[4] = prof[1]; tc_prof[5] = prof[2]; tc_prof[6] = clock64() - t_start; }
+    if (tid == 256) tc_prof[7] = prof[0];                                                                // splitter
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

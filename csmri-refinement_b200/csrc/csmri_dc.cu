@@ -50,6 +50,7 @@
 #include "conv_epilogue.cuh"
 #include "conv_thin.cuh"
 #include "conv_tc.cuh"
+#include "conv_wgrad_tc.cuh"
 
 namespace csmri {
 
@@ -734,6 +735,7 @@ static int g_use_pdl = 1;             // programmatic dependent launch for the s
 static int g_wgrad_cot = 8;      // output channels per thread of conv3x3_wgrad_kernel (8; 4 = A/B baseline)
 static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_set_tuning
 static int g_tc_debug = 0;       // conv3x3_tc_kernel probe bits (tuning key 6)
+static int g_wgrad_tc = 1;       // 32 -> 32 weight gradient on the tensor cores (tuning key 7; 0 = SIMT kernel)
 static long long* g_trace = nullptr;  // tuning probe: per-CTA timeline buffers (2 x 1024 x 40)
 static int g_trace_launch = 0;
 
@@ -780,6 +782,22 @@ static int make_tile_map(CUtensorMap* m, const float* ptr, int B, int H, int W, 
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
+  if (r != CUDA_SUCCESS) return fail(CSMRI_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return CSMRI_OK;
+}
+
+// (N,32,H,W) fp32 viewed as {W, H, 32 N}; one box = 32 channels x 32 pixels of one row,
+// 128-byte swizzled (the K-major UMMA operand layout), out-of-range rows / columns zero-filled
+static int make_conv_map(CUtensorMap* m, const float* ptr, int N, int C, int H, int W) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(CSMRI_E_CUDA, "cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * C};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+  cuuint32_t box[3] = {32, 1, 32};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CSMRI_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return CSMRI_OK;
 }
@@ -1216,6 +1234,7 @@ int csmri_set_tuning(int key, int value) {
   else if (key == 4) g_use_pdl = value;
   else if (key == 5) g_wgrad_cot = value == 8 ? 8 : 4;
   else if (key == 6) g_tc_debug = value & 7;
+  else if (key == 7) g_wgrad_tc = value != 0;
   else return fail(CSMRI_E_ARG, "unknown tuning key %d", key);
   return CSMRI_OK;
 }
@@ -1619,6 +1638,25 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
     }
     wgrad_thin_reduce_kernel<<<(CI * CO * 9 + 63) / 64, 64, 0, s>>>((const float*)workspace, dw,
                                                                     CI * CO * 9, ctas);
+    CSMRI_CUDA(cudaGetLastError());
+    return CSMRI_OK;
+  }
+  if (g_wgrad_tc && CI == kWtcC && CO == kWtcC && pad == 1 && H % kWtcRows == 0 && W % kWtcPx == 0 &&
+      ((uintptr_t)x & 15u) == 0 && (long long)N * (W / kWtcPx) * (H / kWtcRows) <= 0x7fffffffLL) {
+    // tensor-core path (conv_wgrad_tc.cuh): one partial 96 x 96 block per CTA, then a
+    // fixed-order reduction; the workspace of the SIMT path (kWgMaxCtas blocks) is larger
+    alignas(64) CUtensorMap tm_x, tm_dy;
+    CSMRI_TRY(make_conv_map(&tm_x, x, N, CI, H, W));
+    CSMRI_TRY(make_conv_map(&tm_dy, dy, N, CO, H, W));
+    const int nitems = N * (W / kWtcPx) * (H / kWtcRows);
+    int ctas = sm_count();
+    if (ctas > kWgMaxCtas) ctas = kWgMaxCtas;
+    if (ctas > nitems) ctas = nitems;
+    CSMRI_TRY(set_smem(conv3x3_wgrad_tc_kernel, kWtcSmemBytes));
+    conv3x3_wgrad_tc_kernel<<<ctas, kWtcThreads, kWtcSmemBytes, s>>>(tm_x, tm_dy, dy, (float*)workspace,
+                                                                     H, W, nitems, 0);
+    conv3x3_wgrad_tc_reduce_kernel<<<(kWtcPartial + 127) / 128, 128, 0, s>>>((const float*)workspace, dw,
+                                                                             ctas);
     CSMRI_CUDA(cudaGetLastError());
     return CSMRI_OK;
   }

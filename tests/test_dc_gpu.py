@@ -789,6 +789,34 @@ def test_conv3x3_wgrad_matches_torch(shape):
         conv.conv3x3_wgrad(x[:, :1], gy, pad)            # unsupported channel count
 
 
+@pytest.mark.parametrize('shape', [(1, 16, 64), (2, 32, 128), (3, 48, 192), (4, 128, 256)])
+def test_conv3x3_wgrad_tensor_core_path(shape):
+    """The tcgen05 weight gradient (32 -> 32 channels, padding 1, H % 16 == 0, W % 64 == 0:
+    conv_wgrad_tc.cuh) against torch in fp64 and against the SIMT kernel of the same
+    entry point (tuning key 7 = 0); fixed summation order; (N, H, W)."""
+    from csmri_refinement_b200 import conv, _lib
+    n, h, w = shape
+    g = torch.Generator(device='cuda').manual_seed(sum(shape))
+    x = torch.randn(n, 32, h, w, device='cuda', generator=g)
+    gy = torch.randn(n, 32, h, w, device='cuda', generator=g) * 0.05
+    wt = torch.randn(32, 32, 3, 3, device='cuda', generator=g, dtype=torch.float64,
+                     requires_grad=True)
+    torch.nn.functional.conv2d(x.double(), wt, None, 1, 1).backward(gy.double())
+    truth = wt.grad.cpu().numpy()
+    got = conv.conv3x3_wgrad(x, gy, 1)
+    lib = _lib.lib()
+    try:
+        lib.csmri_set_tuning(7, 0)
+        simt = conv.conv3x3_wgrad(x, gy, 1)
+    finally:
+        lib.csmri_set_tuning(7, 1)
+    assert not torch.equal(got, simt)                    # two different kernels ran
+    e_tc, e_simt = orc.rel_l2(got.cpu().numpy(), truth), orc.rel_l2(simt.cpu().numpy(), truth)
+    print('wgrad rel-L2 vs fp64: tensor cores %.2e, SIMT %.2e' % (e_tc, e_simt))
+    assert e_tc < 2e-6 and e_simt < 2e-6
+    assert torch.equal(got, conv.conv3x3_wgrad(x, gy, 1))
+
+
 def test_recnet_training_gradients_with_fast_wgrad():
     """RecNet nf=32 loss gradients with the hand-written weight gradient vs torch's
     own backward for every parameter (north_star gate: rel-L2 <= 1e-5)."""
