@@ -22,8 +22,10 @@ dispatch of a 50-60 us kernel; `roofline.frac` is derived from that same region
 raw C-ABI loops).
 Extra keys: `gpu_baseline_torch_fft` (cuFFT + pointwise, the reference's
 structure, on the same GPU and tensors), `noisy_lambda` (the same microbench
-with noise_lvl = 0.1), `recnet_train` (BASELINE configs[2]: RecNet D5C5 fp32
-training step, batch 32 per GPU, with `tf32_convs` as a context number),
+with noise_lvl = 0.1), `recnet_train` (BASELINE configs[2]: RecNet D5C5
+training step, batch 32 per GPU, 32->32 layers on the tcgen05 tensor cores at
+fp32-level accuracy; `cudnn_fp32` = round 1's cuDNN fp32 path and `tf32_convs`
+= cuDNN's plain-TF32 path as context numbers),
 `recnet_1json` (configs/1-recnet.json unchanged: D3C3-nf32, GLOBAL batch 20,
 512^2, 8x; strong scaling) and `refinement_train` (BASELINE configs[4]).
 """
@@ -150,14 +152,22 @@ def make_batch(dev, B, n, seed):
 
 
 def recnet_train_bench(dev, rank, world, steps=8, warmup=3, batch=32, n=256, blocks=5, convs=5,
-                       filters=32, tf32=False):
+                       filters=32, mode='tc'):
     """BASELINE configs[2]: RecNet D5C5 MSE training step, batch 32 per GPU,
-    batch-sharded, one flat-bucket NCCL allreduce per step, fp32 (no TF32),
-    whole step captured in a CUDA graph.  Returns slices/s over all ranks."""
+    batch-sharded, one flat-bucket NCCL allreduce per step, whole step captured
+    in a CUDA graph.  Returns slices/s over all ranks.  ``mode``:
+    'tc'         the product path: 32 -> 32 layers (forward, data and weight gradient) on
+                 the tcgen05 tensor cores with the error-compensated TF32 split
+                 (fp32-level accuracy, parity-gated), thin layers / epilogues / DC = library kernels;
+    'cudnn_fp32' context: round 1's path - cuDNN fp32 forward / data gradient (TF32 off) and the
+                 SIMT weight-gradient kernel;
+    'cudnn_tf32' context: torch's stock setting, cuDNN with plain TF32 tensor cores (10-bit
+                 mantissa products, NOT parity-gated) + the SIMT weight gradient."""
     import torch.distributed as dist
-    from csmri_refinement_b200 import parallel, recnet, undersampling
-    # tf32=True is torch's stock conv setting (TF32 tensor cores): a context
-    # number only, the parity gate (1e-5) is stated for fp32 arithmetic
+    from csmri_refinement_b200 import _lib, conv, parallel, recnet, undersampling
+    tf32 = mode == 'cudnn_tf32'
+    conv.set_tensor_core_conv(mode == 'tc')
+    _lib.lib().csmri_set_tuning(7, 1 if mode == 'tc' else 0)
     torch.backends.cudnn.allow_tf32 = bool(tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True              # let cuDNN pick its fastest fp32 algorithms
@@ -188,15 +198,21 @@ def recnet_train_bench(dev, rank, world, steps=8, warmup=3, batch=32, n=256, blo
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    conv.set_tensor_core_conv(True)
+    _lib.lib().csmri_set_tuning(7, 1)
+    how = {'tc': '32->32 convolutions (forward, data gradient, weight gradient) = tcgen05 kernels, '
+                 '3-term TF32 split with fp32 accumulation (fp32-level accuracy, parity-gated); '
+                 'thin layers and bias/LeakyReLU epilogues = library kernels',
+           'cudnn_fp32': 'context: cuDNN fp32 forward / data gradient (TF32 off), SIMT weight '
+                         'gradient (round 1 path)',
+           'cudnn_tf32': 'context: cuDNN convs with plain TF32 tensor cores (torch default; not '
+                         'parity-gated), SIMT weight gradient'}[mode]
     return {'metric': 'recnet_train_slices_per_s', 'value': world * batch * steps / (ms * 1e-3),
             'unit': UNIT, 'ms_per_step': ms / steps, 'steps': steps,
             'config': 'RecNet D%dC%d nf=%d, MSE + Adam(2e-4), batch %d/GPU, %dx%d, %s, '
                       'DC = fused strip kernel, CUDA-graph step, '
                       'flat-bucket NCCL allreduce (%d bytes)' % (
-                          blocks, convs, filters, batch, n, n,
-                          'cuDNN convs with TF32 tensor cores (torch default; not parity-gated)'
-                          if tf32 else 'fp32 convs (cuDNN forward / data gradient, TF32 off; weight '
-                          'gradient = csmri_conv3x3_wgrad)', trainer.bucket.nbytes()),
+                          blocks, convs, filters, batch, n, n, how, trainer.bucket.nbytes()),
             'loss': float(loss.item())}
 
 
@@ -635,7 +651,8 @@ def main():
     if not args.no_recnet:
         try:
             line['recnet_train'] = recnet_train_bench(dev, rank, world)
-            line['recnet_train']['tf32_convs'] = recnet_train_bench(dev, rank, world, tf32=True)
+            line['recnet_train']['cudnn_fp32'] = recnet_train_bench(dev, rank, world, mode='cudnn_fp32')
+            line['recnet_train']['tf32_convs'] = recnet_train_bench(dev, rank, world, mode='cudnn_tf32')
         except Exception as e:  # secondary leg: never lose the headline line
             line.setdefault('recnet_train', {})['error'] = repr(e)[:300]
         torch.backends.cudnn.allow_tf32 = False

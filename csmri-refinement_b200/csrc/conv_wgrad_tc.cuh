@@ -39,7 +39,6 @@ namespace csmri {
 constexpr int kWtcC = 32;
 constexpr int kWtcPx = 64;                 // pixels per step (two 32-pixel swizzle atoms)
 constexpr int kWtcRows = 16;               // dy rows per work item (18 input rows loaded)
-constexpr int kWtcDrain = 1;                // steps per accumulator drain (short chains: see above)
 constexpr int kWtcRing = 6;                // input-row ring (+ 2 mirrored slots)
 constexpr int kWtcBox = 32 * 128;          // one TMA box: 32 channels x 32 pixels fp32 (4 KiB)
 constexpr int kWtcXAtom = (kWtcRing + 2) * kWtcBox;          // one atom column of the ring (32 KiB)
@@ -47,7 +46,9 @@ constexpr int kWtcXPart = 2 * kWtcXAtom;                     // hi or lo (64 KiB
 constexpr int kWtcDySlots = 3;
 constexpr int kWtcDyBytes = kWtcDySlots * 2 * kWtcBox;       // 24 KiB
 constexpr int kWtcSmemBytes = 2 * kWtcXPart + kWtcDyBytes + 1024 + 1024;   // + barriers + alignment slack
-constexpr int kWtcThreads = 416;           // 4 drain, 3 staging, 1 TMA, 4 splitter, 1 MMA warp
+// 12 warps = 3 per SM sub-partition: 168 registers per thread (a 13th warp would cap every thread at 128)
+constexpr int kWtcThreads = 384;           // 4 drain, 3 staging, 1 TMA, 2 splitter, 2 MMA warps
+constexpr int kWtcMmaWarp = 10;            // and 11
 constexpr int kWtcPartial = 96 * 96;       // floats per CTA in the workspace
 
 __device__ __forceinline__ void wtc_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -90,6 +91,8 @@ __device__ __forceinline__ void wtc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uin
         "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])    \
       : "r"(addr))
 
+__device__ long long wtc_cta_cycles[256];   // tuning probe (debug bit 7): MMA warp lifetime per CTA
+
 struct WtcItem {
   int n, x0, y0;
 };
@@ -104,27 +107,34 @@ __device__ __forceinline__ WtcItem wtc_item(int item, int xsegs, int yblocks) {
 }
 
 // one dy row segment -> the A operand of one step: lane (KX, co) holds dy[co][x0 + p + 1 - KX], p = 0 .. 63,
-// as hi (columns 0-63 of the buffer) and lo (columns 64-127)
+// as hi (columns 0-63 of the buffer) and lo (columns 64-127).  Half a segment at a time (32 pixels of
+// the row + the one pixel the shift pulls in from the neighbouring half or the halo) to stay inside
+// the register budget of a 448-thread CTA.
 template <int KX>
 __device__ __forceinline__ void wtc_stage_dy(const unsigned char* dy_slot, int co, float halo, uint32_t tmem_a) {
-  float d[kWtcPx + 2];                      // d[1 + p] = dy[x0 + p]; d[0], d[65] = halo pixels
-  d[0] = KX == 2 ? halo : 0.0f;
-  d[kWtcPx + 1] = KX == 0 ? halo : 0.0f;
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 q = *reinterpret_cast<const float4*>(dy_slot + a * kWtcBox + co * 128 + ((c ^ (co & 7)) << 4));
-      d[1 + 32 * a + 4 * c] = q.x;
-      d[2 + 32 * a + 4 * c] = q.y;
-      d[3 + 32 * a + 4 * c] = q.z;
-      d[4 + 32 * a + 4 * c] = q.w;
-    }
+  const unsigned char* row = dy_slot + co * 128;
+  const int sw = co & 7;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
+    float c[32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 q = *reinterpret_cast<const float4*>(row + half * kWtcBox + ((k ^ sw) << 4));
+      c[4 * k] = q.x;
+      c[4 * k + 1] = q.y;
+      c[4 * k + 2] = q.z;
+      c[4 * k + 3] = q.w;
+    }
+    float edge = halo;            // KX = 0: pixel 32 half + 32; KX = 2: pixel 32 half - 1
+    if (KX == 0 && half == 0) edge = *reinterpret_cast<const float*>(row + kWtcBox + ((0 ^ sw) << 4));
+    if (KX == 2 && half == 1) edge = *reinterpret_cast<const float*>(row + ((7 ^ sw) << 4) + 12);
     float hi[32], lo[32];
 #pragma unroll
-    for (int p = 0; p < 32; ++p) tc_split(d[32 * half + p + 2 - KX], hi[p], lo[p]);
+    for (int p = 0; p < 32; ++p) {
+      const float v = KX == 1 ? c[p] : KX == 0 ? (p < 31 ? c[p + 1 > 31 ? 31 : p + 1] : edge)
+                                                : (p > 0 ? c[p - 1 < 0 ? 0 : p - 1] : edge);
+      tc_split(v, hi[p], lo[p]);
+    }
     WTC_ST32(tmem_a + 32 * half, hi);
     WTC_ST32(tmem_a + kWtcPx + 32 * half, lo);
   }
@@ -152,8 +162,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
   const uint32_t dy_full = tc_s32(&bars[18]);     // [3] TMA -> staging
   const uint32_t dy_free = tc_s32(&bars[21]);     // [3] staging -> TMA
   const uint32_t a_full = tc_s32(&bars[24]);      // [2] staging -> MMA
-  const uint32_t a_free = tc_s32(&bars[26]);      // [2] MMA -> staging
-  const uint32_t d_full = tc_s32(&bars[28]);      // [2] MMA -> drain
+  const uint32_t step_done = tc_s32(&bars[26]);   // [2] MMA -> staging (A buffer free) and drain (accumulator ready)
   const uint32_t d_free = tc_s32(&bars[30]);      // [2] drain -> MMA
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int xsegs = W / kWtcPx, yblocks = H / kWtcRows;
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
   if (tid == 0) {
     for (int i = 0; i < kWtcRing; ++i) {
       tc_mbar_init(x_full + 8 * i, 1);
-      tc_mbar_init(xlo_full + 8 * i, 4);
+      tc_mbar_init(xlo_full + 8 * i, 2);
       tc_mbar_init(x_free + 8 * i, 1);
     }
     for (int i = 0; i < kWtcDySlots; ++i) {
@@ -172,15 +181,14 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       tc_mbar_init(a_full + 8 * i, 3);
-      tc_mbar_init(a_free + 8 * i, 1);
-      tc_mbar_init(d_full + 8 * i, 1);
+      tc_mbar_init(step_done + 8 * i, 1);
       tc_mbar_init(d_free + 8 * i, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_dy) : "memory");
   }
-  if (warp == 12) {
+  if (warp == kWtcMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_s32(tmem_slot))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -200,6 +208,11 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
         const uint32_t slot = qx % kWtcRing, use = qx / kWtcRing;
         tc_mbar_wait(x_free + 8 * slot, (use & 1) ^ 1);
         const bool mirror = slot < 2;
+        if (debug & 8) {
+          tc_mbar_arrive(x_full + 8 * slot);
+          ++qx;
+          return;
+        }
         wtc_expect_tx(x_full + 8 * slot, (mirror ? 4 : 2) * kWtcBox);
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
@@ -219,6 +232,10 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
           load_x(t, j + 2);
           const uint32_t slot = qd % kWtcDySlots, use = qd / kWtcDySlots;
           tc_mbar_wait(dy_free + 8 * slot, (use & 1) ^ 1);
+          if (debug & 8) {
+            tc_mbar_arrive(dy_full + 8 * slot);
+            continue;
+          }
           wtc_expect_tx(dy_full + 8 * slot, 2 * kWtcBox);
 #pragma unroll
           for (int a = 0; a < 2; ++a)
@@ -227,17 +244,17 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
         }
       }
     }
-  } else if (warp >= 8 && warp < 12) {
+  } else if (warp >= 8 && warp < 10) {
     // ===== splitters: lo = x - trunc_tf32(x), rounded, next to every landed input row =====
-    const int s = tid - 256;                                  // 0 .. 127
+    const int s = tid - 256;                                  // 0 .. 63
     uint32_t qx = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       for (int i = 0; i < kWtcRows + 2; ++i, ++qx) {
         const uint32_t slot = qx % kWtcRing, use = qx / kWtcRing;
         TC_PROF_WAIT(0, x_full + 8 * slot, use & 1);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int chunk = s + 128 * k;                      // 512 16-byte chunks: 2 atoms x 256
+        for (int k = 0; k < ((debug & 4) ? 0 : 8); ++k) {
+          const int chunk = s + 64 * k;                      // 512 16-byte chunks: 2 atoms x 256
           const int off = (chunk >> 8) * kWtcXAtom + slot * kWtcBox + (chunk & 255) * 16;
           const float4 v = *reinterpret_cast<const float4*>(X_hi + off);
           float4 l;
@@ -261,19 +278,22 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
     uint32_t sc = 0;                                          // steps staged so far
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const WtcItem t = wtc_item(item, xsegs, yblocks);
+      const int hx = kx == 0 ? t.x0 + kWtcPx : t.x0 - 1;
+      const bool has_halo = kx != 1 && hx >= 0 && hx < W;
+      const float* hp = dy_ptr + ((size_t)t.n * kWtcC + co) * plane + (size_t)t.y0 * W + (has_halo ? hx : 0);
       for (int j = 0; j < kWtcRows; ++j, ++sc) {
-        // the one halo pixel this lane needs (kx = 0: right of the segment, kx = 2: left), fetched early
-        float halo = 0.0f;
-        const int hx = kx == 0 ? t.x0 + kWtcPx : t.x0 - 1;
-        if (kx != 1 && hx >= 0 && hx < W)
-          halo = __ldg(dy_ptr + ((size_t)t.n * kWtcC + co) * plane + (size_t)(t.y0 + j) * W + hx);
+        // the one halo pixel this lane needs (kx = 0: right of the segment, kx = 2: left),
+        // straight from global memory, requested before the barrier waits
+        const float halo = has_halo ? __ldg(hp + (size_t)j * W) : 0.0f;
         const uint32_t buf = sc & 1, slot = sc % kWtcDySlots;
-        TC_PROF_WAIT(0, a_free + 8 * buf, ((sc >> 1) & 1) ^ 1);
+        TC_PROF_WAIT(0, step_done + 8 * buf, ((sc >> 1) & 1) ^ 1);
         TC_PROF_WAIT(1, dy_full + 8 * slot, (sc / kWtcDySlots) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long ts0 = (debug & 128) ? clock64() : 0;
         const unsigned char* src = DY_s + slot * 2 * kWtcBox;
         const uint32_t ta = tmem + lane_base + 256 + buf * 128;
-        if (kx == 0) wtc_stage_dy<0>(src, co, halo, ta);
+        if (debug & 1) {
+        } else if (kx == 0) wtc_stage_dy<0>(src, co, halo, ta);
         else if (kx == 1) wtc_stage_dy<1>(src, co, halo, ta);
         else wtc_stage_dy<2>(src, co, halo, ta);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -282,52 +302,72 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
           tc_mbar_arrive(a_full + 8 * buf);
           tc_mbar_arrive(dy_free + 8 * slot);
         }
+        if (debug & 128) prof[2] += clock64() - ts0;
       }
     }
-  } else if (warp == 12) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+  } else if (warp >= kWtcMmaWarp) {
+    // ===== MMA issuers: warp 10 issues the even steps, warp 11 the odd ones =====
+    // The instruction queue of the tensor core is shallow and one thread needs ~500 cycles per
+    // step for its barrier waits, fence and commits - time in which the pipe would run dry.
+    // Even and odd steps use disjoint accumulator and A buffers, so two threads can issue them
+    // independently: the bookkeeping of one overlaps the instructions of the other.
+    const uint32_t par = warp - kWtcMmaWarp;
+    if (lane == 0 && blockIdx.x < nitems) {
       // D fp32, A / B tf32, K-major, M = 128, N = 96
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // 128-byte swizzle, 8-row groups 1024 bytes apart
       const uint64_t db_hi0 = tc_desc(tc_s32(X_hi), 16, 1024) | ((uint64_t)2 << 61);
       const uint64_t db_lo0 = tc_desc(tc_s32(X_lo), 16, 1024) | ((uint64_t)2 << 61);
-      uint32_t sc = 0, qbase = 0, period = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, qbase += kWtcRows + 2) {
-        for (int j = 0; j < kWtcRows; ++j, ++sc) {
-          const uint32_t dbuf = period & 1;
-          const bool first = (j % kWtcDrain) == 0, last = (j % kWtcDrain) == kWtcDrain - 1;
-          if (first) TC_PROF_WAIT(0, d_free + 8 * dbuf, ((period >> 1) & 1) ^ 1);
-          // input rows j, j + 1, j + 2 of the item: ring counters qbase + j ..
-          for (int k = (j == 0 ? 0 : 2); k < 3; ++k) {
-            const uint32_t q = qbase + j + k;
+      const uint32_t total = (uint32_t)((nitems - blockIdx.x + gridDim.x - 1) / gridDim.x) * kWtcRows;
+      long long t_commit = 0, t_fence = 0;
+      auto ready = [&](uint32_t st, int part) {
+        if (part == 0) {                                      // accumulator buffer drained
+          TC_PROF_WAIT(0, d_free + 8 * (st & 1), ((st >> 1) & 1) ^ 1);
+        } else if (part == 1) {                               // input rows j, j + 1, j + 2 of the item split
+          const uint32_t it = st / kWtcRows, j = st - it * kWtcRows;
+          for (uint32_t k = (j < 2 ? 0 : 1); k < 3; ++k) {    // this thread last waited two steps ago
+            const uint32_t q = it * (kWtcRows + 2) + j + k;
             TC_PROF_WAIT(1, xlo_full + 8 * (q % kWtcRing), (q / kWtcRing) & 1);
           }
-          const uint32_t abuf = sc & 1;
-          TC_PROF_WAIT(2, a_full + 8 * abuf, (sc >> 1) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t wslot = (qbase + j) % kWtcRing;      // window = slots wslot .. wslot + 2
-          const uint32_t d_tmem = tmem + dbuf * 128;
-          const uint32_t a_tmem = tmem + 256 + abuf * 128;
+        } else {                                              // dy row staged in tensor memory
+          TC_PROF_WAIT(2, a_full + 8 * (st & 1), (st >> 1) & 1);
+        }
+      };
+      for (uint32_t st = par; st < total; st += 2) {
+        ready(st, 0);
+        ready(st, 1);
+        ready(st, 2);
+        const long long tf0 = (debug & 128) ? clock64() : 0;
+        if (!(debug & 32)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long ti0 = (debug & 128) ? clock64() : 0;
+        t_fence += ti0 - tf0;
+        const uint32_t it = st / kWtcRows, j = st - it * kWtcRows, qb = it * (kWtcRows + 2);
+        const uint32_t wslot = (qb + j) % kWtcRing;           // window = slots wslot .. wslot + 2
+        const uint32_t d_tmem = tmem + (st & 1) * 128;
+        const uint32_t a_tmem = tmem + 256 + (st & 1) * 128;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t boff = (uint32_t)(((ks >> 2) * kWtcXAtom + wslot * kWtcBox + (ks & 3) * 32) >> 4);
-            wtc_mma_ts(d_tmem, a_tmem + kWtcPx + 8 * ks, db_hi0 + boff, idesc, (first && ks == 0) ? 0u : 1u);   // lo * hi
-            wtc_mma_ts(d_tmem, a_tmem + 8 * ks, db_lo0 + boff, idesc, 1u);                                       // hi * lo
-            wtc_mma_ts(d_tmem, a_tmem + 8 * ks, db_hi0 + boff, idesc, 1u);                                       // hi * hi
-          }
-          tc_commit(a_free + 8 * abuf);
-          tc_commit(x_free + 8 * wslot);                       // input row j of the item is not needed again
-          if (j == kWtcRows - 1) {
-            tc_commit(x_free + 8 * ((qbase + j + 1) % kWtcRing));
-            tc_commit(x_free + 8 * ((qbase + j + 2) % kWtcRing));
-          }
-          if (last) {
-            tc_commit(d_full + 8 * dbuf);
-            ++period;
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t boff = (uint32_t)(((ks >> 2) * kWtcXAtom + wslot * kWtcBox + (ks & 3) * 32) >> 4);
+          if (!(debug & 16)) {
+            wtc_mma_ts(d_tmem, a_tmem + kWtcPx + 8 * ks, db_hi0 + boff, idesc, ks == 0 ? 0u : 1u);   // lo * hi
+            wtc_mma_ts(d_tmem, a_tmem + 8 * ks, db_lo0 + boff, idesc, 1u);                            // hi * lo
+            wtc_mma_ts(d_tmem, a_tmem + 8 * ks, db_hi0 + boff, idesc, 1u);                            // hi * hi
           }
         }
+        const long long ti1 = (debug & 128) ? clock64() : 0;
+        tc_commit(step_done + 8 * (st & 1));                   // A buffer free, accumulator ready to drain
+        tc_commit(x_free + 8 * wslot);                         // input row j of the item is not needed again
+        if (j == kWtcRows - 1) {
+          tc_commit(x_free + 8 * ((qb + j + 1) % kWtcRing));
+          tc_commit(x_free + 8 * ((qb + j + 2) % kWtcRing));
+        }
+        if (debug & 128) {
+          prof[3] += ti1 - ti0;                               // issuing the 24 instructions
+          t_commit += clock64() - ti1;                        // issuing the commits
+        }
       }
+      if ((debug & 128) && blockIdx.x == 0 && par == 0) { tc_prof[7] = t_commit; tc_prof[2] = t_fence; }
+      if ((debug & 128) && par == 0 && blockIdx.x < 256) wtc_cta_cycles[blockIdx.x] = clock64() - t_start;
     }
   } else if (warp < 4) {
     // ===== drain: warp w owns TMEM lanes 32 w .. 32 w + 31; lanes 96-127 are never written =====
@@ -337,23 +377,27 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     uint32_t period = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      for (int pr = 0; pr < kWtcRows / kWtcDrain; ++pr, ++period) {
+      for (int pr = 0; pr < kWtcRows; ++pr, ++period) {     // one drain per step
         const uint32_t dbuf = period & 1;
-        tc_mbar_wait(d_full + 8 * dbuf, (period >> 1) & 1);
+        tc_mbar_wait(step_done + 8 * dbuf, (period >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float v0[32], v1[32], v2[32];
-        WTC_LD32(v0, tmem + lane_base + dbuf * 128);
-        WTC_LD32(v1, tmem + lane_base + dbuf * 128 + 32);
-        WTC_LD32(v2, tmem + lane_base + dbuf * 128 + 64);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) tc_mbar_arrive(d_free + 8 * dbuf);
+        if (debug & 2) {
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive(d_free + 8 * dbuf);
+          continue;
+        }
+        float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          acc[i] += v0[i];
-          acc[32 + i] += v1[i];
-          acc[64 + i] += v2[i];
+        for (int g = 0; g < 3; ++g) {
+          WTC_LD32(v, tmem + lane_base + dbuf * 128 + 32 * g);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (g == 2) {                                       // the buffer may be overwritten
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(d_free + 8 * dbuf);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[32 * g + i] += v[i];
         }
       }
     }
@@ -365,13 +409,12 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
     }
   }
   if ((debug & 128) && blockIdx.x == 0) {
-    if (tid == 128) { tc_prof[0] = prof[0]; tc_prof[1] = prof[1]; tc_prof[2] = clock64() - t_start; }   // staging warp kx = 0
-    if (tid == 384) { tc_prof[3] = prof[0]; tc_prof[4] = prof[1]; tc_prof[5] = prof[2]; tc_prof[6] = clock64() - t_start; }
-    if (tid == 256) tc_prof[7] = prof[0];                                                                // splitter
+    if (tid == 192) { tc_prof[0] = prof[0]; tc_prof[1] = prof[1]; tc_prof[6] = prof[2]; }   // staging warp kx = 2
+    if (tid == kWtcMmaWarp * 32) { tc_prof[3] = prof[0]; tc_prof[4] = prof[1]; tc_prof[5] = prof[2]; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  if (warp == kWtcMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 // dw[co][ci][ky][kx] = sum over CTAs, in CTA order, of partial[cta][(kx, co)][(ky, ci)]

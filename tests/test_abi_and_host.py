@@ -85,6 +85,18 @@ def test_sass_is_blackwell_native(built_lib):
         assert hist[k].get('FFMA2', 0) + hist[k].get('FADD2', 0) + hist[k].get('FMUL2', 0) >= 300, k
         assert hist[k].get('HMMA', 0) == 0 and hist[k].get('UTCHMMA', 0) == 0   # no tensor cores: not a contraction
     assert any(hist[k].get('LDGSTS', 0) for k in hist if 'conv3x3' in k)
+    # the 32 -> 32 convolutions (the one GEMM-shaped piece) run on the 5th-generation
+    # tensor cores: UTCHMMA = tcgen05.mma, accumulators read back with LDTM, and the
+    # weight gradient feeds its A operand through STTM and its B operand through TMA
+    tc = [k for k in hist if 'conv3x3_tc_kernel' in k]
+    wtc = [k for k in hist if 'conv3x3_wgrad_tc_kernel' in k]
+    assert tc and wtc, 'tensor-core convolution kernels missing from the library'
+    for k in tc + wtc:
+        assert hist[k].get('UTCHMMA', 0) >= 20, (k, hist[k].get('UTCHMMA', 0))
+        assert hist[k].get('LDTM', 0) >= 1, k
+        assert hist[k].get('HMMA', 0) == 0, k           # no legacy warp-level MMA
+    for k in wtc:
+        assert hist[k].get('UTMALDG', 0) >= 1 and hist[k].get('STTM', 0) >= 1, k
 
 
 def test_build_staleness_covers_every_source(built_lib):

@@ -189,6 +189,105 @@ __global__ void __launch_bounds__(128) timing(long long* cycles, int mode, int n
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// groups of 24 MMAs (TS, N = 96, swizzled B; A alternating between two column ranges as the
+// weight-gradient kernel does) followed by `ncommit` tcgen05.commit to barriers nobody waits on;
+// `fresh` = 1: the first MMA of every group overwrites the accumulator (accumulate = 0)
+__global__ void __launch_bounds__(512) groups(long long* cycles, int ncommit, int fresh, int ngroups, int n, int spin_mode) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 98304);
+  uint32_t* tmem_base = reinterpret_cast<uint32_t*>(smem + 98304 + 64);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 98304 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.0f;
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(bar + i)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(n);
+    const uint64_t db0 = make_desc(s32(smem), 16, 1024, 2);
+    const long long t0 = clock64();
+    for (int g = 0; g < ngroups; ++g) {
+      const uint32_t d = tmem + (g & 1) * 128, a = tmem + 256 + (g & 1) * 128;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t boff = (uint32_t)(((ks >> 2) * 32768 + (ks & 3) * 32) >> 4);
+        mma_ts(d, a + 64 + 8 * ks, db0 + boff, idesc, (fresh && ks == 0) ? 0u : 1u);
+        mma_ts(d, a + 8 * ks, db0 + boff + (49152 >> 4), idesc, 1u);
+        mma_ts(d, a + 8 * ks, db0 + boff, idesc, 1u);
+      }
+      for (int c = 0; c < ncommit; ++c) commit(s32(bar + c));
+    }
+    commit(s32(bar + 3));
+    wait(s32(bar + 3), 0);
+    if (blockIdx.x == 0) cycles[0] = clock64() - t0;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar + 7)) : "memory");   // release the spinners
+  } else if (warp >= 1) {
+    // spinners: what the other roles of a warp-specialised kernel do while they wait
+    const uint32_t b = s32(bar + 7);
+    if (spin_mode == 0) {
+      wait(b, 0);
+    } else if (spin_mode == 1) {            // try_wait with a suspend-time hint
+      uint32_t done;
+      do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(b), "r"(0u), "r"(1000000u) : "memory");
+      } while (!done);
+    } else if (spin_mode == 2) {            // test_wait + nanosleep back-off
+      uint32_t done;
+      do {
+        asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(b), "r"(0u) : "memory");
+        if (!done) __nanosleep(64);
+      } while (!done);
+    } else {                                // one lane polls, the rest of the warp parks at a warp barrier
+      if ((tid & 31) == 0) wait(b, 0);
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// mbarrier ping-pong between two warps: lane 0 of warp 0 arrives on bar[0] and waits for bar[1],
+// lane 0 of warp 1 does the opposite; mode 1: warp 0's arrival is a tcgen05.commit (no MMAs pending);
+// mode 2: all 32 lanes of both warps wait, one lane arrives
+__global__ void __launch_bounds__(64) pingpong(long long* cycles, int mode, int iters) {
+  __shared__ __align__(8) uint64_t bar[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const bool waiter = mode == 2 || lane == 0;
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    if (warp == 0) {
+      if (lane == 0) {
+        if (mode == 1) commit(s32(&bar[0]));
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&bar[0])) : "memory");
+      }
+      if (waiter) wait(s32(&bar[1]), i & 1);
+    } else {
+      if (waiter) wait(s32(&bar[0]), i & 1);
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&bar[1])) : "memory");
+    }
+    if (mode == 2) __syncwarp();
+  }
+  if (tid == 0) cycles[0] = clock64() - t0;
+}
+
 int main() {
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 50176);
   cudaFuncSetAttribute(timing, cudaFuncAttributeMaxDynamicSharedMemorySize, 99328);
@@ -254,6 +353,38 @@ int main() {
     cudaDeviceSynchronize();
     long long c = 0; cudaMemcpy(&c, dcyc, 8, cudaMemcpyDeviceToHost);
     printf("latency: %d MMAs (SS, N=96) + commit + mbarrier wait: %lld cycles\n", reps, c);
+  }
+  cudaFuncSetAttribute(groups, cudaFuncAttributeMaxDynamicSharedMemorySize, 99328);
+  for (int t = 0; t < 8; ++t) {
+    const int nc[8] = {0, 1, 3, 0, 3, 0, 0, 3}, fr[8] = {0, 0, 0, 1, 1, 0, 0, 0}, nn[8] = {96, 96, 96, 96, 96, 128, 64, 64};
+    groups<<<1, 32, 99328>>>(dcyc, nc[t], fr[t], 200, nn[t], 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long c = 0; cudaMemcpy(&c, dcyc, 8, cudaMemcpyDeviceToHost);
+    printf("groups of 24 TS MMAs N=%3d, %d commits per group, fresh accumulator %d: %.0f cycles per group = %.1f per MMA [%s]\n",
+           nn[t], nc[t], fr[t], c / 200.0, c / 200.0 / 24, cudaGetErrorString(e));
+  }
+  for (int t = 0; t < 9; ++t) {
+    const int warps[9] = {5, 13, 13, 13, 13, 16, 16, 16, 16}, sm[9] = {0, 0, 1, 2, 3, 0, 1, 2, 3};
+    groups<<<1, 32 * warps[t], 99328>>>(dcyc, 3, 1, 200, 96, sm[t]);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long c = 0; cudaMemcpy(&c, dcyc, 8, cudaMemcpyDeviceToHost);
+    const char* nm[4] = {"try_wait loop", "try_wait with suspend hint", "test_wait + nanosleep(64)", "one lane polls"};
+    printf("24 TS MMAs N=96 + 3 commits with %2d warps waiting on a barrier (%s): %.0f cycles per group [%s]\n", warps[t] - 1,
+           nm[sm[t]], c / 200.0, cudaGetErrorString(e));
+  }
+  for (int t = 0; t < 4; ++t) {
+    const int grid[4] = {1, 37, 74, 148};
+    groups<<<grid[t], 32, 99328>>>(dcyc, 3, 1, 2000, 96, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long c = 0; cudaMemcpy(&c, dcyc, 8, cudaMemcpyDeviceToHost);
+    printf("24 TS MMAs N=96 + 3 commits on %3d SMs at once: %.0f cycles per group [%s]\n", grid[t], c / 2000.0, cudaGetErrorString(e));
+  }
+  for (int mode = 0; mode < 3; ++mode) {
+    pingpong<<<1, 64>>>(dcyc, mode, 1000);
+    cudaDeviceSynchronize();
+    long long c = 0; cudaMemcpy(&c, dcyc, 8, cudaMemcpyDeviceToHost);
+    const char* nm[3] = {"mbarrier.arrive both ways, one lane waits", "tcgen05.commit one way", "mbarrier.arrive both ways, 32 lanes wait"};
+    printf("ping-pong round trip (%s): %.0f cycles\n", nm[mode], c / 1000.0);
   }
   printf(bad_total ? "UMMA PROBE2 FAILED\n" : "UMMA PROBE2 OK\n");
   return bad_total != 0;

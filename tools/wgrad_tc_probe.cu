@@ -106,12 +106,19 @@ int main() {
     const double flop = 2.0 * 9 * 32 * 32 * (double)N * H * W;
     printf("N=%d %dx%d: %.3f ms per layer  %.1f TFLOP/s (fp32-equivalent)  %.0f GB/s of x + dy traffic (%s)\n", N, H, W, ms,
            flop / ms / 1e9, 2.0 * ne * 4 / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
-    launch(dx, ddy, ddw, ws, N, H, W, 128);
+    const int dbg[8] = {0, 32, 15, 15 | 32, 16, 31, 1, 1 | 32};
+    for (int di = 0; di < 1; ++di) {
+    launch(dx, ddy, ddw, ws, N, H, W, 128 | dbg[di]);
     cudaDeviceSynchronize();
     long long pr[8]; cudaMemcpyFromSymbol(pr, tc_prof, sizeof(pr));
     const double steps = (double)((N * (W / kWtcPx) * (H / kWtcRows) + g_sms - 1) / g_sms) * kWtcRows;
-    printf("    CTA 0, cycles per step: staging waits A buffer %.0f, waits dy row %.0f, total %.0f | MMA waits drain %.0f, waits input rows %.0f, waits A %.0f, total %.0f | splitter waits TMA %.0f\n",
-           pr[0] / steps, pr[1] / steps, pr[2] / steps, pr[3] / steps, pr[4] / steps, pr[5] / steps, pr[6] / steps, pr[7] / steps);
+    printf("    [skip bits %2d: 1 staging, 2 drain, 4 splitter, 8 TMA, 16 MMA, 32 fence] CTA 0, cycles per step: staging waits A buffer %.0f, waits dy row %.0f | MMA thread fence %.0f | MMA waits drain %.0f, waits input rows %.0f, waits A %.0f, staging (kx 2) works %.0f, MMA thread issues commits %.0f\n",
+           dbg[di], pr[0] / steps, pr[1] / steps, pr[2] / steps, pr[3] / steps, pr[4] / steps, pr[5] / steps, pr[6] / steps, pr[7] / steps);
+    long long cc[256]; cudaMemcpyFromSymbol(cc, wtc_cta_cycles, sizeof(cc));
+    long long mn = cc[0], mx = cc[0]; double av = 0;
+    for (int i = 0; i < g_sms; ++i) { if (cc[i] < mn) mn = cc[i]; if (cc[i] > mx) mx = cc[i]; av += cc[i]; }
+    printf("    MMA-warp lifetime over the %d CTAs (cycles): min %lld, mean %.0f, max %lld; CTA 0: %lld = %.0f per step\n", g_sms, mn, av / g_sms, mx, cc[0], cc[0] / steps);
+    }
     cudaFree(dx); cudaFree(ddy); cudaFree(ddw); cudaFree(ws);
   }
   printf(fails ? "WGRAD TC PROBE FAILED\n" : "WGRAD TC PROBE OK\n");
