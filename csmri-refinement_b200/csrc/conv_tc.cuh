@@ -25,13 +25,13 @@
 //   (tools/umma_probe2.cu), so an N = 32 instruction runs the tensor pipe at a third
 //   of its rate.  The three VERTICAL taps are therefore stacked along N: the B
 //   operand of a horizontal tap is [ky = 0 co | ky = 1 co | ky = 2 co] (N = 96), and
-//   the accumulators of consecutive output rows sit side by side in tensor memory in
-//   DESCENDING row order, so that one instruction adds input row r's contribution to
-//   output rows r+1, r, r-1 at once.  An input row is staged once and consumed by
-//   36 instructions (3 horizontal taps x 4 k-steps x 3 split terms).
-// * work item = 8 output rows x 128 pixels = 256 accumulator columns; the 512 TMEM
-//   columns hold two items, so the epilogue of one overlaps the MMAs of the next.
-//   At the top / bottom of an item the N window shrinks to the rows that exist.
+//   one instruction computes input row r's contribution to output rows r+1, r, r-1
+//   at once, into a 96-column accumulator block of its own.  An input row is staged
+//   once and consumed by 36 instructions (3 horizontal taps x 4 k-steps x 3 split
+//   terms).  Five blocks rotate through tensor memory; the epilogue adds the three
+//   blocks that hold an output row's contributions in fp32 registers.
+// * work item = 8 output rows x 128 pixels (10 staged rows).  At the top / bottom
+//   of an item the N window shrinks to the taps that land inside it.
 // * staging = 4 producer warps: coalesced fp32 loads straight from the NCHW
 //   tensor, hi / lo split in registers, two 16-byte shared stores per (pixel,
 //   4 channels), fence.proxy.async, mbarrier arrive.  A ring of 4 row slots, each
@@ -60,7 +60,8 @@ constexpr int kTcBPlane = 3 * kTcC * 16;            // B: bytes between 4-channe
 constexpr int kTcBPart = 8 * kTcBPlane;             // one horizontal tap, hi or lo: [ci/4][ky co][ci%4] (12 KiB)
 constexpr int kTcBBytes = 3 * 2 * kTcBPart;         // 72 KiB
 constexpr int kTcRowBlock = 8;                      // output rows per work item (10 staged rows)
-constexpr int kTcAccCols = kTcRowBlock * kTcC;      // TMEM columns per item (two items resident)
+constexpr int kTcBlocks = 5;                        // accumulator blocks of 96 columns in tensor memory (one per staged row in flight)
+static_assert((kTcRowBlock + 2) % kTcBlocks == 0, "the block of a staged row must not depend on the item");
 constexpr int kTcABytes = kTcSlots * 2 * kTcSlotPart;
 constexpr int kTcSmemBytes = kTcBBytes + kTcABytes + 512;
 constexpr int kTcThreads = 448;          // 4 epilogue warps, 2 x 4 producer warps, 1 halo warp, 1 MMA warp
@@ -132,6 +133,23 @@ __device__ long long tc_prof[8];
     }                                                                     \
   } while (0)
 
+#define TC_LD16(v, addr)                                                                                      \
+  asm volatile(                                                                                               \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, " \
+      "%15}, [%16];"                                                                                          \
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),        \
+        "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])   \
+      : "r"(addr))
+#define TC_LD32(v, addr)                                                                                         \
+  asm volatile(                                                                                                  \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "  \
+      "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"              \
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),           \
+        "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]),     \
+        "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),   \
+        "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])    \
+      : "r"(addr))
+
 struct TcItem {
   int n, x0, y0;
 };
@@ -161,8 +179,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
   const uint32_t row_full = tc_s32(&bars[0]);         // [4] producers -> MMA
   const uint32_t row_free = tc_s32(&bars[4]);         // [4] MMA -> producers
-  const uint32_t acc_free = tc_s32(&bars[8]);         // [2] epilogue -> MMA (one per resident item)
-  const uint32_t acc_full = tc_s32(&bars[10]);        // [2][8] MMA -> epilogue (one per output row)
+  const uint32_t acc_free = tc_s32(&bars[8]);         // [5] epilogue -> MMA (one per accumulator block)
+  const uint32_t acc_full = tc_s32(&bars[16]);        // [5] MMA -> epilogue
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long prof[4] = {0, 0, 0, 0};
   const long long t_start = clock64();
@@ -175,8 +193,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       tc_mbar_init(row_full + 8 * i, 5);          // one arrival per producer warp of the row's group + the halo warp
       tc_mbar_init(row_free + 8 * i, 1);
     }
-    for (int i = 0; i < 2; ++i) tc_mbar_init(acc_free + 8 * i, 4);   // one arrival per epilogue warp
-    for (int i = 0; i < 2 * kTcRowBlock; ++i) tc_mbar_init(acc_full + 8 * i, 1);
+    for (int i = 0; i < kTcBlocks; ++i) {
+      tc_mbar_init(acc_free + 8 * i, 4);          // one arrival per epilogue warp
+      tc_mbar_init(acc_full + 8 * i, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kTcMmaWarp) {
@@ -306,29 +326,31 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const uint64_t db_base = tc_desc(tc_s32(B_s), kTcBPlane, 128);
       uint32_t q = 0, itemc = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++itemc) {
-        const uint32_t buf = itemc & 1;
-        TC_PROF_WAIT(1, acc_free + 8 * buf, ((itemc >> 1) & 1) ^ 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_base = tmem + buf * kTcAccCols;
         for (int i = 0; i < kTcRowBlock + 2; ++i, ++q) {
-          // staged row i is image row y0 - 1 + i; it feeds output row y0 + i - ky, kept in
-          // column block 7 - (i - ky): vertical taps ky_lo .. ky_hi exist inside this item
-          const uint32_t slot = q & 3;
+          // staged row i is image row y0 - 1 + i; it feeds output row y0 + i - ky through vertical
+          // tap ky, and only the taps ky_lo .. ky_hi land inside this item.  The row gets a FRESH
+          // accumulator block (i % 5; the first instruction overwrites it): column group ky of
+          // the block holds this row's contribution to output row i - ky, and the epilogue adds
+          // the three contributions of an output row in fp32 registers.  The tensor core rounds
+          // its accumulator toward zero after every instruction, so 36-instruction chains
+          // instead of 108 are what keeps the result at fp32 level (rel-L2 5e-7 instead of 1.6e-6).
+          const uint32_t slot = q & 3, blk = (uint32_t)i % kTcBlocks;
+          const uint32_t use = itemc * ((kTcRowBlock + 2) / kTcBlocks) + (uint32_t)i / kTcBlocks;
+          TC_PROF_WAIT(1, acc_free + 8 * blk, (use & 1) ^ 1);
           TC_PROF_WAIT(2, row_full + 8 * slot, (q >> 2) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int ky_lo = i > kTcRowBlock - 1 ? i - (kTcRowBlock - 1) : 0;
           const int ky_hi = i < 2 ? i : 2;
           const int nky = ky_hi - ky_lo + 1;
-          const uint32_t d_win = d_base + (uint32_t)(kTcRowBlock - 1 - i + ky_lo) * kTcC;
-          const uint32_t idesc_all = idesc0 | ((uint32_t)(nky * kTcC >> 3) << 17);
+          const uint32_t d_win = tmem + blk * (3 * kTcC) + (uint32_t)ky_lo * kTcC;
+          const uint32_t idesc = idesc0 | ((uint32_t)(nky * kTcC >> 3) << 17);
           const uint64_t da_hi = da_base + (uint32_t)((slot * (2 * kTcSlotPart)) >> 4);
           const uint64_t da_lo = da_hi + (uint32_t)(kTcSlotPart >> 4);
           const uint64_t db_hi = db_base + (uint32_t)((ky_lo * kTcC * 16) >> 4);
           const uint64_t db_lo = db_hi + (uint32_t)(kTcBPart >> 4);
-          bool first = ky_lo == 0;      // the ky = 0 block of this window has not been written yet
           if (!(debug & 1)) {
 #pragma unroll
-            for (int term = 0; term < 3; ++term) {          // lo*hi, hi*lo, hi*hi
+            for (int term = 0; term < 3; ++term) {          // lo*hi, hi*lo, then hi*hi
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
@@ -337,20 +359,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                   const uint64_t da = (term == 0 ? da_lo : da_hi) + (uint32_t)((2 * ks * kTcPlane + kx * 16) >> 4);
                   const uint64_t db = (term == 1 ? db_lo : db_hi) +
                                       (uint32_t)((kx * (2 * kTcBPart) + 2 * ks * kTcBPlane) >> 4);
-                  if (term == 0 && kx == 0 && ks == 0 && first) {
-                    tc_mma(d_win, da, db, idesc0 | ((uint32_t)(kTcC >> 3) << 17), 0u);
-                    if (nky > 1)
-                      tc_mma(d_win + kTcC, da, db + (uint32_t)((kTcC * 16) >> 4),
-                             idesc0 | ((uint32_t)((nky - 1) * kTcC >> 3) << 17), 1u);
-                  } else {
-                    tc_mma(d_win, da, db, idesc_all, 1u);
-                  }
+                  tc_mma(d_win, da, db, idesc, (term == 0 && kx == 0 && ks == 0) ? 0u : 1u);
                 }
               }
             }
           }
           tc_commit(row_free + 8 * slot);                   // the ring slot may be refilled
-          if (i >= 2) tc_commit(acc_full + 8 * (buf * kTcRowBlock + i - 2));   // output row y0 + i - 2 is complete
+          tc_commit(acc_full + 8 * blk);                    // this row's contributions are complete
         }
       }
     }
@@ -359,44 +374,48 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     float bv[kTcC];
 #pragma unroll
     for (int c = 0; c < kTcC; ++c) bv[c] = bias != nullptr ? __ldg(bias + c) : 0.0f;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     uint32_t itemc = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++itemc) {
       const TcItem t = tc_item(item, xsegs, yblocks);
-      const uint32_t buf = itemc & 1;
       float* yn = y + (size_t)t.n * kTcC * plane + t.x0 + tid;
       for (int r = 0; r < kTcRowBlock; ++r) {
-        TC_PROF_WAIT(3, acc_full + 8 * (buf * kTcRowBlock + r), (itemc >> 1) & 1);
+        // output row r = staged rows r (tap 0), r + 1 (tap 1), r + 2 (tap 2); the MMA thread works
+        // in row order, so the block of row r + 2 being complete implies the other two
+        const uint32_t i2 = (uint32_t)r + 2, use2 = itemc * ((kTcRowBlock + 2) / kTcBlocks) + i2 / kTcBlocks;
+        TC_PROF_WAIT(3, acc_full + 8 * (i2 % kTcBlocks), use2 & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (debug & 32) {
-          if (r == kTcRowBlock - 1 && lane == 0) tc_mbar_arrive(acc_free + 8 * buf);
-          continue;
+        float o[kTcC];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                       // 16 channels at a time (register budget)
+          float v0[16], v1[16], v2[16];
+          if (!(debug & 32)) {
+            TC_LD16(v0, tmem + lane_base + ((uint32_t)r % kTcBlocks) * (3 * kTcC) + 16 * h);
+            TC_LD16(v1, tmem + lane_base + (((uint32_t)r + 1) % kTcBlocks) * (3 * kTcC) + kTcC + 16 * h);
+            TC_LD16(v2, tmem + lane_base + (i2 % kTcBlocks) * (3 * kTcC) + 2 * kTcC + 16 * h);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) o[16 * h + c] = (debug & 32) ? 0.0f : (v0[c] + v2[c]) + v1[c];
         }
-        uint32_t v[kTcC];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + buf * kTcAccCols +
-                               (uint32_t)(kTcRowBlock - 1 - r) * kTcC;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11,"
-            " %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28,"
-            " %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-              "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-              "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-              "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
-              "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (r == kTcRowBlock - 1) {                         // the item's columns may be overwritten
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) tc_mbar_arrive(acc_free + 8 * buf);
+        // staged row r is read for the last time here (the last row of an item also
+        // retires the two rows below it): their accumulator blocks may be overwritten
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tc_mbar_arrive(acc_free + 8 * ((uint32_t)r % kTcBlocks));
+          if (r == kTcRowBlock - 1) {
+            tc_mbar_arrive(acc_free + 8 * (((uint32_t)r + 1) % kTcBlocks));
+            tc_mbar_arrive(acc_free + 8 * (i2 % kTcBlocks));
+          }
         }
         float* dst = yn + (size_t)(t.y0 + r) * W;
 #pragma unroll
         for (int c = 0; c < kTcC; ++c) {
-          float o = __uint_as_float(v[c]) + bv[c];
-          if (slope > 0.0f) o = o > 0.0f ? o : o * slope;
+          float ov = o[c] + bv[c];
+          if (slope > 0.0f) ov = ov > 0.0f ? ov : ov * slope;
           if (!(debug & 4))
-            asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(dst + (size_t)c * plane), "f"(o)
+            asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(dst + (size_t)c * plane), "f"(ov)
                          : "memory");
         }
       }

@@ -894,13 +894,13 @@ def test_conv3x3_tc_matches_torch(shape):
     lin = torch.nn.functional.conv2d(x64, wt.double(), bias.double(), 1, 1)
     ref = torch.nn.functional.leaky_relu(lin, slope) if slope else lin
     got = conv.conv3x3_tc(x, wt, bias, slope)
-    assert orc.rel_l2(got.cpu().numpy(), ref.detach().cpu().numpy()) < 2e-6
+    assert orc.rel_l2(got.cpu().numpy(), ref.detach().cpu().numpy()) < 5e-7
     nob = conv.conv3x3_tc(x, wt, None, 0.0)
-    assert orc.rel_l2(nob.cpu().numpy(), (lin - bias.double().view(1, 32, 1, 1)).detach().cpu().numpy()) < 2e-6
+    assert orc.rel_l2(nob.cpu().numpy(), (lin - bias.double().view(1, 32, 1, 1)).detach().cpu().numpy()) < 5e-7
     gy = torch.randn(n, 32, h, w, device='cuda', generator=g)
     lin.backward(gy.double())
     gx = conv.conv3x3_tc(gy, wt, None, 0.0, transpose_flip=True)
-    assert orc.rel_l2(gx.cpu().numpy(), x64.grad.cpu().numpy()) < 2e-6
+    assert orc.rel_l2(gx.cpu().numpy(), x64.grad.cpu().numpy()) < 5e-7
     # cuDNN's fp32 kernels on the same operands, for scale (not a gate)
     prev = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
@@ -1118,8 +1118,12 @@ def test_1recnet_json_unchanged_on_gpu_matches_cpu_mirror_with_oracle_dc():
         # 1.8e-5 of its own norm) does not come from this library's kernels - the figure is
         # bit-for-bit the same with one- and two-level accumulation in csmri_conv3x3_wgrad -
         # but from cuDNN's fp32 convolution algorithms in forward / data gradient.
+        # (Single parameters scatter by a small factor either way between two correct fp32
+        # implementations: a pre-activation within rounding of 0 flips a LeakyReLU branch and
+        # with it a whole gradient path.  5x the fp32 CPU arm's own error bounds that scatter;
+        # the aggregate above is the tight criterion.)
         for eg, ec, nt, line in rows_:
-            assert eg < max(2.0 * ec, 3e-5 * max(nt, 5e-2 * scale)), (line, scale)
+            assert eg < max(5.0 * ec, 3e-5 * max(nt, 5e-2 * scale)), (line, scale)
         trainer, local_b = harness.recnet_trainer(conf, dev, rank=7, world=8)   # 2 of the 20 slices
         assert local_b == 2 and trainer.cuda_graph
         losses = [float(trainer.step(batch).item()) for _ in range(4)]

@@ -39,6 +39,14 @@ refinement_ops.refinement_real_penalty_add(t, learn, sc)['pred'].sum().backward(
 for ci, co, h, w, pad in ((32, 32, 8, 32, 1), (64, 32, 4, 64, 0), (2, 32, 16, 32, 1), (32, 2, 32, 64, 0)):
     conv.conv3x3_wgrad(torch.randn(2, ci, h + 2 - 2 * pad, w + 2 - 2 * pad, device=dev),
                        torch.randn(2, co, h, w, device=dev), pad)
+# tensor-core kernels (tcgen05): forward / data gradient and weight gradient of the 32 -> 32 layers
+xt = torch.randn(2, 32, 16, 128, device=dev)
+wt = torch.randn(32, 32, 3, 3, device=dev) * 0.1
+conv.conv3x3_tc(xt, wt, torch.randn(32, device=dev), 0.01)
+conv.conv3x3_tc(xt, wt, None, 0.0, transpose_flip=True)
+conv.conv3x3_wgrad(xt, torch.randn(2, 32, 16, 128, device=dev), 1)
+torch.cuda.synchronize()
+print('ok tensor-core convolutions')
 img = torch.rand(2, 32, 32, device=dev)
 rows = undersampling.cartesian_rows((2, 32, 32), 4, 8, False, np.random.RandomState(1))
 batch = undersampling.undersample(img, rows)

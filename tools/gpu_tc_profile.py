@@ -1,0 +1,40 @@
+"""The three tensor-core kernels of a 32 -> 32 RecNet layer at the D5C5 training shape
+(batch 32, 256 x 256), a few launches each - the target of `ncu -k regex:conv3x3.*tc`."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from csmri_refinement_b200 import conv  # noqa: E402
+
+dev = torch.device('cuda:0')
+n, h, w = (int(v) for v in (sys.argv[1:4] if len(sys.argv) > 3 else (32, 256, 256)))
+x = torch.randn(n, 32, h, w, device=dev)
+gy = torch.randn(n, 32, h, w, device=dev) * 0.05
+wt = torch.randn(32, 32, 3, 3, device=dev) * 0.08
+b = torch.randn(32, device=dev)
+for _ in range(3):
+    y = conv.conv3x3_tc(x, wt, b, 0.01)
+    gx = conv.conv3x3_tc(gy, wt, None, 0.0, transpose_flip=True)
+    dw = conv.conv3x3_wgrad(x, gy, 1)
+torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+ev[0].record()
+for _ in range(10):
+    y = conv.conv3x3_tc(x, wt, b, 0.01)
+ev[1].record()
+for _ in range(10):
+    gx = conv.conv3x3_tc(gy, wt, None, 0.0, transpose_flip=True)
+ev[2].record()
+for _ in range(10):
+    dw = conv.conv3x3_wgrad(x, gy, 1)
+ev[3].record()
+torch.cuda.synchronize()
+flop = 2.0 * 9 * 32 * 32 * n * h * w
+byt = 2.0 * x.numel() * 4
+for name, a, c in (('forward (bias + LeakyReLU fused)', 0, 1), ('data gradient', 1, 2), ('weight gradient', 2, 3)):
+    ms = ev[a].elapsed_time(ev[c]) / 10
+    print('%-34s %.3f ms  %.0f TFLOP/s fp32-equivalent  %.0f GB/s of operand traffic' % (
+        name, ms, flop / ms / 1e9, byt / ms / 1e6))
