@@ -24,12 +24,16 @@ def main():
         if os.path.exists(os.path.join(G, src)):
             shutil.copy(os.path.join(G, src), os.path.join(P, dst % R))
     rep = os.path.join(G, 'prof_final.ncu-rep')
-    if os.path.exists(rep):
-        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-        src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'],
-                             capture_output=True, text=True).stdout
-        open(os.path.join(G, 'raw_final.csv'), 'w').write(raw)
-        open(os.path.join(G, 'src_final.csv'), 'w').write(src)
+    have_csv = os.path.exists(os.path.join(G, 'raw_final.csv')) and os.path.exists(os.path.join(G, 'src_final.csv'))
+    if os.path.exists(rep) or have_csv:
+        if os.path.exists(rep):
+            raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+            src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'],
+                                 capture_output=True, text=True).stdout
+            open(os.path.join(G, 'raw_final.csv'), 'w').write(raw)
+            open(os.path.join(G, 'src_final.csv'), 'w').write(src)
+        else:       # the .ncu-rep (> 40 MB) stayed on the GPU box; its two CSV pages were exported there
+            raw = open(os.path.join(G, 'raw_final.csv')).read()
         out = ''
         for k in (0, 1):
             res = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ncu_summary.py'),
@@ -38,7 +42,7 @@ def main():
             out += res if k == 0 else res[res.index('==== source'):]
         open(os.path.join(P, '%s_strip_kernel_ncu_full.txt' % R), 'w').write(
             '# ncu --set full --clock-control none --import-source on -k regex:dc_strip_pipev -s 6 -c 2 '
-            'python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-recnet\n' + out)
+            'python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-recnet --no-refinement\n' + out)
         rows = list(csv.reader(raw.splitlines()))
         idx = {h: i for i, h in enumerate(rows[0])}
         tr = {}
@@ -65,8 +69,8 @@ def main():
                 name = re.sub(r'void at::.*', 'at:: RNG / elementwise kernel (synthetic data setup)', d['Kernel Name'])
                 out.append((d['ID'], name[:150], d['Block Size'], d['Grid Size'], d['Metric Value']))
         with open(os.path.join(P, '%s_launches_bench.csv' % R), 'w') as f:
-            f.write('# ncu --metrics gpu__time_duration.sum --clock-control none -c 200 python bench.py '
-                    '--steps 3 --warmup 3 --no-cpu-baseline --no-recnet\n# cold-cache, serialised launches: '
+            f.write('# ncu --metrics gpu__time_duration.sum --clock-control none -c 300 python bench.py '
+                    '--steps 3 --warmup 3 --no-cpu-baseline --no-recnet --no-refinement\n# cold-cache, serialised launches: '
                     'compare SHARES, not absolutes\nid,kernel,block,grid,duration_ns\n')
             for o in out:
                 f.write(','.join('"%s"' % x if ',' in x else x for x in o) + '\n')
@@ -77,7 +81,7 @@ def main():
             cnt[k] += 1
         tot = sum(agg.values())
         with open(os.path.join(P, '%s_launches_summary.txt' % R), 'w') as f:
-            f.write('share of summed kernel time over the first 200 launches of `bench.py --steps 3 --warmup 3` '
+            f.write('share of summed kernel time over the first 300 launches of `bench.py --steps 3 --warmup 3` '
                     '(setup, prepare, warm-up, timed steps, per-kernel timing loops)\n')
             for k, v in agg.most_common():
                 f.write('%-45s n=%3d %9.1f us %5.1f %%\n' % (k, cnt[k], v / 1e3, 100 * v / tot))
