@@ -1,14 +1,22 @@
-"""nn.Conv2d whose weight gradient runs through ``csmri_conv3x3_wgrad``.
+"""nn.Conv2d whose kernels come from libcsmri_dc.
 
 RecNet's convolutions (models/recnet.py:37-48) stay what they are in the
 reference - ``torch.nn.Conv2d`` modules with the same parameters, state-dict
-keys and forward arithmetic (cuDNN).  Only the backward-weight product of the
-fp32 training step (training/runner.py:154-178) is rerouted: cuDNN's kernel for
-these shapes is 64 % of the whole D5C5 step on a B200
-(profiles/r1_recnet_step_kernels.txt).  Covered: channel counts that are
-multiples of 32 on both sides, and RecNet's thin first / last layers (2 -> 32,
-32 -> 2).  Anything else (other kernel sizes, strides, dilations, CPU tensors)
-keeps torch's own backward.
+keys and forward values.  What runs underneath on a B200:
+
+* 32 -> 32 layers (zero padding 1, H % 8 == 0, W % 128 == 0): forward and data
+  gradient through ``csmri_conv3x3_tc``, weight gradient through
+  ``csmri_conv3x3_wgrad`` - the tcgen05 tensor cores with an error-compensated
+  TF32 split (fp32-level accuracy: rel-L2 against float64 2.6e-7 / 4.7e-7,
+  cuDNN's fp32 kernels 2.5e-7), bias + LeakyReLU fused into the forward kernel;
+* RecNet's thin first / last layers (2 -> 32, 32 -> 2): everything through
+  ``csmri_conv3x3_thin`` and the thin weight-gradient kernels;
+* other channel counts that are multiples of 32: cuDNN forward / data gradient,
+  the SIMT weight-gradient kernel (cuDNN's fp32 weight gradient was 64 % of the
+  D5C5 step, profiles/r1_recnet_step_kernels.txt) and the fused epilogues.
+
+Anything else (other kernel sizes, strides, dilations, channels_last, autocast,
+CPU tensors) keeps torch's own kernels.
 """
 import torch
 from torch import nn
@@ -163,9 +171,10 @@ def _is_thin(weight, pad):
 
 
 class _Conv3x3(torch.autograd.Function):
-    """conv (+ bias) [+ LeakyReLU when ``slope`` is given].  32k -> 32k layers:
-    forward and data gradient stay cuDNN, epilogues and the weight gradient run
-    through libcsmri_dc.  Thin layers (2 -> 32, 32 -> 2): everything does."""
+    """conv (+ bias) [+ LeakyReLU when ``slope`` is given].  32 -> 32 layers and the
+    thin layers (2 -> 32, 32 -> 2): everything runs through libcsmri_dc.  Other
+    32k -> 32k layers: forward and data gradient stay cuDNN, epilogues and the
+    weight gradient run through libcsmri_dc."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, pad, slope):

@@ -652,6 +652,29 @@ def test_integration_md_binding_runs_as_written():
             assert orc.rel_l2(xd.grad.cpu().numpy(), orc.dc_adjoint_np(w, mask, noise)) < TOL
 
 
+def test_integration_md_conv_binding_runs_as_written():
+    """The ctypes stub INTEGRATION.md shows for csmri_conv3x3_tc, executed verbatim on top
+    of the DC stub's definitions, against torch in float64."""
+    import re
+    from csmri_refinement_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    base = re.search(r'```python\n(# data/reconstruction/.*?)```', text, re.S).group(1)
+    base = base.replace("ctypes.CDLL('libcsmri_dc.so')", 'ctypes.CDLL(%r)' % _lib.LIB_PATH)
+    snippet = re.search(r'```python\n(_lib\.csmri_conv3x3_tc\.argtypes.*?)```', text, re.S).group(1)
+    ns = {}
+    exec(compile(base, 'INTEGRATION.md', 'exec'), ns)
+    exec(compile(snippet, 'INTEGRATION.md (conv)', 'exec'), ns)
+    g = torch.Generator(device='cuda').manual_seed(5)
+    x = torch.randn(2, 32, 16, 128, device='cuda', generator=g)
+    w = torch.randn(32, 32, 3, 3, device='cuda', generator=g) * 0.1
+    b = torch.randn(32, device='cuda', generator=g)
+    got = ns['conv32'](x, w, b, 0.01)
+    ref = torch.nn.functional.leaky_relu(
+        torch.nn.functional.conv2d(x.double(), w.double(), b.double(), 1, 1), 0.01)
+    assert orc.rel_l2(got.cpu().numpy(), ref.cpu().numpy()) < 5e-7
+
+
 def test_single_slice_and_second_device():
     """B=1 (fewer tiles than resident CTAs) and, when the box has one, a
     non-default device (per-device twiddle upload, scheduler slots, stream)."""
