@@ -160,6 +160,59 @@ def conv3x3_tc(x, weight, bias, slope=0.0, transpose_flip=False):
     return y
 
 
+def conv3x3_tc_signs(x, weight, bias, slope):
+    """``conv3x3_tc`` forward that also returns the sign word of every output pixel
+    ((N,H,W) int32, bit c = output channel c > 0) for :func:`conv3x3_tc_masked`."""
+    _require_cuda_f32(x, weight, bias)
+    x, weight = x.contiguous(), weight.contiguous()
+    n, c, h, w = x.shape
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x)
+        signs = torch.empty((n, h, w), dtype=torch.int32, device=x.device)
+        _lib.check(_lib.lib().csmri_conv3x3_tc_signs(
+            x.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
+            y.data_ptr(), signs.data_ptr(), n, c, h, w, float(slope),
+            torch.cuda.current_stream().cuda_stream))
+    return y, signs
+
+
+def conv3x3_tc_masked(x, weight, signs, act_slope, transpose_flip=True):
+    """``conv(x, weight)[:, c] * (bit c of signs ? 1 : act_slope)`` through
+    ``csmri_conv3x3_tc_masked``: with ``transpose_flip`` the data gradient of a 32 -> 32
+    layer followed by the backward of the LeakyReLU that produced that layer's input, whose
+    output signs :func:`conv3x3_tc_signs` recorded - in one pass."""
+    _require_cuda_f32(x, weight)
+    x, weight = x.contiguous(), weight.contiguous()
+    n, c, h, w = x.shape
+    if signs.dtype != torch.int32 or tuple(signs.shape) != (n, h, w) or not signs.is_cuda \
+            or not signs.is_contiguous():
+        raise RuntimeError('signs must be a contiguous CUDA int32 tensor of shape (N, H, W)')
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x)
+        _lib.check(_lib.lib().csmri_conv3x3_tc_masked(
+            x.data_ptr(), weight.data_ptr(), signs.data_ptr(), y.data_ptr(), n, c, h, w,
+            float(act_slope), int(bool(transpose_flip)), torch.cuda.current_stream().cuda_stream))
+    return y
+
+
+def conv3x3_wgrad_bias(x, grad_out):
+    """(dW, db) of a 32 -> 32 layer with zero padding 1 on the tensor-core path
+    (H % 16 == 0, W % 64 == 0): the bias gradient is a by-product of the kernel."""
+    _require_cuda_f32(x, grad_out)
+    x, grad_out = _aligned16(x.contiguous()), _aligned16(grad_out.contiguous())
+    n, _, h, w = grad_out.shape
+    lib = _lib.lib()
+    with torch.cuda.device(x.device):
+        dw = torch.empty((32, 32, 3, 3), dtype=torch.float32, device=x.device)
+        db = torch.empty((32,), dtype=torch.float32, device=x.device)
+        ws = torch.empty((lib.csmri_conv3x3_wgrad_workspace_bytes(32, 32) // 4,),
+                         dtype=torch.float32, device=x.device)
+        _lib.check(lib.csmri_conv3x3_wgrad_bias(
+            x.data_ptr(), grad_out.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), n, h, w,
+            torch.cuda.current_stream().cuda_stream))
+    return dw, db
+
+
 def _is_tc(x, weight, pad):
     """Shapes csmri_conv3x3_tc covers: 32 -> 32 channels, padding 1, H % 8 == 0, W % 128 == 0."""
     return (_TC_ENABLED and pad == 1 and tuple(weight.shape[:2]) == (32, 32) and
@@ -249,6 +302,89 @@ class _Conv3x3(torch.autograd.Function):
         elif need_w:
             gw = conv3x3_wgrad(x, grad_out, pad)
         return gx, gw, gb, None, None
+
+
+class _TcChain(torch.autograd.Function):
+    """A run of consecutive 32 -> 32 layers, each followed by LeakyReLU(slope), as ONE
+    autograd node (models/recnet.py:37-47: the inner layers of a ConvBlock).  Forward is
+    the fused conv + bias + LeakyReLU kernel per layer.  Backward applies the activation
+    derivative of layer k inside the data-gradient kernel of layer k + 1 (its saved input IS
+    that activation's output) and takes the bias gradients from the weight-gradient kernel,
+    so only the last layer of the run needs a LeakyReLU-backward pass of its own.  The
+    activation signs travel as one 32-bit word per pixel written by the forward kernel."""
+
+    @staticmethod
+    def forward(ctx, x, slope, *params):
+        ws, bs = params[0::2], params[1::2]
+        acts, signs = [x], []
+        for k, (w, b) in enumerate(zip(ws, bs)):
+            if k < len(ws) - 1:                 # the next layer's data gradient applies this mask
+                y, sg = conv3x3_tc_signs(acts[-1], w, b, slope)
+                signs.append(sg)
+            else:
+                y = conv3x3_tc(acts[-1], w, b, slope)
+            acts.append(y)
+        ctx.slope, ctx.n = slope, len(ws)
+        ctx.save_for_backward(*acts, *ws, *signs)
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        n, slope = ctx.n, ctx.slope
+        saved = ctx.saved_tensors
+        acts, ws, signs = saved[:n + 1], saved[n + 1:2 * n + 1], saved[2 * n + 1:]
+        grads = [None] * (2 * n)
+        # last layer: its activation's backward is a pass of its own (+ bias gradient)
+        gz, gb = bias_lrelu_backward(grad_out.contiguous(), acts[n], slope)
+        for k in range(n - 1, -1, -1):          # layer k: input acts[k], output acts[k + 1]
+            need_w, need_b = ctx.needs_input_grad[2 + 2 * k], ctx.needs_input_grad[3 + 2 * k]
+            if need_w and k < n - 1:
+                grads[2 * k], gb = conv3x3_wgrad_bias(acts[k], gz)
+            elif need_w:
+                grads[2 * k] = conv3x3_wgrad(acts[k], gz, 1)
+            elif need_b and k < n - 1:
+                gb = gz.sum(dim=(0, 2, 3))
+            if need_b:
+                grads[2 * k + 1] = gb
+            if k > 0:                           # data gradient + derivative of layer k - 1's activation
+                gz = conv3x3_tc_masked(gz, ws[k], signs[k - 1], slope)
+            elif ctx.needs_input_grad[0]:
+                gz = conv3x3_tc(gz, ws[0], None, 0.0, transpose_flip=True)
+            else:
+                gz = None
+        return (gz, None) + tuple(grads)
+
+
+def tc_chain_eligible(x, convs):
+    """True when every module of ``convs`` is a 32 -> 32 ``Conv2d`` with bias, padding 1
+    and the same fused LeakyReLU slope, and ``x`` has a shape both tensor-core kernels
+    cover (H % 16 == 0, W % 128 == 0)."""
+    if len(convs) < 2 or not (_ENABLED and _TC_ENABLED) or torch.is_autocast_enabled():
+        return False
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()):
+        return False
+    if x.shape[1] != 32 or x.shape[2] % 16 != 0 or x.shape[3] % 128 != 0:
+        return False
+    slope = convs[0].fused_slope
+    for m in convs:
+        if not isinstance(m, Conv2d) or m.bias is None or m.fused_slope is None or \
+                m.fused_slope != slope or not slope > 0:
+            return False
+        if tuple(m.weight.shape) != (32, 32, 3, 3) or m.padding_mode != 'zeros' or \
+                isinstance(m.padding, str) or tuple(m.padding) != (1, 1) or \
+                tuple(m.stride) != (1, 1) or tuple(m.dilation) != (1, 1) or m.groups != 1:
+            return False
+        if not (m.weight.is_contiguous() and m.weight.dtype == torch.float32):
+            return False
+    return True
+
+
+def tc_chain(x, convs):
+    """Run ``convs`` (see :func:`tc_chain_eligible`) as one fused autograd node."""
+    params = []
+    for m in convs:
+        params += [m.weight, m.bias]
+    return _TcChain.apply(x, float(convs[0].fused_slope), *params)
 
 
 class Conv2d(nn.Conv2d):

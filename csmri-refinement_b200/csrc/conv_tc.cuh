@@ -48,8 +48,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// The tuning probes (tools/conv_tc_probe.cu, tools/wgrad_tc_probe.cu) compile the kernels with
+// CSMRI_TC_PROBE=1: `debug` bits then skip roles / record clock64 accounting.  In the library the
+// checks fold away (the kernels are instruction-cache sensitive: 12-14 warps run different code).
+#ifndef CSMRI_TC_PROBE
+#define CSMRI_TC_PROBE 0
+#endif
+
 namespace csmri {
 
+constexpr bool kTcProbe = CSMRI_TC_PROBE != 0;
 constexpr int kTcC = 32;                 // channels in and out
 constexpr int kTcM = 128;                // pixels per tile (one row segment)
 constexpr int kTcPA = 136;               // staged pixels per row slot (130 used), 16-byte units
@@ -105,6 +113,13 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+// one lane of a converged warp; everything around the guarded instructions stays warp-uniform,
+// which lets the compiler keep descriptors and barrier addresses in uniform registers
+__device__ __forceinline__ bool tc_elect() {
+  uint32_t p;
+  asm volatile("{ .reg .pred q; elect.sync _|q, 0xffffffff; selp.u32 %0, 1, 0, q; }" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ float tc_tf32(float v) {     // round to nearest TF32, as a float
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -124,7 +139,7 @@ __device__ __forceinline__ void tc_split(float v, float& hi, float& lo) {
 __device__ long long tc_prof[8];
 #define TC_PROF_WAIT(slot_, bar_, par_)                                   \
   do {                                                                    \
-    if (debug & 128) {                                                    \
+    if (kTcProbe && (debug & 128)) {                                                    \
       const long long t0_ = clock64();                                    \
       tc_mbar_wait(bar_, par_);                                           \
       prof[slot_] += clock64() - t0_;                                     \
@@ -168,15 +183,25 @@ __device__ __forceinline__ TcItem tc_item(int item, int xsegs, int yblocks) {
 // (the data gradient of the same layer).  H % kTcRowBlock == 0, W % 128 == 0.
 // `debug` (tuning probes only): bit 0 skip the MMAs, bit 1 skip the global loads,
 // bit 2 skip the global stores.
+// `signs` (N,H,W) uint32, bit c of a pixel = (output channel c > 0):
+// MASKED = false: optional OUTPUT of the forward pass (one 4-byte store per pixel);
+// MASKED = true (the data gradient feeding a LeakyReLU layer): no bias, no activation, and
+// the result is multiplied by the derivative of that LeakyReLU, (bit c ? 1 : slope), read from
+// the `signs` its forward pass wrote - the backward pass of the activation
+// (models/recnet.py:45-47: nn.LeakyReLU after every inner convolution) costs a 4-byte load
+// per pixel here instead of a read-read-write pass over 32 channels of its own.
+template <bool MASKED>
 __global__ void __launch_bounds__(kTcThreads, 1)
     conv3x3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                      const float* __restrict__ bias, float* __restrict__ y, int H, int W, int nitems,
+                      const float* __restrict__ bias, float* __restrict__ y, uint32_t* __restrict__ signs,
+                      int H, int W, int nitems,
                       float slope, int transpose_flip, int debug) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   unsigned char* B_s = tc_smem;                       // [kx][hi | lo][ci/4][ky co 0-95][ci%4]
   unsigned char* A_s = tc_smem + kTcBBytes;           // [slot][hi | lo][ci/4][pixel][ci%4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + kTcBBytes + kTcABytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  float* bias_s = reinterpret_cast<float*>(bars + 34);      // [32] the layer's bias (zeros without one)
   const uint32_t row_full = tc_s32(&bars[0]);         // [4] producers -> MMA
   const uint32_t row_free = tc_s32(&bars[4]);         // [4] MMA -> producers
   const uint32_t acc_free = tc_s32(&bars[8]);         // [5] epilogue -> MMA (one per accumulator block)
@@ -199,6 +224,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < kTcC) bias_s[tid] = (!MASKED && bias != nullptr) ? __ldg(bias + tid) : 0.0f;
   if (warp == kTcMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
                      tc_s32(tmem_slot))
@@ -237,7 +263,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     float v[kTcC], vn[kTcC];
     auto fetch = [&](float* dst) {
       const int gy = t.y0 - 1 + r;
-      const bool ok = item < nitems && gy >= 0 && gy < H && !(debug & 2);
+      const bool ok = item < nitems && gy >= 0 && gy < H && !(kTcProbe && (debug & 2));
       const float* src = x + ((size_t)t.n * kTcC * H + (ok ? gy : 0)) * W + t.x0 + j;
 #pragma unroll
       for (int c = 0; c < kTcC; ++c) dst[c] = ok ? __ldg(src + (size_t)c * plane) : 0.0f;
@@ -256,7 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       TC_PROF_WAIT(0, row_free + 8 * slot, ((q >> 2) & 1) ^ 1);
       unsigned char* hi_s = A_s + (size_t)slot * 2 * kTcSlotPart + (j + 1) * 16;
       unsigned char* lo_s = hi_s + kTcSlotPart;
-      if (!(debug & 16)) {
+      if (!(kTcProbe && (debug & 16))) {
 #pragma unroll
         for (int kc = 0; kc < 8; ++kc) {
           float4 h, l;
@@ -270,7 +296,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       // every thread publishes its own stores to the async proxy, then ONE lane per warp
       // arrives (an arrival per thread is serialised on the barrier word)
-      if (!(debug & 8)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (!(kTcProbe && (debug & 8))) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(row_full + 8 * slot);
       q += 2;
@@ -287,7 +313,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     float a0, a1, n0, n1;
     auto fetch = [&](float& o0, float& o1) {
       const int gy = t.y0 - 1 + r, gx = side ? t.x0 + kTcM : t.x0 - 1;
-      const bool ok = item < nitems && gy >= 0 && gy < H && gx >= 0 && gx < W && !(debug & 2);
+      const bool ok = item < nitems && gy >= 0 && gy < H && gx >= 0 && gx < W && !(kTcProbe && (debug & 2));
       const float* src = x + (((size_t)t.n * kTcC + c0) * H + (ok ? gy : 0)) * W + (ok ? gx : 0);
       o0 = ok ? __ldg(src) : 0.0f;
       o1 = ok ? __ldg(src + plane) : 0.0f;
@@ -318,8 +344,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       a1 = n1;
     }
   } else if (warp == kTcMmaWarp) {
-    // ===== MMA issuer: one elected thread =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop (uniform control flow), one elected lane issues =====
+    const bool leader = tc_elect();
+    {
       // D fp32, A / B tf32, both K-major, M = 128, N = 32 x (vertical taps in the window)
       const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcM >> 4) << 24);
       const uint64_t da_base = tc_desc(tc_s32(A_s), kTcPlane, 128);
@@ -348,7 +375,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const uint64_t da_lo = da_hi + (uint32_t)(kTcSlotPart >> 4);
           const uint64_t db_hi = db_base + (uint32_t)((ky_lo * kTcC * 16) >> 4);
           const uint64_t db_lo = db_hi + (uint32_t)(kTcBPart >> 4);
-          if (!(debug & 1)) {
+          if (leader && !(kTcProbe && (debug & 1))) {
 #pragma unroll
             for (int term = 0; term < 3; ++term) {          // lo*hi, hi*lo, then hi*hi
 #pragma unroll
@@ -364,64 +391,91 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               }
             }
           }
-          tc_commit(row_free + 8 * slot);                   // the ring slot may be refilled
-          tc_commit(acc_full + 8 * blk);                    // this row's contributions are complete
+          if (leader) {
+            tc_commit(row_free + 8 * slot);                 // the ring slot may be refilled
+            tc_commit(acc_full + 8 * blk);                  // this row's contributions are complete
+          }
+          __syncwarp();
         }
       }
     }
   } else {
     // ===== epilogue: warp e owns TMEM lanes 32e .. 32e + 31 = pixels of the segment =====
-    float bv[kTcC];
-#pragma unroll
-    for (int c = 0; c < kTcC; ++c) bv[c] = bias != nullptr ? __ldg(bias + c) : 0.0f;
+    uint32_t positive = 0u;         // bit c = (output channel c of this pixel > 0)
+    uint32_t sign_next = 0u;        // MASKED only: the sign word of the NEXT row, in flight
+    if (MASKED && blockIdx.x < nitems) {
+      const TcItem t0 = tc_item(blockIdx.x, xsegs, yblocks);
+      sign_next = __ldg(signs + ((size_t)t0.n * H + t0.y0) * W + t0.x0 + tid);
+    }
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     uint32_t itemc = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++itemc) {
       const TcItem t = tc_item(item, xsegs, yblocks);
       float* yn = y + (size_t)t.n * kTcC * plane + t.x0 + tid;
       for (int r = 0; r < kTcRowBlock; ++r) {
+        if (MASKED) {
+          // this row's sign word was requested one row ago; request the next one (same item,
+          // or the first row of this CTA's next item)
+          positive = sign_next;
+          size_t nx = ((size_t)t.n * H + (t.y0 + r + 1)) * W + t.x0 + tid;
+          bool more = true;
+          if (r == kTcRowBlock - 1) {
+            const int nitem = item + gridDim.x;
+            more = nitem < nitems;
+            const TcItem tn = tc_item(more ? nitem : item, xsegs, yblocks);
+            nx = ((size_t)tn.n * H + tn.y0) * W + tn.x0 + tid;
+          }
+          if (more) sign_next = __ldg(signs + nx);
+        }
         // output row r = staged rows r (tap 0), r + 1 (tap 1), r + 2 (tap 2); the MMA thread works
         // in row order, so the block of row r + 2 being complete implies the other two
         const uint32_t i2 = (uint32_t)r + 2, use2 = itemc * ((kTcRowBlock + 2) / kTcBlocks) + i2 / kTcBlocks;
         TC_PROF_WAIT(3, acc_full + 8 * (i2 % kTcBlocks), use2 & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float o[kTcC];
+        float* dst = yn + (size_t)(t.y0 + r) * W;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {                       // 16 channels at a time (register budget)
           float v0[16], v1[16], v2[16];
-          if (!(debug & 32)) {
+          if (!(kTcProbe && (debug & 32))) {
             TC_LD16(v0, tmem + lane_base + ((uint32_t)r % kTcBlocks) * (3 * kTcC) + 16 * h);
             TC_LD16(v1, tmem + lane_base + (((uint32_t)r + 1) % kTcBlocks) * (3 * kTcC) + kTcC + 16 * h);
             TC_LD16(v2, tmem + lane_base + (i2 % kTcBlocks) * (3 * kTcC) + 2 * kTcC + 16 * h);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           }
+          if (h == 1) {
+            // staged row r is read for the last time here (the last row of an item also
+            // retires the two rows below it): their accumulator blocks may be overwritten
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tc_mbar_arrive(acc_free + 8 * ((uint32_t)r % kTcBlocks));
+              if (r == kTcRowBlock - 1) {
+                tc_mbar_arrive(acc_free + 8 * (((uint32_t)r + 1) % kTcBlocks));
+                tc_mbar_arrive(acc_free + 8 * (i2 % kTcBlocks));
+              }
+            }
+          }
 #pragma unroll
-          for (int c = 0; c < 16; ++c) o[16 * h + c] = (debug & 32) ? 0.0f : (v0[c] + v2[c]) + v1[c];
-        }
-        // staged row r is read for the last time here (the last row of an item also
-        // retires the two rows below it): their accumulator blocks may be overwritten
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          tc_mbar_arrive(acc_free + 8 * ((uint32_t)r % kTcBlocks));
-          if (r == kTcRowBlock - 1) {
-            tc_mbar_arrive(acc_free + 8 * (((uint32_t)r + 1) % kTcBlocks));
-            tc_mbar_arrive(acc_free + 8 * (i2 % kTcBlocks));
+          for (int c = 0; c < 16; ++c) {
+            const float o = (kTcProbe && (debug & 32)) ? 0.0f : (v0[c] + v2[c]) + v1[c];
+            float ov;
+            if (MASKED) {
+              ov = ((positive >> (16 * h + c)) & 1u) ? o : o * slope;
+            } else {
+              ov = o + bias_s[16 * h + c];
+              positive = (h == 0 && c == 0 ? 0u : positive) | ((ov > 0.0f ? 1u : 0u) << (16 * h + c));
+              if (slope > 0.0f) ov = ov > 0.0f ? ov : ov * slope;
+            }
+            if (!(kTcProbe && (debug & 4)))
+              asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(dst + (size_t)(16 * h + c) * plane), "f"(ov)
+                           : "memory");
           }
         }
-        float* dst = yn + (size_t)(t.y0 + r) * W;
-#pragma unroll
-        for (int c = 0; c < kTcC; ++c) {
-          float ov = o[c] + bv[c];
-          if (slope > 0.0f) ov = ov > 0.0f ? ov : ov * slope;
-          if (!(debug & 4))
-            asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(dst + (size_t)c * plane), "f"(ov)
-                         : "memory");
-        }
+        if (!MASKED && signs != nullptr) signs[((size_t)t.n * H + (t.y0 + r)) * W + t.x0 + tid] = positive;
       }
     }
   }
-  if ((debug & 128) && blockIdx.x == 0) {
+  if ((kTcProbe && (debug & 128)) && blockIdx.x == 0) {
     if (tid == 128) tc_prof[0] = prof[0];                      // producer group 0: waiting for a free ring slot
     if (tid == kTcMmaWarp * 32) { tc_prof[1] = prof[1]; tc_prof[2] = prof[2]; tc_prof[5] = clock64() - t_start; }
     if (tid == 0) tc_prof[3] = prof[3];                        // epilogue: waiting for a finished row

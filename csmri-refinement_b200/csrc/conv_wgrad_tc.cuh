@@ -110,10 +110,11 @@ __device__ __forceinline__ WtcItem wtc_item(int item, int xsegs, int yblocks) {
 // as hi (columns 0-63 of the buffer) and lo (columns 64-127).  Half a segment at a time (32 pixels of
 // the row + the one pixel the shift pulls in from the neighbouring half or the halo) to stay inside
 // the register budget of a 448-thread CTA.
-template <int KX>
-__device__ __forceinline__ void wtc_stage_dy(const unsigned char* dy_slot, int co, float halo, uint32_t tmem_a) {
+template <int KX, bool BIAS>
+__device__ __forceinline__ float wtc_stage_dy(const unsigned char* dy_slot, int co, float halo, uint32_t tmem_a) {
   const unsigned char* row = dy_slot + co * 128;
   const int sw = co & 7;
+  float rowsum = 0.0f;            // KX == 1 only: sum of this channel's 64 dy values (bias gradient)
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float c[32];
@@ -124,6 +125,12 @@ __device__ __forceinline__ void wtc_stage_dy(const unsigned char* dy_slot, int c
       c[4 * k + 1] = q.y;
       c[4 * k + 2] = q.z;
       c[4 * k + 3] = q.w;
+    }
+    if (KX == 1 && BIAS) {
+      float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int p = 0; p < 32; ++p) s4[p & 3] += c[p];
+      rowsum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
     }
     float edge = halo;            // KX = 0: pixel 32 half + 32; KX = 2: pixel 32 half - 1
     if (KX == 0 && half == 0) edge = *reinterpret_cast<const float*>(row + kWtcBox + ((0 ^ sw) << 4));
@@ -139,15 +146,18 @@ __device__ __forceinline__ void wtc_stage_dy(const unsigned char* dy_slot, int c
     WTC_ST32(tmem_a + kWtcPx + 32 * half, lo);
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  return rowsum;
 }
 
 // x, dy: (N, 32, H, W) fp32 as 3-D tensor maps {W, H, N * 32}, box {32, 1, 32}, 128-byte swizzle.
 // H % kWtcRows == 0, W % kWtcPx == 0.  partial: gridDim.x blocks of 96 x 96 floats,
 // [(kx, co)][(ky, ci)].  dy_ptr: the same dy tensor, for the two halo pixels of a segment.
+// bias_partial (may be null): gridDim.x x 32 floats, the per-CTA sums of dy over all pixels
+// (the bias gradient of the layer, a by-product of the kx = 1 staging warp reading every dy value).
 __global__ void __launch_bounds__(kWtcThreads, 1)
     conv3x3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
-                            const float* __restrict__ dy_ptr, float* __restrict__ partial, int H, int W, int nitems,
-                            int debug) {
+                            const float* __restrict__ dy_ptr, float* __restrict__ partial,
+                            float* __restrict__ bias_partial, int H, int W, int nitems, int debug) {
   extern __shared__ unsigned char wtc_smem_raw[];
   // 128-byte-swizzled boxes are anchored at 1024-byte boundaries
   unsigned char* smem = wtc_smem_raw + ((1024u - (tc_s32(wtc_smem_raw) & 1023u)) & 1023u);
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
         const uint32_t slot = qx % kWtcRing, use = qx / kWtcRing;
         tc_mbar_wait(x_free + 8 * slot, (use & 1) ^ 1);
         const bool mirror = slot < 2;
-        if (debug & 8) {
+        if (kTcProbe && (debug & 8)) {
           tc_mbar_arrive(x_full + 8 * slot);
           ++qx;
           return;
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
           load_x(t, j + 2);
           const uint32_t slot = qd % kWtcDySlots, use = qd / kWtcDySlots;
           tc_mbar_wait(dy_free + 8 * slot, (use & 1) ^ 1);
-          if (debug & 8) {
+          if (kTcProbe && (debug & 8)) {
             tc_mbar_arrive(dy_full + 8 * slot);
             continue;
           }
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
         const uint32_t slot = qx % kWtcRing, use = qx / kWtcRing;
         TC_PROF_WAIT(0, x_full + 8 * slot, use & 1);
 #pragma unroll
-        for (int k = 0; k < ((debug & 4) ? 0 : 8); ++k) {
+        for (int k = 0; k < ((kTcProbe && (debug & 4)) ? 0 : 8); ++k) {
           const int chunk = s + 64 * k;                      // 512 16-byte chunks: 2 atoms x 256
           const int off = (chunk >> 8) * kWtcXAtom + slot * kWtcBox + (chunk & 255) * 16;
           const float4 v = *reinterpret_cast<const float4*>(X_hi + off);
@@ -276,8 +286,10 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
     const uint32_t lane_base = (uint32_t)(kx * 32) << 16;
     const size_t plane = (size_t)H * W;
     uint32_t sc = 0;                                          // steps staged so far
+    float bsum = 0.0f;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const WtcItem t = wtc_item(item, xsegs, yblocks);
+      float isum = 0.0f;                                      // two-level sum: segment -> item -> CTA
       const int hx = kx == 0 ? t.x0 + kWtcPx : t.x0 - 1;
       const bool has_halo = kx != 1 && hx >= 0 && hx < W;
       const float* hp = dy_ptr + ((size_t)t.n * kWtcC + co) * plane + (size_t)t.y0 * W + (has_halo ? hx : 0);
@@ -289,22 +301,25 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
         TC_PROF_WAIT(0, step_done + 8 * buf, ((sc >> 1) & 1) ^ 1);
         TC_PROF_WAIT(1, dy_full + 8 * slot, (sc / kWtcDySlots) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const long long ts0 = (debug & 128) ? clock64() : 0;
+        const long long ts0 = (kTcProbe && (debug & 128)) ? clock64() : 0;
         const unsigned char* src = DY_s + slot * 2 * kWtcBox;
         const uint32_t ta = tmem + lane_base + 256 + buf * 128;
-        if (debug & 1) {
-        } else if (kx == 0) wtc_stage_dy<0>(src, co, halo, ta);
-        else if (kx == 1) wtc_stage_dy<1>(src, co, halo, ta);
-        else wtc_stage_dy<2>(src, co, halo, ta);
+        if (kTcProbe && (debug & 1)) {
+        } else if (kx == 0) wtc_stage_dy<0, false>(src, co, halo, ta);
+        else if (kx == 1 && bias_partial != nullptr) isum += wtc_stage_dy<1, true>(src, co, halo, ta);
+        else if (kx == 1) wtc_stage_dy<1, false>(src, co, halo, ta);
+        else wtc_stage_dy<2, false>(src, co, halo, ta);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
           tc_mbar_arrive(a_full + 8 * buf);
           tc_mbar_arrive(dy_free + 8 * slot);
         }
-        if (debug & 128) prof[2] += clock64() - ts0;
+        if (kTcProbe && (debug & 128)) prof[2] += clock64() - ts0;
       }
+      bsum += isum;
     }
+    if (kx == 1 && bias_partial != nullptr) bias_partial[blockIdx.x * kWtcC + co] = bsum;
   } else if (warp >= kWtcMmaWarp) {
     // ===== MMA issuers: warp 10 issues the even steps, warp 11 the odd ones =====
     // The instruction queue of the tensor core is shallow and one thread needs ~500 cycles per
@@ -337,9 +352,9 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
         ready(st, 0);
         ready(st, 1);
         ready(st, 2);
-        const long long tf0 = (debug & 128) ? clock64() : 0;
-        if (!(debug & 32)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const long long ti0 = (debug & 128) ? clock64() : 0;
+        const long long tf0 = (kTcProbe && (debug & 128)) ? clock64() : 0;
+        if (!(kTcProbe && (debug & 32))) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long ti0 = (kTcProbe && (debug & 128)) ? clock64() : 0;
         t_fence += ti0 - tf0;
         const uint32_t it = st / kWtcRows, j = st - it * kWtcRows, qb = it * (kWtcRows + 2);
         const uint32_t wslot = (qb + j) % kWtcRing;           // window = slots wslot .. wslot + 2
@@ -348,26 +363,26 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint32_t boff = (uint32_t)(((ks >> 2) * kWtcXAtom + wslot * kWtcBox + (ks & 3) * 32) >> 4);
-          if (!(debug & 16)) {
+          if (!(kTcProbe && (debug & 16))) {
             wtc_mma_ts(d_tmem, a_tmem + kWtcPx + 8 * ks, db_hi0 + boff, idesc, ks == 0 ? 0u : 1u);   // lo * hi
             wtc_mma_ts(d_tmem, a_tmem + 8 * ks, db_lo0 + boff, idesc, 1u);                            // hi * lo
             wtc_mma_ts(d_tmem, a_tmem + 8 * ks, db_hi0 + boff, idesc, 1u);                            // hi * hi
           }
         }
-        const long long ti1 = (debug & 128) ? clock64() : 0;
+        const long long ti1 = (kTcProbe && (debug & 128)) ? clock64() : 0;
         tc_commit(step_done + 8 * (st & 1));                   // A buffer free, accumulator ready to drain
         tc_commit(x_free + 8 * wslot);                         // input row j of the item is not needed again
         if (j == kWtcRows - 1) {
           tc_commit(x_free + 8 * ((qb + j + 1) % kWtcRing));
           tc_commit(x_free + 8 * ((qb + j + 2) % kWtcRing));
         }
-        if (debug & 128) {
+        if (kTcProbe && (debug & 128)) {
           prof[3] += ti1 - ti0;                               // issuing the 24 instructions
           t_commit += clock64() - ti1;                        // issuing the commits
         }
       }
-      if ((debug & 128) && blockIdx.x == 0 && par == 0) { tc_prof[7] = t_commit; tc_prof[2] = t_fence; }
-      if ((debug & 128) && par == 0 && blockIdx.x < 256) wtc_cta_cycles[blockIdx.x] = clock64() - t_start;
+      if ((kTcProbe && (debug & 128)) && blockIdx.x == 0 && par == 0) { tc_prof[7] = t_commit; tc_prof[2] = t_fence; }
+      if ((kTcProbe && (debug & 128)) && par == 0 && blockIdx.x < 256) wtc_cta_cycles[blockIdx.x] = clock64() - t_start;
     }
   } else if (warp < 4) {
     // ===== drain: warp w owns TMEM lanes 32 w .. 32 w + 31; lanes 96-127 are never written =====
@@ -381,7 +396,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
         const uint32_t dbuf = period & 1;
         tc_mbar_wait(step_done + 8 * dbuf, (period >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (debug & 2) {
+        if (kTcProbe && (debug & 2)) {
           __syncwarp();
           if (lane == 0) tc_mbar_arrive(d_free + 8 * dbuf);
           continue;
@@ -408,7 +423,7 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
         *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
     }
   }
-  if ((debug & 128) && blockIdx.x == 0) {
+  if ((kTcProbe && (debug & 128)) && blockIdx.x == 0) {
     if (tid == 192) { tc_prof[0] = prof[0]; tc_prof[1] = prof[1]; tc_prof[6] = prof[2]; }   // staging warp kx = 2
     if (tid == kWtcMmaWarp * 32) { tc_prof[3] = prof[0]; tc_prof[4] = prof[1]; tc_prof[5] = prof[2]; }
   }
@@ -417,11 +432,21 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
   if (warp == kWtcMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-// dw[co][ci][ky][kx] = sum over CTAs, in CTA order, of partial[cta][(kx, co)][(ky, ci)]
+// dw[co][ci][ky][kx] = sum over CTAs, in CTA order, of partial[cta][(kx, co)][(ky, ci)];
+// db[co] (optional) = sum over CTAs of bias_partial[cta][co]
 __global__ void __launch_bounds__(128)
-    conv3x3_wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nctas) {
-  const int e = blockIdx.x * 128 + threadIdx.x;                // (kx, co, ky, ci)
-  if (e >= kWtcPartial) return;
+    conv3x3_wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                   const float* __restrict__ bias_partial, float* __restrict__ db, int nctas) {
+  const int e = blockIdx.x * 128 + threadIdx.x;                // (kx, co, ky, ci), then 32 bias entries
+  if (e >= kWtcPartial) {
+    const int co = e - kWtcPartial;
+    if (co < kWtcC && db != nullptr) {
+      float s = 0.0f;
+      for (int c = 0; c < nctas; ++c) s += bias_partial[c * kWtcC + co];
+      db[co] = s;
+    }
+    return;
+  }
   float s = 0.0f;
   for (int c = 0; c < nctas; ++c) s += partial[(size_t)c * kWtcPartial + e];
   const int row = e / 96, col = e - row * 96;

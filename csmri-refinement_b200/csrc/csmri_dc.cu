@@ -1584,8 +1584,26 @@ size_t csmri_conv3x3_wgrad_workspace_bytes(int CI, int CO) {
          sizeof(float);
 }
 
+static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float* db, void* workspace, int N,
+                              int CI, int CO, int H, int W, int pad, void* stream);
+
 int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* workspace, int N, int CI,
                         int CO, int H, int W, int pad, void* stream) {
+  return conv3x3_wgrad_impl(x, dy, dw, nullptr, workspace, N, CI, CO, H, W, pad, stream);
+}
+
+int csmri_conv3x3_wgrad_bias(const float* x, const float* dy, float* dw, float* db, void* workspace,
+                             int N, int H, int W, void* stream) {
+  CSMRI_TRY(check_ptr(db, "db"));
+  if (!g_wgrad_tc || H % kWtcRows != 0 || W % kWtcPx != 0 || ((uintptr_t)x & 15u) != 0)
+    return fail(CSMRI_E_SHAPE,
+                "conv3x3_wgrad_bias is the tensor-core path only: H %% %d == 0, W %% %d == 0, x 16-byte "
+                "aligned (got %dx%dx%d)", kWtcRows, kWtcPx, N, H, W);
+  return conv3x3_wgrad_impl(x, dy, dw, db, workspace, N, kWtcC, kWtcC, H, W, 1, stream);
+}
+
+static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float* db, void* workspace, int N,
+                              int CI, int CO, int H, int W, int pad, void* stream) {
   CSMRI_TRY(wgrad_check_channels(CI, CO));
   const bool thin = wgrad_thin(CI, CO);
   const int th = thin ? kWtRows : kWgTH;
@@ -1653,13 +1671,15 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
     if (ctas > kWgMaxCtas) ctas = kWgMaxCtas;
     if (ctas > nitems) ctas = nitems;
     CSMRI_TRY(set_smem(conv3x3_wgrad_tc_kernel, kWtcSmemBytes));
+    float* bias_partial = db != nullptr ? (float*)workspace + (size_t)ctas * kWtcPartial : nullptr;
     conv3x3_wgrad_tc_kernel<<<ctas, kWtcThreads, kWtcSmemBytes, s>>>(tm_x, tm_dy, dy, (float*)workspace,
-                                                                     H, W, nitems, 0);
-    conv3x3_wgrad_tc_reduce_kernel<<<(kWtcPartial + 127) / 128, 128, 0, s>>>((const float*)workspace, dw,
-                                                                             ctas);
+                                                                     bias_partial, H, W, nitems, 0);
+    conv3x3_wgrad_tc_reduce_kernel<<<(kWtcPartial + kWtcC + 127) / 128, 128, 0, s>>>(
+        (const float*)workspace, dw, bias_partial, db, ctas);
     CSMRI_CUDA(cudaGetLastError());
     return CSMRI_OK;
   }
+  if (db != nullptr) return fail(CSMRI_E_SHAPE, "conv3x3_wgrad_bias: shape not covered by the tensor-core path");
   constexpr int smem = kWgSmemFloats * (int)sizeof(float);
   const dim3 grid(parts, CO / kWgC, CI / kWgC);
   if (g_wgrad_cot == 8) {
@@ -1712,8 +1732,9 @@ int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float*
 }
 
 // ---- 32 -> 32 convolution on the tensor cores, 3xTF32 (conv_tc.cuh) -------------
-int csmri_conv3x3_tc(const float* x, const float* w, const float* bias, float* y, int N, int C,
-                     int H, int W, float slope, int transpose_flip, void* stream) {
+static int conv3x3_tc_launch(const float* x, const float* w, const float* bias, float* y, unsigned* signs,
+                             int N, int C, int H, int W, float slope, int transpose_flip, bool masked,
+                             void* stream) {
   if (C != kTcC) return fail(CSMRI_E_SHAPE, "conv3x3_tc handles %d -> %d channels (got %d)", kTcC, kTcC, C);
   if (N <= 0 || H <= 0 || W <= 0 || H % kTcRowBlock != 0 || W % kTcM != 0)
     return fail(CSMRI_E_SHAPE, "conv3x3_tc needs H %% %d == 0 and W %% %d == 0 (got %dx%dx%d)",
@@ -1722,16 +1743,40 @@ int csmri_conv3x3_tc(const float* x, const float* w, const float* bias, float* y
   CSMRI_TRY(check_ptr(x, "x"));
   CSMRI_TRY(check_ptr(w, "w"));
   CSMRI_TRY(check_ptr(y, "y"));
+  if (masked) CSMRI_TRY(check_ptr(signs, "signs"));
   if (x == y) return fail(CSMRI_E_ARG, "y must not alias x");
   const long long nitems_ll = (long long)N * (W / kTcM) * (H / kTcRowBlock);
   if (nitems_ll > 0x7fffffffLL) return fail(CSMRI_E_SHAPE, "too many tiles");
-  CSMRI_TRY(set_smem(conv3x3_tc_kernel, kTcSmemBytes));
   int grid = sm_count();
   if (grid > nitems_ll) grid = (int)nitems_ll;
-  conv3x3_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(
-      x, w, bias, y, H, W, (int)nitems_ll, slope, transpose_flip != 0, g_tc_debug);
+  if (masked) {
+    CSMRI_TRY(set_smem(conv3x3_tc_kernel<true>, kTcSmemBytes));
+    conv3x3_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(
+        x, w, nullptr, y, signs, H, W, (int)nitems_ll, slope, transpose_flip != 0, g_tc_debug);
+  } else {
+    CSMRI_TRY(set_smem(conv3x3_tc_kernel<false>, kTcSmemBytes));
+    conv3x3_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(
+        x, w, bias, y, signs, H, W, (int)nitems_ll, slope, transpose_flip != 0, g_tc_debug);
+  }
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
+}
+
+int csmri_conv3x3_tc(const float* x, const float* w, const float* bias, float* y, int N, int C,
+                     int H, int W, float slope, int transpose_flip, void* stream) {
+  return conv3x3_tc_launch(x, w, bias, y, nullptr, N, C, H, W, slope, transpose_flip, false, stream);
+}
+
+int csmri_conv3x3_tc_signs(const float* x, const float* w, const float* bias, float* y, unsigned* signs,
+                           int N, int C, int H, int W, float slope, void* stream) {
+  CSMRI_TRY(check_ptr(signs, "signs"));
+  return conv3x3_tc_launch(x, w, bias, y, signs, N, C, H, W, slope, 0, false, stream);
+}
+
+int csmri_conv3x3_tc_masked(const float* x, const float* w, const unsigned* signs, float* y, int N,
+                            int C, int H, int W, float act_slope, int transpose_flip, void* stream) {
+  return conv3x3_tc_launch(x, w, nullptr, y, const_cast<unsigned*>(signs), N, C, H, W, act_slope,
+                           transpose_flip, true, stream);
 }
 
 // ---- bias + LeakyReLU epilogue of the convolutions (conv_epilogue.cuh) ---------

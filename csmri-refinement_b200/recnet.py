@@ -96,6 +96,21 @@ class ConvBlock(nn.Module):
                     nn.init.constant_(m.bias.data, 0.0)
 
     def forward(self, x):
+        # the run of 32 -> 32 layers in the middle of the block as one autograd node (the
+        # LeakyReLU derivatives ride on the data-gradient kernels); same values, same
+        # parameters - anything the fused node does not cover takes the plain Sequential
+        mods = list(self.layers)
+        convs = [m for m in mods if isinstance(m, nn.Conv2d)]
+        inner = convs[1:-1]
+        if torch.is_grad_enabled() and len(inner) >= 2 and all(
+                isinstance(m, (nn.Conv2d, nn.Identity)) for m in mods) and convs[0].fused_slope is not None:
+            from . import conv as _conv
+            y = convs[0](x)
+            if _conv.tc_chain_eligible(y, inner):
+                return convs[-1](_conv.tc_chain(y, inner))
+            for m in inner:
+                y = m(y)
+            return convs[-1](y)
         return self.layers(x)
 
 

@@ -236,6 +236,13 @@ int csmri_refine_real_penalty_add_backward(const float* grad_pred, const float* 
 size_t csmri_conv3x3_wgrad_workspace_bytes(int CI, int CO);
 int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* workspace,
                         int N, int CI, int CO, int H, int W, int pad, void* stream);
+/* 32 -> 32 channels, zero padding 1, H % 16 == 0, W % 64 == 0 (the tensor-core path of
+ * the call above): the same dw plus the bias gradient of the layer,
+ *   db[co] = sum_{n,y,x} dy[n][co][y][x]        (what autograd computes for `bias`),
+ * a by-product of the kernel reading every dy value once; db (32), overwritten.  Same
+ * workspace.  Other shapes are CSMRI_E_SHAPE. */
+int csmri_conv3x3_wgrad_bias(const float* x, const float* dy, float* dw, float* db, void* workspace,
+                             int N, int H, int W, void* stream);
 
 /* RecNet's thin 3x3 convolutions (first / last layer of a block, models/recnet.py:
  * 45-48), stride 1, zero padding 1:  y = act(conv(x, w) + bias)
@@ -259,6 +266,19 @@ int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float*
  * own convolution backend for those shapes). */
 int csmri_conv3x3_tc(const float* x, const float* w, const float* bias, float* y,
                      int N, int C, int H, int W, float slope, int transpose_flip, void* stream);
+/* The forward form of the call above that also records the sign of every output:
+ *   signs (N,H,W) uint32, bit c of a pixel = (y[n][c][h][w] > 0)   (4 bytes per pixel). */
+int csmri_conv3x3_tc_signs(const float* x, const float* w, const float* bias, float* y, unsigned* signs,
+                           int N, int C, int H, int W, float slope, void* stream);
+/* The same convolution without bias / activation, its result multiplied by the derivative
+ * of the LeakyReLU that produced its consumer's input:
+ *   y[n][c] = conv(x, wq)[n][c] * (bit c of signs[n] ? 1 : act_slope)
+ * With transpose_flip = 1 this is "data gradient of layer L+1, then backward of the
+ * nn.LeakyReLU(relu_leakiness) between layer L and L+1" (models/recnet.py:45-47) in one
+ * pass: signs is what csmri_conv3x3_tc_signs wrote in layer L's forward pass. */
+int csmri_conv3x3_tc_masked(const float* x, const float* w, const unsigned* signs, float* y,
+                            int N, int C, int H, int W, float act_slope, int transpose_flip,
+                            void* stream);
 
 /* Bias + LeakyReLU after a convolution (models/recnet.py:45-48: Conv2d(bias=True)
  * followed by nn.LeakyReLU(relu_leakiness, inplace=True)), fused into one pass:

@@ -940,6 +940,64 @@ def test_conv3x3_tc_matches_torch(shape):
         conv.conv3x3_tc(torch.zeros(1, 32, 8, 192, device='cuda'), wt, bias, slope)    # W % 128 != 0
 
 
+def test_fused_leaky_relu_backward_and_bias_gradient_on_the_tensor_core_path():
+    """csmri_conv3x3_tc_masked (data gradient x LeakyReLU derivative in one pass) and
+    csmri_conv3x3_wgrad_bias (bias gradient as a by-product of the weight-gradient kernel)
+    against torch in float64, and the fused chain node (conv._TcChain) against the same
+    three layers run module by module: values and every gradient."""
+    from csmri_refinement_b200 import conv
+    g = torch.Generator(device='cuda').manual_seed(77)
+    n, h, w, slope = 2, 32, 128, 0.01
+    gz = torch.randn(n, 32, h, w, device='cuda', generator=g)
+    wt = torch.randn(32, 32, 3, 3, device='cuda', generator=g) * 0.08
+    xa = torch.randn(n, 32, h, w, device='cuda', generator=g)
+    ba = torch.randn(32, device='cuda', generator=g)
+    act, signs = conv.conv3x3_tc_signs(xa, wt, ba, slope)    # forward that records the output signs
+    assert torch.equal(act, conv.conv3x3_tc(xa, wt, ba, slope))
+    bits = ((signs.unsqueeze(1) >> torch.arange(32, device='cuda').view(1, 32, 1, 1)) & 1).bool()
+    assert torch.equal(bits, act > 0)                        # exact zeros would take the `slope` branch
+    want = torch.nn.functional.conv_transpose2d(gz.double(), wt.double(), None, 1, 1) * \
+        torch.where(act > 0, 1.0, slope).double()
+    got = conv.conv3x3_tc_masked(gz, wt, signs, slope)
+    assert orc.rel_l2(got.cpu().numpy(), want.cpu().numpy()) < 5e-7
+    x = torch.randn(n, 32, h, w, device='cuda', generator=g)
+    w64 = wt.double().requires_grad_(True)
+    b64 = torch.zeros(32, device='cuda', dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(x.double(), w64, b64, 1, 1).backward(gz.double())
+    dw, db = conv.conv3x3_wgrad_bias(x, gz)
+    assert orc.rel_l2(dw.cpu().numpy(), w64.grad.cpu().numpy()) < 2e-6
+    assert orc.rel_l2(db.cpu().numpy(), b64.grad.cpu().numpy()) < 2e-6
+    assert torch.equal(db, conv.conv3x3_wgrad_bias(x, gz)[1])
+    with pytest.raises(RuntimeError):
+        conv.conv3x3_wgrad_bias(x[:, :, :8].contiguous(), gz[:, :, :8].contiguous())   # H % 16 != 0
+    # the chain node vs the same modules one by one
+    torch.manual_seed(5)
+    mods = [conv.Conv2d(32, 32, 3, padding=1).cuda() for _ in range(3)]
+    for m in mods:
+        m.fused_slope = slope
+        torch.nn.init.normal_(m.bias, std=0.1)
+    xin = torch.randn(n, 32, h, w, device='cuda', generator=g)
+    seed = torch.randn(n, 32, h, w, device='cuda', generator=g)
+    res = []
+    for fused in (True, False):
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        xi = xin.clone().requires_grad_(True)
+        assert conv.tc_chain_eligible(xi, mods)
+        if fused:
+            y = conv.tc_chain(xi, mods)
+        else:
+            y = xi
+            for m in mods:
+                y = m(y)
+        (y * seed).sum().backward()
+        res.append([y.detach(), xi.grad] + [p.grad for m in mods for p in (m.weight, m.bias)])
+    assert torch.equal(res[0][0], res[1][0])                 # same forward kernels
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert (a - b).norm().item() <= 2e-6 * b.norm().item()
+    assert not conv.tc_chain_eligible(xin[:, :, :, :64].contiguous(), mods)
+
+
 def test_recnet_training_gradients_with_tensor_core_convs():
     """RecNet nf=32 at a width the tensor-core kernel covers (128): output, loss and
     every parameter gradient with the tcgen05 forward / data-gradient kernels against

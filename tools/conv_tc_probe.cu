@@ -1,5 +1,6 @@
 // Standalone check + timing of csrc/conv_tc.cuh (tcgen05 3xTF32 32->32 convolution).
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I csmri-refinement_b200/csrc -o tools/conv_tc_probe tools/conv_tc_probe.cu
+#define CSMRI_TC_PROBE 1
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -24,11 +25,11 @@ static void reference(const std::vector<float>& x, const std::vector<float>& w, 
 
 static int launch(const float* x, const float* w, const float* b, float* y, int N, int H, int W, float slope, int tf, int debug = 0) {
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes); attr = true; }
+  if (!attr) { cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes); attr = true; }
   int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int nitems = N * (W / kTcM) * (H / kTcRowBlock);
   const int grid = nitems < sms ? nitems : sms;
-  conv3x3_tc_kernel<<<grid, kTcThreads, kTcSmemBytes>>>(x, w, b, y, H, W, nitems, slope, tf, debug);
+  conv3x3_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes>>>(x, w, b, y, nullptr, H, W, nitems, slope, tf, debug);
   return 0;
 }
 

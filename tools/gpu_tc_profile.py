@@ -20,7 +20,12 @@ for _ in range(3):
     gx = conv.conv3x3_tc(gy, wt, None, 0.0, transpose_flip=True)
     dw = conv.conv3x3_wgrad(x, gy, 1)
 torch.cuda.synchronize()
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+act, sg = conv.conv3x3_tc_signs(x, wt, b, 0.01)
+for _ in range(3):
+    gm = conv.conv3x3_tc_masked(gy, wt, sg, 0.01)
+    dwb = conv.conv3x3_wgrad_bias(x, gy)
+torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
 ev[0].record()
 for _ in range(10):
     y = conv.conv3x3_tc(x, wt, b, 0.01)
@@ -31,10 +36,17 @@ ev[2].record()
 for _ in range(10):
     dw = conv.conv3x3_wgrad(x, gy, 1)
 ev[3].record()
+for _ in range(10):
+    gm = conv.conv3x3_tc_masked(gy, wt, sg, 0.01)
+ev[4].record()
+for _ in range(10):
+    dwb = conv.conv3x3_wgrad_bias(x, gy)
+ev[5].record()
 torch.cuda.synchronize()
 flop = 2.0 * 9 * 32 * 32 * n * h * w
 byt = 2.0 * x.numel() * 4
-for name, a, c in (('forward (bias + LeakyReLU fused)', 0, 1), ('data gradient', 1, 2), ('weight gradient', 2, 3)):
+for name, a, c in (('forward (bias + LeakyReLU fused)', 0, 1), ('data gradient', 1, 2), ('weight gradient', 2, 3),
+                   ('data gradient x LeakyReLU derivative', 3, 4), ('weight + bias gradient', 4, 5)):
     ms = ev[a].elapsed_time(ev[c]) / 10
-    print('%-34s %.3f ms  %.0f TFLOP/s fp32-equivalent  %.0f GB/s of operand traffic' % (
+    print('%-38s %.3f ms  %.0f TFLOP/s fp32-equivalent  %.0f GB/s of operand traffic' % (
         name, ms, flop / ms / 1e9, byt / ms / 1e6))

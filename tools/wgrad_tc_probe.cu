@@ -1,5 +1,6 @@
 // Standalone check + timing of csrc/conv_wgrad_tc.cuh (tcgen05 weight gradient, 32 -> 32 channels).
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I csmri-refinement_b200/csrc -o tools/wgrad_tc_probe tools/wgrad_tc_probe.cu
+#define CSMRI_TC_PROBE 1
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -40,8 +41,8 @@ static void launch(const float* x, const float* dy, float* dw, float* ws, int N,
   make_map(&td, dy, N, H, W);
   const int nitems = N * (W / kWtcPx) * (H / kWtcRows);
   const int grid = nitems < g_sms ? nitems : g_sms;
-  conv3x3_wgrad_tc_kernel<<<grid, kWtcThreads, kWtcSmemBytes>>>(tx, td, dy, ws, H, W, nitems, debug);
-  conv3x3_wgrad_tc_reduce_kernel<<<(kWtcPartial + 127) / 128, 128>>>(ws, dw, grid);
+  conv3x3_wgrad_tc_kernel<<<grid, kWtcThreads, kWtcSmemBytes>>>(tx, td, dy, ws, nullptr, H, W, nitems, debug);
+  conv3x3_wgrad_tc_reduce_kernel<<<(kWtcPartial + 127) / 128, 128>>>(ws, dw, nullptr, nullptr, grid);
 }
 
 int main() {
