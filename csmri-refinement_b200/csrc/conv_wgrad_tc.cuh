@@ -326,8 +326,11 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
     // step for its barrier waits, fence and commits - time in which the pipe would run dry.
     // Even and odd steps use disjoint accumulator and A buffers, so two threads can issue them
     // independently: the bookkeeping of one overlaps the instructions of the other.
+    // Each warp runs its loop with uniform control flow and one elected lane issues (descriptors
+    // and barrier addresses then live in uniform registers).
     const uint32_t par = warp - kWtcMmaWarp;
-    if (lane == 0 && blockIdx.x < nitems) {
+    const bool leader = tc_elect();
+    if (blockIdx.x < nitems) {
       // D fp32, A / B tf32, K-major, M = 128, N = 96
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // 128-byte swizzle, 8-row groups 1024 bytes apart
@@ -363,26 +366,29 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint32_t boff = (uint32_t)(((ks >> 2) * kWtcXAtom + wslot * kWtcBox + (ks & 3) * 32) >> 4);
-          if (!(kTcProbe && (debug & 16))) {
+          if (leader && !(kTcProbe && (debug & 16))) {
             wtc_mma_ts(d_tmem, a_tmem + kWtcPx + 8 * ks, db_hi0 + boff, idesc, ks == 0 ? 0u : 1u);   // lo * hi
             wtc_mma_ts(d_tmem, a_tmem + 8 * ks, db_lo0 + boff, idesc, 1u);                            // hi * lo
             wtc_mma_ts(d_tmem, a_tmem + 8 * ks, db_hi0 + boff, idesc, 1u);                            // hi * hi
           }
         }
         const long long ti1 = (kTcProbe && (debug & 128)) ? clock64() : 0;
-        tc_commit(step_done + 8 * (st & 1));                   // A buffer free, accumulator ready to drain
-        tc_commit(x_free + 8 * wslot);                         // input row j of the item is not needed again
-        if (j == kWtcRows - 1) {
-          tc_commit(x_free + 8 * ((qb + j + 1) % kWtcRing));
-          tc_commit(x_free + 8 * ((qb + j + 2) % kWtcRing));
+        if (leader) {
+          tc_commit(step_done + 8 * (st & 1));                 // A buffer free, accumulator ready to drain
+          tc_commit(x_free + 8 * wslot);                       // input row j of the item is not needed again
+          if (j == kWtcRows - 1) {
+            tc_commit(x_free + 8 * ((qb + j + 1) % kWtcRing));
+            tc_commit(x_free + 8 * ((qb + j + 2) % kWtcRing));
+          }
         }
+        __syncwarp();
         if (kTcProbe && (debug & 128)) {
           prof[3] += ti1 - ti0;                               // issuing the 24 instructions
           t_commit += clock64() - ti1;                        // issuing the commits
         }
       }
-      if ((kTcProbe && (debug & 128)) && blockIdx.x == 0 && par == 0) { tc_prof[7] = t_commit; tc_prof[2] = t_fence; }
-      if ((kTcProbe && (debug & 128)) && par == 0 && blockIdx.x < 256) wtc_cta_cycles[blockIdx.x] = clock64() - t_start;
+      if ((kTcProbe && (debug & 128)) && lane == 0 && blockIdx.x == 0 && par == 0) { tc_prof[7] = t_commit; tc_prof[2] = t_fence; }
+      if ((kTcProbe && (debug & 128)) && lane == 0 && par == 0 && blockIdx.x < 256) wtc_cta_cycles[blockIdx.x] = clock64() - t_start;
     }
   } else if (warp < 4) {
     // ===== drain: warp w owns TMEM lanes 32 w .. 32 w + 31; lanes 96-127 are never written =====
