@@ -72,8 +72,8 @@ constexpr int kTcBlocks = 5;                        // accumulator blocks of 96 
 static_assert((kTcRowBlock + 2) % kTcBlocks == 0, "the block of a staged row must not depend on the item");
 constexpr int kTcABytes = kTcSlots * 2 * kTcSlotPart;
 constexpr int kTcSmemBytes = kTcBBytes + kTcABytes + 512;
-constexpr int kTcThreads = 448;          // 4 epilogue warps, 2 x 4 producer warps, 1 halo warp, 1 MMA warp
-constexpr int kTcMmaWarp = 13;
+constexpr int kTcThreads = 480;          // 4 epilogue warps, 2 x 4 producer warps, 1 halo warp, 2 MMA warps
+constexpr int kTcMmaWarp = 13;           // and 14
 
 __device__ __forceinline__ uint32_t tc_s32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -343,17 +343,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       a0 = n0;
       a1 = n1;
     }
-  } else if (warp == kTcMmaWarp) {
-    // ===== MMA issuer: the whole warp runs the loop (uniform control flow), one elected lane issues =====
+  } else if (warp >= kTcMmaWarp) {
+    // ===== MMA issuers: warp 13 issues the even staged rows, warp 14 the odd ones.  Every row
+    // has an accumulator block, a ring slot and barriers of its own, so the two are independent;
+    // one thread alone needs ~500 cycles per row for waits, fence and commits, during which the
+    // (shallow) instruction queue of the tensor core would run dry.  Each warp runs its loop
+    // with uniform control flow, one elected lane issues. =====
     const bool leader = tc_elect();
+    const uint32_t par = warp - kTcMmaWarp;
     {
       // D fp32, A / B tf32, both K-major, M = 128, N = 32 x (vertical taps in the window)
       const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcM >> 4) << 24);
       const uint64_t da_base = tc_desc(tc_s32(A_s), kTcPlane, 128);
       const uint64_t db_base = tc_desc(tc_s32(B_s), kTcBPlane, 128);
-      uint32_t q = 0, itemc = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++itemc) {
-        for (int i = 0; i < kTcRowBlock + 2; ++i, ++q) {
+      const uint32_t total = blockIdx.x < nitems
+                                 ? (uint32_t)((nitems - blockIdx.x + gridDim.x - 1) / gridDim.x) * (kTcRowBlock + 2)
+                                 : 0u;
+      for (uint32_t q = par; q < total; q += 2) {
+        {
+          const uint32_t itemc = q / (kTcRowBlock + 2);
+          const int i = (int)(q - itemc * (kTcRowBlock + 2));
           // staged row i is image row y0 - 1 + i; it feeds output row y0 + i - ky through vertical
           // tap ky, and only the taps ky_lo .. ky_hi land inside this item.  The row gets a FRESH
           // accumulator block (i % 5; the first instruction overwrites it): column group ky of
@@ -427,10 +436,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           }
           if (more) sign_next = __ldg(signs + nx);
         }
-        // output row r = staged rows r (tap 0), r + 1 (tap 1), r + 2 (tap 2); the MMA thread works
-        // in row order, so the block of row r + 2 being complete implies the other two
-        const uint32_t i2 = (uint32_t)r + 2, use2 = itemc * ((kTcRowBlock + 2) / kTcBlocks) + i2 / kTcBlocks;
-        TC_PROF_WAIT(3, acc_full + 8 * (i2 % kTcBlocks), use2 & 1);
+        // output row r = staged rows r (tap 0), r + 1 (tap 1), r + 2 (tap 2), issued by two
+        // independent threads: wait for all three blocks (the first two are normally long done)
+        const uint32_t i2 = (uint32_t)r + 2;
+#pragma unroll
+        for (uint32_t k = 0; k < 3; ++k) {
+          const uint32_t ik = (uint32_t)r + k, usek = itemc * ((kTcRowBlock + 2) / kTcBlocks) + ik / kTcBlocks;
+          TC_PROF_WAIT(3, acc_full + 8 * (ik % kTcBlocks), usek & 1);
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* dst = yn + (size_t)(t.y0 + r) * W;
 #pragma unroll
@@ -477,7 +490,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
   if ((kTcProbe && (debug & 128)) && blockIdx.x == 0) {
     if (tid == 128) tc_prof[0] = prof[0];                      // producer group 0: waiting for a free ring slot
-    if (tid == kTcMmaWarp * 32) { tc_prof[1] = prof[1]; tc_prof[2] = prof[2]; tc_prof[5] = clock64() - t_start; }
+    if (tid == kTcMmaWarp * 32) { tc_prof[1] = 2 * prof[1]; tc_prof[2] = 2 * prof[2]; tc_prof[5] = clock64() - t_start; }
     if (tid == 0) tc_prof[3] = prof[3];                        // epilogue: waiting for a finished row
   }
   // ---- teardown ------------------------------------------------------------------
