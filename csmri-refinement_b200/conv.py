@@ -219,6 +219,28 @@ def _is_tc(x, weight, pad):
             x.shape[2] % 8 == 0 and x.shape[3] % 128 == 0)
 
 
+def conv3x3_thin_masked(x, weight, signs, act_slope):
+    """2 -> 32 thin convolution (no bias) times the LeakyReLU derivative selected by
+    ``signs`` ((N,H,W) int32 from :func:`conv3x3_tc_signs`): the data gradient of RecNet's
+    32 -> 2 layer (``weight`` = its weights flipped and transposed) and the backward of the
+    activation in front of it, in one pass."""
+    _require_cuda_f32(x, weight)
+    x, weight = x.contiguous(), weight.contiguous()
+    n, a, h, w = x.shape
+    if a != 2 or tuple(weight.shape) != (32, 2, 3, 3):
+        raise RuntimeError('conv3x3_thin_masked is the 2 -> 32 form (got %s, %s)'
+                           % (tuple(x.shape), tuple(weight.shape)))
+    if signs.dtype != torch.int32 or tuple(signs.shape) != (n, h, w) or not signs.is_cuda \
+            or not signs.is_contiguous():
+        raise RuntimeError('signs must be a contiguous CUDA int32 tensor of shape (N, H, W)')
+    with torch.cuda.device(x.device):
+        y = torch.empty((n, 32, h, w), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().csmri_conv3x3_thin_masked(
+            x.data_ptr(), weight.data_ptr(), signs.data_ptr(), y.data_ptr(), n, h, w,
+            float(act_slope), torch.cuda.current_stream().cuda_stream))
+    return y
+
+
 def _is_thin(weight, pad):
     return pad == 1 and (weight.shape[1], weight.shape[0]) in ((2, 32), (32, 2))
 
@@ -230,7 +252,10 @@ class _Conv3x3(torch.autograd.Function):
     weight gradient run through libcsmri_dc."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, pad, slope):
+    def forward(ctx, x, weight, bias, pad, slope, in_signs=None, in_slope=0.0):
+        # in_signs (thin 32 -> 2 layer only): sign words of x, the output of a LeakyReLU whose
+        # producer (_TcChain) expects its incoming gradient already multiplied by the derivative
+        ctx.in_signs, ctx.in_slope = in_signs, in_slope
         ctx.pad, ctx.slope = pad, slope
         ctx.has_bias = bias is not None
         ctx.thin = _is_thin(weight, pad) and (slope is None or weight.shape[1] == 2)
@@ -278,7 +303,10 @@ class _Conv3x3(torch.autograd.Function):
         if ctx.thin:
             if need_b and gb is None:
                 gb = grad_out.sum(dim=(0, 2, 3))
-            if need_x:     # the same kernel family on flipped, transposed weights
+            if need_x and ctx.in_signs is not None:
+                gx = conv3x3_thin_masked(grad_out, weight.flip(2, 3).transpose(0, 1), ctx.in_signs,
+                                         ctx.in_slope)
+            elif need_x:   # the same kernel family on flipped, transposed weights
                 gx = conv3x3_thin(grad_out, weight.flip(2, 3).transpose(0, 1), None, 0.0)
         elif ctx.tc:
             if need_b and gb is None:
@@ -301,7 +329,7 @@ class _Conv3x3(torch.autograd.Function):
             grad_out.record_stream(side)
         elif need_w:
             gw = conv3x3_wgrad(x, grad_out, pad)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None, None
 
 
 class _TcChain(torch.autograd.Function):
@@ -314,35 +342,39 @@ class _TcChain(torch.autograd.Function):
     activation signs travel as one 32-bit word per pixel written by the forward kernel."""
 
     @staticmethod
-    def forward(ctx, x, slope, *params):
+    def forward(ctx, x, slope, out_premasked, *params):
+        # out_premasked: the consumer of the output promises to multiply the gradient it sends
+        # back by the last activation's derivative (it gets the sign words for that)
         ws, bs = params[0::2], params[1::2]
         acts, signs = [x], []
         for k, (w, b) in enumerate(zip(ws, bs)):
-            if k < len(ws) - 1:                 # the next layer's data gradient applies this mask
-                y, sg = conv3x3_tc_signs(acts[-1], w, b, slope)
-                signs.append(sg)
-            else:
-                y = conv3x3_tc(acts[-1], w, b, slope)
+            y, sg = conv3x3_tc_signs(acts[-1], w, b, slope)
+            signs.append(sg)
             acts.append(y)
-        ctx.slope, ctx.n = slope, len(ws)
-        ctx.save_for_backward(*acts, *ws, *signs)
-        return acts[-1]
+        ctx.slope, ctx.n, ctx.out_premasked = slope, len(ws), bool(out_premasked)
+        ctx.save_for_backward(*acts, *ws, *signs[:-1])
+        ctx.mark_non_differentiable(signs[-1])
+        return acts[-1], signs[-1]
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_out, _grad_signs):
         n, slope = ctx.n, ctx.slope
         saved = ctx.saved_tensors
         acts, ws, signs = saved[:n + 1], saved[n + 1:2 * n + 1], saved[2 * n + 1:]
         grads = [None] * (2 * n)
-        # last layer: its activation's backward is a pass of its own (+ bias gradient)
-        gz, gb = bias_lrelu_backward(grad_out.contiguous(), acts[n], slope)
+        if ctx.out_premasked:                   # the consumer applied the last activation's derivative
+            gz, gb, have_gb = grad_out.contiguous(), None, False
+        else:                                   # a pass of its own (+ bias gradient)
+            gz, gb = bias_lrelu_backward(grad_out.contiguous(), acts[n], slope)
+            have_gb = True
         for k in range(n - 1, -1, -1):          # layer k: input acts[k], output acts[k + 1]
-            need_w, need_b = ctx.needs_input_grad[2 + 2 * k], ctx.needs_input_grad[3 + 2 * k]
-            if need_w and k < n - 1:
+            need_w, need_b = ctx.needs_input_grad[3 + 2 * k], ctx.needs_input_grad[4 + 2 * k]
+            fresh = k < n - 1 or not have_gb    # gb of this layer not known yet
+            if need_w and fresh:
                 grads[2 * k], gb = conv3x3_wgrad_bias(acts[k], gz)
             elif need_w:
                 grads[2 * k] = conv3x3_wgrad(acts[k], gz, 1)
-            elif need_b and k < n - 1:
+            elif need_b and fresh:
                 gb = gz.sum(dim=(0, 2, 3))
             if need_b:
                 grads[2 * k + 1] = gb
@@ -352,7 +384,7 @@ class _TcChain(torch.autograd.Function):
                 gz = conv3x3_tc(gz, ws[0], None, 0.0, transpose_flip=True)
             else:
                 gz = None
-        return (gz, None) + tuple(grads)
+        return (gz, None, None) + tuple(grads)
 
 
 def tc_chain_eligible(x, convs):
@@ -379,12 +411,26 @@ def tc_chain_eligible(x, convs):
     return True
 
 
-def tc_chain(x, convs):
-    """Run ``convs`` (see :func:`tc_chain_eligible`) as one fused autograd node."""
+def tc_chain(x, convs, last=None):
+    """Run ``convs`` (see :func:`tc_chain_eligible`) as one fused autograd node.  ``last``
+    (optional): the 32 -> 2 ``Conv2d`` that consumes the result - if it is the plain thin
+    layer (padding 1, bias, no activation) it is applied too, and its data gradient carries
+    the derivative of the run's last LeakyReLU (no separate pass for it either)."""
     params = []
     for m in convs:
         params += [m.weight, m.bias]
-    return _TcChain.apply(x, float(convs[0].fused_slope), *params)
+    slope = float(convs[0].fused_slope)
+    fuse_last = last is not None and isinstance(last, Conv2d) and last.fused_slope is None and \
+        last.bias is not None and tuple(last.weight.shape) == (2, 32, 3, 3) and \
+        last.padding_mode == 'zeros' and not isinstance(last.padding, str) and \
+        tuple(last.padding) == (1, 1) and tuple(last.stride) == (1, 1) and \
+        tuple(last.dilation) == (1, 1) and last.groups == 1 and last.weight.is_contiguous()
+    y, signs = _TcChain.apply(x, slope, fuse_last, *params)
+    if last is None:
+        return y
+    if fuse_last:
+        return _Conv3x3.apply(y, last.weight, last.bias, 1, None, signs, slope)
+    return last(y)
 
 
 class Conv2d(nn.Conv2d):

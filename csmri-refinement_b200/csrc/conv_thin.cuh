@@ -84,7 +84,11 @@ __device__ __forceinline__ ThinTile thin_tile(int tile, int tiles_x, int tiles_y
 __global__ void __launch_bounds__(256, 2)
     conv3x3_thin_out_kernel(const float* __restrict__ x, const float* __restrict__ w,
                             const float* __restrict__ bias, float* __restrict__ y, int H, int W,
-                            int tiles_x, int tiles_y, int ntiles, float slope) {
+                            int tiles_x, int tiles_y, int ntiles, float slope,
+                            const unsigned* __restrict__ msigns, float mslope) {
+  // msigns (optional; (N,H,W) uint32 sign words, see csmri_conv3x3_tc_signs): the result of
+  // channel c is multiplied by (bit c ? 1 : mslope) - this kernel as the data gradient of the
+  // 32 -> 2 layer, followed by the backward of the LeakyReLU in front of that layer
   constexpr int A = 2, B = 32, BT = 4, R = kThinOutRows;
   constexpr int kBuf = kThinLead + A * (R + 2) * kThinPC;
   __shared__ __align__(16) float stage[2][kBuf];
@@ -127,6 +131,7 @@ __global__ void __launch_bounds__(256, 2)
     __syncthreads();
     const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
     float* yn = y + ((size_t)t.n * B + cob) * plane + (size_t)t.y0 * W + t.x0 + lane;
+    const unsigned* sg = msigns != nullptr ? msigns + ((size_t)t.n * H + t.y0) * W + t.x0 + lane : nullptr;
     float win[A][3][3];
 #pragma unroll
     for (int c = 0; c < A; ++c)
@@ -158,11 +163,17 @@ __global__ void __launch_bounds__(256, 2)
             for (int o = 0; o < BT / 2; ++o)
               acc[o] = f2fma(wp[c][ky * 3 + kx][o], mk(win[c][ky][kx], win[c][ky][kx]), acc[o]);
 #pragma unroll
+      const unsigned bits = sg != nullptr ? __ldg(sg + (size_t)r * W) >> cob : 0xffffffffu;
+#pragma unroll
       for (int o = 0; o < BT / 2; ++o) {
         float a = acc[o].x, b = acc[o].y;
         if (slope > 0.0f) {
           a = a > 0.0f ? a : a * slope;
           b = b > 0.0f ? b : b * slope;
+        }
+        if (sg != nullptr) {
+          a = ((bits >> (2 * o)) & 1u) ? a : a * mslope;
+          b = ((bits >> (2 * o + 1)) & 1u) ? b : b * mslope;
         }
         yn[(size_t)(2 * o) * plane + (size_t)r * W] = a;
         yn[(size_t)(2 * o + 1) * plane + (size_t)r * W] = b;

@@ -1699,8 +1699,9 @@ static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float*
   return CSMRI_OK;
 }
 
-int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float* y, int N, int A,
-                       int B, int H, int W, float slope, void* stream) {
+static int conv3x3_thin_impl(const float* x, const float* w, const float* bias, float* y, int N, int A,
+                             int B, int H, int W, float slope, const unsigned* msigns, float mslope,
+                             void* stream) {
   if (!wgrad_thin(A, B))
     return fail(CSMRI_E_SHAPE, "conv3x3_thin handles 2 -> 32 and 32 -> 2 channels (got %d -> %d)", A, B);
   if (N <= 0 || H <= 0 || W <= 0 || H % kThinOutRows != 0 || W % 32 != 0)
@@ -1721,7 +1722,7 @@ int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float*
   cudaStream_t s = (cudaStream_t)stream;
   if (A == 2) {
     conv3x3_thin_out_kernel<<<ctas, 256, 0, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
-                                                 (int)ntiles_ll, slope);
+                                                 (int)ntiles_ll, slope, msigns, mslope);
   } else {
     CSMRI_TRY(set_smem(conv3x3_thin_in_kernel, kThinInSmem));
     conv3x3_thin_in_kernel<<<ctas, 256, kThinInSmem, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
@@ -1729,6 +1730,18 @@ int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float*
   }
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
+}
+
+int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float* y, int N, int A,
+                       int B, int H, int W, float slope, void* stream) {
+  return conv3x3_thin_impl(x, w, bias, y, N, A, B, H, W, slope, nullptr, 0.0f, stream);
+}
+
+int csmri_conv3x3_thin_masked(const float* x, const float* w, const unsigned* signs, float* y, int N,
+                              int H, int W, float act_slope, void* stream) {
+  CSMRI_TRY(check_ptr(signs, "signs"));
+  if (!(act_slope >= 0.0f)) return fail(CSMRI_E_ARG, "act_slope must be >= 0 (got %g)", act_slope);
+  return conv3x3_thin_impl(x, w, nullptr, y, N, 2, 32, H, W, 0.0f, signs, act_slope, stream);
 }
 
 // ---- 32 -> 32 convolution on the tensor cores, 3xTF32 (conv_tc.cuh) -------------

@@ -107,7 +107,7 @@ class ConvBlock(nn.Module):
             from . import conv as _conv
             y = convs[0](x)
             if _conv.tc_chain_eligible(y, inner):
-                return convs[-1](_conv.tc_chain(y, inner))
+                return _conv.tc_chain(y, inner, last=convs[-1])
             for m in inner:
                 y = m(y)
             return convs[-1](y)

@@ -252,6 +252,14 @@ int csmri_conv3x3_wgrad_bias(const float* x, const float* dy, float* dw, float* 
  * spatial axes and its first two axes transposed.  H % 16 == 0, W % 32 == 0. */
 int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float* y,
                        int N, int A, int B, int H, int W, float slope, void* stream);
+/* The 2 -> 32 form without bias / activation, its result multiplied by the derivative of a
+ * LeakyReLU whose output signs csmri_conv3x3_tc_signs recorded:
+ *   y[n][c] = conv(x, w)[n][c] * (bit c of signs[n] ? 1 : act_slope)
+ * With w = the 32 -> 2 layer's weights flipped and transposed this is that layer's data
+ * gradient followed by the backward of the nn.LeakyReLU in front of it (models/recnet.py:
+ * 45-48), in one pass.  x (N,2,H,W), w (32,2,3,3), signs (N,H,W) uint32, y (N,32,H,W). */
+int csmri_conv3x3_thin_masked(const float* x, const float* w, const unsigned* signs, float* y,
+                              int N, int H, int W, float act_slope, void* stream);
 
 /* RecNet's 32 -> 32 channel 3x3 convolutions (the inner layers of every ConvBlock,
  * models/recnet.py:37-44), stride 1, zero padding 1, on the tcgen05 tensor cores

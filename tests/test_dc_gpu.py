@@ -976,22 +976,24 @@ def test_fused_leaky_relu_backward_and_bias_gradient_on_the_tensor_core_path():
     for m in mods:
         m.fused_slope = slope
         torch.nn.init.normal_(m.bias, std=0.1)
+    tail = conv.Conv2d(32, 2, 3, padding=1).cuda()           # the block's thin 32 -> 2 layer
     xin = torch.randn(n, 32, h, w, device='cuda', generator=g)
-    seed = torch.randn(n, 32, h, w, device='cuda', generator=g)
+    seed = torch.randn(n, 2, h, w, device='cuda', generator=g)
     res = []
     for fused in (True, False):
-        for m in mods:
+        for m in mods + [tail]:
             m.zero_grad(set_to_none=True)
         xi = xin.clone().requires_grad_(True)
         assert conv.tc_chain_eligible(xi, mods)
         if fused:
-            y = conv.tc_chain(xi, mods)
+            y = conv.tc_chain(xi, mods, last=tail)
         else:
             y = xi
             for m in mods:
                 y = m(y)
+            y = tail(y)
         (y * seed).sum().backward()
-        res.append([y.detach(), xi.grad] + [p.grad for m in mods for p in (m.weight, m.bias)])
+        res.append([y.detach(), xi.grad] + [p.grad for m in mods + [tail] for p in (m.weight, m.bias)])
     assert torch.equal(res[0][0], res[1][0])                 # same forward kernels
     for a, b in zip(res[0][1:], res[1][1:]):
         assert (a - b).norm().item() <= 2e-6 * b.norm().item()

@@ -45,6 +45,9 @@ wt = torch.randn(32, 32, 3, 3, device=dev) * 0.1
 conv.conv3x3_tc(xt, wt, torch.randn(32, device=dev), 0.01)
 conv.conv3x3_tc(xt, wt, None, 0.0, transpose_flip=True)
 conv.conv3x3_wgrad(xt, torch.randn(2, 32, 16, 128, device=dev), 1)
+_, sg = conv.conv3x3_tc_signs(xt, wt, torch.randn(32, device=dev), 0.01)
+conv.conv3x3_tc_masked(xt, wt, sg, 0.01)
+conv.conv3x3_wgrad_bias(xt, torch.randn(2, 32, 16, 128, device=dev))
 torch.cuda.synchronize()
 print('ok tensor-core convolutions')
 img = torch.rand(2, 32, 32, device=dev)
