@@ -391,7 +391,7 @@ def tc_chain_eligible(x, convs):
     """True when every module of ``convs`` is a 32 -> 32 ``Conv2d`` with bias, padding 1
     and the same fused LeakyReLU slope, and ``x`` has a shape both tensor-core kernels
     cover (H % 16 == 0, W % 128 == 0)."""
-    if len(convs) < 2 or not (_ENABLED and _TC_ENABLED) or torch.is_autocast_enabled():
+    if len(convs) < 1 or not (_ENABLED and _TC_ENABLED) or torch.is_autocast_enabled():
         return False
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()):
         return False

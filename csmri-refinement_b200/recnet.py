@@ -102,7 +102,7 @@ class ConvBlock(nn.Module):
         mods = list(self.layers)
         convs = [m for m in mods if isinstance(m, nn.Conv2d)]
         inner = convs[1:-1]
-        if torch.is_grad_enabled() and len(inner) >= 2 and all(
+        if torch.is_grad_enabled() and len(inner) >= 1 and all(
                 isinstance(m, (nn.Conv2d, nn.Identity)) for m in mods) and convs[0].fused_slope is not None:
             from . import conv as _conv
             y = convs[0](x)
