@@ -16,6 +16,7 @@
 // (output pair) float2 so that every multiply-add is a packed FFMA2, and a
 // thread slides a 3x3 window down its column.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -268,6 +269,152 @@ __global__ void __launch_bounds__(256, 2)
       yn[(size_t)r * W + lane] = sum.x;
       yn[plane + (size_t)r * W + lane] = sum.y;
     }
+  }
+}
+
+// The same 32 -> 2 convolution with the input tile staged by TMA instead of cp.async:
+// one box {36 columns from x0 - 4, 10 rows from y0 - 1, 32 channels} per tile, zero-filled
+// outside the image (= the convolution's padding), issued by one thread one tile ahead on an
+// mbarrier.  (The innermost start coordinate of a TMA box must be 16-byte aligned - x0 - 1 is an
+// illegal instruction, tools/tma_box_probe.cu - so the box starts 4 columns to the left and
+// column x0 + j sits at offset j + 4.)  The box ends at column x0 + 31; the right halo column
+// x0 + 32 of row r is read straight from global memory one tile ahead and dropped into the
+// unused first slot of row r + 1, which is exactly where offset 32 + 4 of row r points.
+// The cp.async version spends 40 % of its 1031 instructions per pixel on staging address
+// arithmetic (profiles/r1_training_kernels_ncu.txt: 81 M warp instructions, issue-bound at 3x
+// the HBM floor); here staging costs three instructions per tile plus two loads per thread.
+constexpr int kThinTmaPC = 36;                                              // box width (floats)
+constexpr int kThinTmaBox = 32 * (kThinInRows + 2) * kThinTmaPC;            // floats in one box
+constexpr int kThinTmaBuf = kThinTmaBox + 32;                               // + the last row's halo slot; keeps buffer 1 128-byte aligned
+constexpr int kThinTmaSmem = (2 * kThinTmaBuf + 8 * kThinInRows * 32 * 2) * 4 + 64 + 128;   // + partials, barriers, alignment slack
+
+__global__ void __launch_bounds__(256, 2)
+    conv3x3_thin_in_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ x,
+                               const float* __restrict__ w, const float* __restrict__ bias,
+                               float* __restrict__ y, int H, int W,
+                               int tiles_x, int tiles_y, int ntiles) {
+  constexpr int A = 32, AT = 4, R = kThinInRows;
+  extern __shared__ unsigned char thin_tma_raw[];
+  // TMA destinations are 128-byte aligned (the dynamic shared-memory base is only 16)
+  float* thin_smem = reinterpret_cast<float*>(
+      thin_tma_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(thin_tma_raw) & 127u)) & 127u));
+  cf* part = reinterpret_cast<cf*>(thin_smem + 2 * kThinTmaBuf);   // [8][R][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(thin_smem + 2 * kThinTmaBuf + 8 * R * 32 * 2);
+  const uint32_t full = (uint32_t)__cvta_generic_to_shared(bars);  // [2] tile landed
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int cib = warp * AT;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+  }
+  cf wp[AT][9];
+#pragma unroll
+  for (int c = 0; c < AT; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      wp[c][t] = mk(__ldg(w + (cib + c) * 9 + t), __ldg(w + (A + cib + c) * 9 + t));
+  const cf bp = bias != nullptr ? mk(__ldg(bias), __ldg(bias + 1)) : mk(0.0f, 0.0f);
+  const size_t plane = (size_t)H * W;
+  __syncthreads();
+  auto stage_tile = [&](int tile, int b) {          // one thread: expect the bytes, fire the box
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(thin_smem + b * kThinTmaBuf);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full + 8 * b),
+                 "r"((uint32_t)(kThinTmaBox * 4))
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(&tm_x), "r"(full + 8 * b), "r"(t.x0 - 4), "r"(t.y0 - 1), "r"(t.n * A)
+        : "memory");
+  };
+  // right halo column: 32 channels x 10 rows = 320 values per tile, thread i takes entries i and
+  // i + 256 (entry e = channel * 10 + row), requested one tile ahead
+  auto fetch_halo = [&](int tile, int e) -> float {
+    if (e >= A * (R + 2)) return 0.0f;
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    const int c = e / (R + 2), r = e - c * (R + 2);
+    const int gy = t.y0 - 1 + r, gx = t.x0 + 32;
+    if (gy < 0 || gy >= H || gx >= W) return 0.0f;
+    return __ldg(x + ((size_t)t.n * A + c) * plane + (size_t)gy * W + gx);
+  };
+  int tile = blockIdx.x;
+  float h0 = 0.0f, h1 = 0.0f;
+  if (tile < ntiles) {
+    if (threadIdx.x == 0) stage_tile(tile, 0);
+    h0 = fetch_halo(tile, threadIdx.x);
+    h1 = fetch_halo(tile, threadIdx.x + 256);
+  }
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const int b = it & 1;
+    const float* cur = thin_smem + b * kThinTmaBuf + cib * (R + 2) * kThinTmaPC;
+    const int next = tile + gridDim.x;
+    // buffer b ^ 1 was last read in iteration it - 1, whose trailing __syncthreads has passed
+    if (threadIdx.x == 0 && next < ntiles) stage_tile(next, b ^ 1);
+    {
+      uint32_t done;
+      do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;"
+            " selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(full + 8 * b), "r"((uint32_t)((it >> 1) & 1))
+            : "memory");
+      } while (!done);
+    }
+    {   // the box has landed: drop this tile's right halo column into the slots behind the rows
+      float* buf = thin_smem + b * kThinTmaBuf;
+      buf[(threadIdx.x + 1) * kThinTmaPC] = h0;
+      if (threadIdx.x + 256 < A * (R + 2)) buf[(threadIdx.x + 256 + 1) * kThinTmaPC] = h1;
+    }
+    if (next < ntiles) {
+      h0 = fetch_halo(next, threadIdx.x);
+      h1 = fetch_halo(next, threadIdx.x + 256);
+    }
+    __syncthreads();
+    float win[AT][3][3];
+#pragma unroll
+    for (int c = 0; c < AT; ++c)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        win[c][1][kx] = cur[(c * (R + 2) + 0) * kThinTmaPC + lane + kx + 3];
+        win[c][2][kx] = cur[(c * (R + 2) + 1) * kThinTmaPC + lane + kx + 3];
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int c = 0; c < AT; ++c)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          win[c][0][kx] = win[c][1][kx];
+          win[c][1][kx] = win[c][2][kx];
+          win[c][2][kx] = cur[(c * (R + 2) + r + 2) * kThinTmaPC + lane + kx + 3];
+        }
+      cf acc = mk(0.0f, 0.0f);
+#pragma unroll
+      for (int c = 0; c < AT; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            acc = f2fma(wp[c][ky * 3 + kx], mk(win[c][ky][kx], win[c][ky][kx]), acc);
+      part[(warp * R + r) * 32 + lane] = acc;
+    }
+    __syncthreads();   // partial sums complete; everyone is done reading the tile
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    float* yn = y + (size_t)t.n * 2 * plane + (size_t)t.y0 * W + t.x0;
+    {
+      const int r = threadIdx.x >> 5;                 // 8 rows x 32 pixels = 256 threads
+      cf sum = bp;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) sum = f2add(sum, part[(g * R + r) * 32 + lane]);
+      yn[(size_t)r * W + lane] = sum.x;
+      yn[plane + (size_t)r * W + lane] = sum.y;
+    }
+    __syncthreads();   // partial sums consumed before the next tile overwrites them
   }
 }
 

@@ -736,6 +736,7 @@ static int g_wgrad_cot = 8;      // output channels per thread of conv3x3_wgrad_
 static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_set_tuning
 static int g_tc_debug = 0;       // conv3x3_tc_kernel probe bits (tuning key 6)
 static int g_wgrad_tc = 1;       // 32 -> 32 weight gradient on the tensor cores (tuning key 7; 0 = SIMT kernel)
+static int g_thin_tma = 1;       // 32 -> 2 thin convolution staged by TMA (tuning key 8; 0 = cp.async staging)
 static long long* g_trace = nullptr;  // tuning probe: per-CTA timeline buffers (2 x 1024 x 40)
 static int g_trace_launch = 0;
 
@@ -1235,6 +1236,7 @@ int csmri_set_tuning(int key, int value) {
   else if (key == 5) g_wgrad_cot = value == 8 ? 8 : 4;
   else if (key == 6) g_tc_debug = value & 7;
   else if (key == 7) g_wgrad_tc = value != 0;
+  else if (key == 8) g_thin_tma = value != 0;
   else return fail(CSMRI_E_ARG, "unknown tuning key %d", key);
   return CSMRI_OK;
 }
@@ -1724,9 +1726,27 @@ static int conv3x3_thin_impl(const float* x, const float* w, const float* bias, 
     conv3x3_thin_out_kernel<<<ctas, 256, 0, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
                                                  (int)ntiles_ll, slope, msigns, mslope);
   } else {
-    CSMRI_TRY(set_smem(conv3x3_thin_in_kernel, kThinInSmem));
-    conv3x3_thin_in_kernel<<<ctas, 256, kThinInSmem, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
-                                                          (int)ntiles_ll);
+    if (g_thin_tma) {
+      // input tiles by TMA (box {36, 10, 32} from (x0 - 4, y0 - 1), zero-filled outside the image)
+      EncodeTiledFn enc = encode_tiled_fn();
+      if (enc == nullptr) return fail(CSMRI_E_CUDA, "cuTensorMapEncodeTiled is unavailable");
+      alignas(64) CUtensorMap tm;
+      cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * 32};
+      cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+      cuuint32_t box[3] = {(cuuint32_t)kThinTmaPC, (cuuint32_t)(kThinInRows + 2), 32};
+      cuuint32_t es[3] = {1, 1, 1};
+      CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(CSMRI_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+      CSMRI_TRY(set_smem(conv3x3_thin_in_tma_kernel, kThinTmaSmem));
+      conv3x3_thin_in_tma_kernel<<<ctas, 256, kThinTmaSmem, s>>>(tm, x, w, bias, y, H, W, tiles_x, tiles_y,
+                                                                 (int)ntiles_ll);
+    } else {
+      CSMRI_TRY(set_smem(conv3x3_thin_in_kernel, kThinInSmem));
+      conv3x3_thin_in_kernel<<<ctas, 256, kThinInSmem, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
+                                                            (int)ntiles_ll);
+    }
   }
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;

@@ -50,3 +50,21 @@ for name, a, c in (('forward (bias + LeakyReLU fused)', 0, 1), ('data gradient',
     ms = ev[a].elapsed_time(ev[c]) / 10
     print('%-38s %.3f ms  %.0f TFLOP/s fp32-equivalent  %.0f GB/s of operand traffic' % (
         name, ms, flop / ms / 1e9, byt / ms / 1e6))
+
+# the thin 32 -> 2 layer (forward of a block's last layer / data gradient of its first), TMA vs cp.async staging
+from csmri_refinement_b200 import _lib  # noqa: E402
+w2 = torch.randn(2, 32, 3, 3, device=dev) * 0.1
+b2 = torch.randn(2, device=dev)
+for key, name in ((1, 'thin 32 -> 2, TMA-staged'), (0, 'thin 32 -> 2, cp.async-staged')):
+    _lib.lib().csmri_set_tuning(8, key)
+    for _ in range(3):
+        t2 = conv.conv3x3_thin(x, w2, b2, 0.0)
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        t2 = conv.conv3x3_thin(x, w2, b2, 0.0)
+    c.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(c) / 10
+    print('%-38s %.3f ms  %.0f GB/s of operand traffic' % (name, ms, (x.numel() + t2.numel()) * 4 / ms / 1e6))
+_lib.lib().csmri_set_tuning(8, 1)
