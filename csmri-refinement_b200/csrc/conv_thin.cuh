@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(256, 2)
     const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
     float* yn = y + ((size_t)t.n * B + cob) * plane + (size_t)t.y0 * W + t.x0 + lane;
     const unsigned* sg = msigns != nullptr ? msigns + ((size_t)t.n * H + t.y0) * W + t.x0 + lane : nullptr;
+    unsigned sw[R];                    // the tile's sign words, all requested before the row loop
+#pragma unroll
+    for (int r = 0; r < R; ++r) sw[r] = sg != nullptr ? __ldg(sg + (size_t)r * W) : 0xffffffffu;
     float win[A][3][3];
 #pragma unroll
     for (int c = 0; c < A; ++c)
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(256, 2)
         win[c][1][kx] = cur[(c * (R + 2) + 0) * kThinPC + lane + kx - 1];
         win[c][2][kx] = cur[(c * (R + 2) + 1) * kThinPC + lane + kx - 1];
       }
-#pragma unroll 8
+#pragma unroll
     for (int r = 0; r < R; ++r) {
 #pragma unroll
       for (int c = 0; c < A; ++c)
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256, 2)
             for (int o = 0; o < BT / 2; ++o)
               acc[o] = f2fma(wp[c][ky * 3 + kx][o], mk(win[c][ky][kx], win[c][ky][kx]), acc[o]);
 #pragma unroll
-      const unsigned bits = sg != nullptr ? __ldg(sg + (size_t)r * W) >> cob : 0xffffffffu;
+      const unsigned bits = sw[r] >> cob;
 #pragma unroll
       for (int o = 0; o < BT / 2; ++o) {
         float a = acc[o].x, b = acc[o].y;
@@ -499,6 +502,146 @@ __global__ void __launch_bounds__(256, 2)
                 f2fma(d, mk(win[c][ky][kx], win[c][ky][kx]), acc[c][ky * 3 + kx]);
     }
     __syncthreads();   // `cur` is the staging target of the next iteration
+  }
+  // fold the 32 pixel-lanes; lane 0 writes the warp's sums in dW order [o][c][tap]
+  float* dst = partial + (size_t)blockIdx.x * (A * 2 * 9);
+#pragma unroll
+  for (int c = 0; c < AT; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float a = acc[c][t].x, b = acc[c][t].y;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, m);
+        b += __shfl_xor_sync(0xffffffffu, b, m);
+      }
+      if (lane == 0) {
+        dst[(0 * A + cib + c) * 9 + t] = a;
+        dst[(1 * A + cib + c) * 9 + t] = b;
+      }
+    }
+}
+
+// The same weight gradient with the input tile staged by TMA (see conv3x3_thin_in_tma_kernel:
+// box {36, 10, 32} from (x0 - 4, y0 - 1), right halo column dropped behind the rows).
+constexpr int kThinWgTmaSmem = 2 * kThinTmaBuf * 4 + 64 + 128;   // two tile buffers + barriers + alignment slack
+
+__global__ void __launch_bounds__(256, 2)
+    conv3x3_wgrad_thin_staged_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ x,
+                                         const float* __restrict__ dy, float* __restrict__ partial, int H,
+                                         int W, int tiles_x, int tiles_y, int ntiles) {
+  constexpr int A = 32, AT = 4, R = kThinInRows;
+  extern __shared__ unsigned char thin_tma_raw[];
+  float* thin_smem = reinterpret_cast<float*>(
+      thin_tma_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(thin_tma_raw) & 127u)) & 127u));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(thin_smem + 2 * kThinTmaBuf);
+  const uint32_t full = (uint32_t)__cvta_generic_to_shared(bars);  // [2] tile landed
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int cib = warp * AT;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+  }
+  cf acc[AT][9];
+#pragma unroll
+  for (int c = 0; c < AT; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[c][t] = mk(0.0f, 0.0f);
+  const size_t plane = (size_t)H * W;
+  __syncthreads();
+  auto stage_tile = [&](int tile, int b) {
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(thin_smem + b * kThinTmaBuf);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full + 8 * b),
+                 "r"((uint32_t)(kThinTmaBox * 4))
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(&tm_x), "r"(full + 8 * b), "r"(t.x0 - 4), "r"(t.y0 - 1), "r"(t.n * A)
+        : "memory");
+  };
+  auto fetch_halo = [&](int tile, int e) -> float {
+    if (e >= A * (R + 2)) return 0.0f;
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    const int c = e / (R + 2), r = e - c * (R + 2);
+    const int gy = t.y0 - 1 + r, gx = t.x0 + 32;
+    if (gy < 0 || gy >= H || gx >= W) return 0.0f;
+    return __ldg(x + ((size_t)t.n * A + c) * plane + (size_t)gy * W + gx);
+  };
+  int tile = blockIdx.x;
+  float h0 = 0.0f, h1 = 0.0f;
+  if (tile < ntiles) {
+    if (threadIdx.x == 0) stage_tile(tile, 0);
+    h0 = fetch_halo(tile, threadIdx.x);
+    h1 = fetch_halo(tile, threadIdx.x + 256);
+  }
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const int b = it & 1;
+    const float* cur = thin_smem + b * kThinTmaBuf + cib * (R + 2) * kThinTmaPC;
+    const int next = tile + gridDim.x;
+    if (threadIdx.x == 0 && next < ntiles) stage_tile(next, b ^ 1);
+    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+    const float* dn = dy + ((size_t)t.n * 2 * H + t.y0) * W + t.x0 + lane;
+    float d0[R], d1[R];   // this tile's dY column: in flight while the tile lands
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      d0[r] = __ldg(dn + (size_t)r * W);
+      d1[r] = __ldg(dn + plane + (size_t)r * W);
+    }
+    {
+      uint32_t done;
+      do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;"
+            " selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(full + 8 * b), "r"((uint32_t)((it >> 1) & 1))
+            : "memory");
+      } while (!done);
+    }
+    {
+      float* buf = thin_smem + b * kThinTmaBuf;
+      buf[(threadIdx.x + 1) * kThinTmaPC] = h0;
+      if (threadIdx.x + 256 < A * (R + 2)) buf[(threadIdx.x + 256 + 1) * kThinTmaPC] = h1;
+    }
+    if (next < ntiles) {
+      h0 = fetch_halo(next, threadIdx.x);
+      h1 = fetch_halo(next, threadIdx.x + 256);
+    }
+    __syncthreads();
+    float win[AT][3][3];
+#pragma unroll
+    for (int c = 0; c < AT; ++c)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        win[c][1][kx] = cur[(c * (R + 2) + 0) * kThinTmaPC + lane + kx + 3];
+        win[c][2][kx] = cur[(c * (R + 2) + 1) * kThinTmaPC + lane + kx + 3];
+      }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int c = 0; c < AT; ++c)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          win[c][0][kx] = win[c][1][kx];
+          win[c][1][kx] = win[c][2][kx];
+          win[c][2][kx] = cur[(c * (R + 2) + r + 2) * kThinTmaPC + lane + kx + 3];
+        }
+      const cf d = mk(d0[r], d1[r]);
+#pragma unroll
+      for (int c = 0; c < AT; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            acc[c][ky * 3 + kx] =
+                f2fma(d, mk(win[c][ky][kx], win[c][ky][kx]), acc[c][ky * 3 + kx]);
+    }
+    __syncthreads();   // everyone is done with buffer b before it becomes a TMA target again
   }
   // fold the 32 pixel-lanes; lane 0 writes the warp's sums in dW order [o][c][tap]
   float* dst = partial + (size_t)blockIdx.x * (A * 2 * 9);

@@ -1649,9 +1649,25 @@ static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float*
       if (ctas > kWgMaxCtas) ctas = kWgMaxCtas;
       if (ctas > nt8) ctas = nt8;
       constexpr int smem_staged = 2 * kThinInBuf * (int)sizeof(float);
-      CSMRI_TRY(set_smem(conv3x3_wgrad_thin_staged_kernel, smem_staged));
-      conv3x3_wgrad_thin_staged_kernel<<<ctas, 256, smem_staged, s>>>(x, dy, (float*)workspace, H, W,
-                                                                      tiles_x, ty8, nt8);
+      EncodeTiledFn enc = g_thin_tma ? encode_tiled_fn() : nullptr;
+      if (enc != nullptr) {
+        alignas(64) CUtensorMap tm;
+        cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N * 32};
+        cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+        cuuint32_t box[3] = {(cuuint32_t)kThinTmaPC, (cuuint32_t)(kThinInRows + 2), 32};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(CSMRI_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        CSMRI_TRY(set_smem(conv3x3_wgrad_thin_staged_tma_kernel, kThinWgTmaSmem));
+        conv3x3_wgrad_thin_staged_tma_kernel<<<ctas, 256, kThinWgTmaSmem, s>>>(
+            tm, x, dy, (float*)workspace, H, W, tiles_x, ty8, nt8);
+      } else {
+        CSMRI_TRY(set_smem(conv3x3_wgrad_thin_staged_kernel, smem_staged));
+        conv3x3_wgrad_thin_staged_kernel<<<ctas, 256, smem_staged, s>>>(x, dy, (float*)workspace, H, W,
+                                                                        tiles_x, ty8, nt8);
+      }
     } else {
       conv3x3_wgrad_thin_kernel<4, 2, false><<<ctas, 256, 0, s>>>(
           x, dy, (float*)workspace, H, W, HI, WI, pad, tiles_x, tiles_y, ntiles);

@@ -68,3 +68,19 @@ for key, name in ((1, 'thin 32 -> 2, TMA-staged'), (0, 'thin 32 -> 2, cp.async-s
     ms = a.elapsed_time(c) / 10
     print('%-38s %.3f ms  %.0f GB/s of operand traffic' % (name, ms, (x.numel() + t2.numel()) * 4 / ms / 1e6))
 _lib.lib().csmri_set_tuning(8, 1)
+
+# the thin 2 -> 32 layer (forward of a block's first layer / data gradient of its last), plain and with the sign-word mask
+w3 = torch.randn(32, 2, 3, 3, device=dev) * 0.1
+x2 = torch.randn(n, 2, h, w, device=dev)
+for name, fn in (('thin 2 -> 32', lambda: conv.conv3x3_thin(x2, w3, None, 0.0)),
+                 ('thin 2 -> 32 x LeakyReLU derivative', lambda: conv.conv3x3_thin_masked(x2, w3, sg, 0.01))):
+    for _ in range(3):
+        fn()
+    a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        t3 = fn()
+    c.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(c) / 10
+    print('%-38s %.3f ms  %.0f GB/s of operand traffic' % (name, ms, (x2.numel() + t3.numel()) * 4 / ms / 1e6))
