@@ -231,17 +231,35 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // weights: split into hi / lo, laid out as the B operand of each horizontal tap
-  for (int e = tid; e < 9 * kTcC * kTcC; e += kTcThreads) {
-    const int tap = e / (kTcC * kTcC), r = e - tap * (kTcC * kTcC);
-    const int co = r / kTcC, ci = r - co * kTcC;       // operator element (co, ci, tap)
-    const int ky = tap / 3, kx = tap - 3 * ky;
-    const float v = transpose_flip ? __ldg(w + ((ci * kTcC + co) * 3 + (2 - ky)) * 3 + (2 - kx))
+  // weights: split into hi / lo, laid out as the B operand of each horizontal tap.  All of a
+  // thread's loads are issued before the first is used (a rolled loop paid one global-memory
+  // round trip per element: ~12 us of the ~20 us fixed cost of a launch).
+  {
+    constexpr int kPer = (9 * kTcC * kTcC + kTcThreads - 1) / kTcThreads;
+    float wv[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int e = tid + i * kTcThreads;
+      const int tap = e / (kTcC * kTcC), r = e - tap * (kTcC * kTcC);
+      const int co = r / kTcC, ci = r - co * kTcC;     // operator element (co, ci, tap)
+      const int ky = tap / 3, kx = tap - 3 * ky;
+      wv[i] = e >= 9 * kTcC * kTcC ? 0.0f
+              : transpose_flip     ? __ldg(w + ((ci * kTcC + co) * 3 + (2 - ky)) * 3 + (2 - kx))
                                    : __ldg(w + ((co * kTcC + ci) * 3 + ky) * 3 + kx);
-    const float hi = tc_tf32(v), lo = tc_tf32(v - hi);
-    const int off = kx * (2 * kTcBPart) + (ci >> 2) * kTcBPlane + (ky * kTcC + co) * 16 + (ci & 3) * 4;
-    *reinterpret_cast<float*>(B_s + off) = hi;
-    *reinterpret_cast<float*>(B_s + off + kTcBPart) = lo;
+    }
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int e = tid + i * kTcThreads;
+      if (e < 9 * kTcC * kTcC) {
+        const int tap = e / (kTcC * kTcC), r = e - tap * (kTcC * kTcC);
+        const int co = r / kTcC, ci = r - co * kTcC;
+        const int ky = tap / 3, kx = tap - 3 * ky;
+        const float hi = tc_tf32(wv[i]), lo = tc_tf32(wv[i] - hi);
+        const int off = kx * (2 * kTcBPart) + (ci >> 2) * kTcBPlane + (ky * kTcC + co) * 16 + (ci & 3) * 4;
+        *reinterpret_cast<float*>(B_s + off) = hi;
+        *reinterpret_cast<float*>(B_s + off + kTcBPart) = lo;
+      }
+    }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
