@@ -92,6 +92,8 @@ _SIGNATURES = {
     'csmri_conv3x3_wgrad_workspace_bytes': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     'csmri_conv3x3_wgrad': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_void_p] + [ctypes.c_int] * 6 +
                             [ctypes.c_void_p]),
+    'csmri_conv3x3_wgrad_thin_bias': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_void_p] + [ctypes.c_int] * 3 +
+                                      [ctypes.c_void_p]),
     'csmri_conv3x3_thin_masked': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 3 +
                                   [ctypes.c_float, ctypes.c_void_p]),
     'csmri_conv3x3_wgrad_bias': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_void_p] + [ctypes.c_int] * 3 +
@@ -100,7 +102,7 @@ _SIGNATURES = {
                            [ctypes.c_float, ctypes.c_void_p]),
     'csmri_conv3x3_tc': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 4 +
                          [ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),
-    'csmri_conv3x3_tc_signs': (ctypes.c_int, [_c_float_p] * 5 + [ctypes.c_int] * 4 +
+    'csmri_conv3x3_tc_signs': (ctypes.c_int, [_c_float_p] * 6 + [ctypes.c_int] * 4 +
                                [ctypes.c_float, ctypes.c_void_p]),
     'csmri_conv3x3_tc_masked': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 4 +
                                 [ctypes.c_float, ctypes.c_int, ctypes.c_void_p]),

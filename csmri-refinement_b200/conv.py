@@ -160,20 +160,22 @@ def conv3x3_tc(x, weight, bias, slope=0.0, transpose_flip=False):
     return y
 
 
-def conv3x3_tc_signs(x, weight, bias, slope):
+def conv3x3_tc_signs(x, weight, bias, slope, want_in_signs=False):
     """``conv3x3_tc`` forward that also returns the sign word of every output pixel
-    ((N,H,W) int32, bit c = output channel c > 0) for :func:`conv3x3_tc_masked`."""
+    ((N,H,W) int32, bit c = output channel c > 0) for :func:`conv3x3_tc_masked` and, with
+    ``want_in_signs``, the same word for the input ``x`` (else ``None``)."""
     _require_cuda_f32(x, weight, bias)
     x, weight = x.contiguous(), weight.contiguous()
     n, c, h, w = x.shape
     with torch.cuda.device(x.device):
         y = torch.empty_like(x)
         signs = torch.empty((n, h, w), dtype=torch.int32, device=x.device)
+        in_signs = torch.empty((n, h, w), dtype=torch.int32, device=x.device) if want_in_signs else None
         _lib.check(_lib.lib().csmri_conv3x3_tc_signs(
             x.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
-            y.data_ptr(), signs.data_ptr(), n, c, h, w, float(slope),
-            torch.cuda.current_stream().cuda_stream))
-    return y, signs
+            y.data_ptr(), signs.data_ptr(), None if in_signs is None else in_signs.data_ptr(),
+            n, c, h, w, float(slope), torch.cuda.current_stream().cuda_stream))
+    return y, signs, in_signs
 
 
 def conv3x3_tc_masked(x, weight, signs, act_slope, transpose_flip=True):
@@ -208,6 +210,24 @@ def conv3x3_wgrad_bias(x, grad_out):
         ws = torch.empty((lib.csmri_conv3x3_wgrad_workspace_bytes(32, 32) // 4,),
                          dtype=torch.float32, device=x.device)
         _lib.check(lib.csmri_conv3x3_wgrad_bias(
+            x.data_ptr(), grad_out.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), n, h, w,
+            torch.cuda.current_stream().cuda_stream))
+    return dw, db
+
+
+def conv3x3_wgrad_thin_bias(x, grad_out):
+    """(dW, db) of RecNet's 2 -> 32 layer (zero padding 1): the bias gradient is a
+    by-product of the weight-gradient kernel."""
+    _require_cuda_f32(x, grad_out)
+    x, grad_out = _aligned16(x.contiguous()), _aligned16(grad_out.contiguous())
+    n, _, h, w = grad_out.shape
+    lib = _lib.lib()
+    with torch.cuda.device(x.device):
+        dw = torch.empty((32, 2, 3, 3), dtype=torch.float32, device=x.device)
+        db = torch.empty((32,), dtype=torch.float32, device=x.device)
+        ws = torch.empty((lib.csmri_conv3x3_wgrad_workspace_bytes(2, 32) // 4,),
+                         dtype=torch.float32, device=x.device)
+        _lib.check(lib.csmri_conv3x3_wgrad_thin_bias(
             x.data_ptr(), grad_out.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), n, h, w,
             torch.cuda.current_stream().cuda_stream))
     return dw, db
@@ -252,7 +272,10 @@ class _Conv3x3(torch.autograd.Function):
     weight gradient run through libcsmri_dc."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, pad, slope, in_signs=None, in_slope=0.0):
+    def forward(ctx, x, weight, bias, pad, slope, in_signs=None, in_slope=0.0, out_premasked=False):
+        # out_premasked (thin 2 -> 32 layer with fused LeakyReLU only): the consumer (_TcChain)
+        # sends the gradient back already multiplied by this layer's activation derivative
+        ctx.out_premasked = bool(out_premasked)
         # in_signs (thin 32 -> 2 layer only): sign words of x, the output of a LeakyReLU whose
         # producer (_TcChain) expects its incoming gradient already multiplied by the derivative
         ctx.in_signs, ctx.in_slope = in_signs, in_slope
@@ -286,6 +309,12 @@ class _Conv3x3(torch.autograd.Function):
         gx = gb = gw = None
         if ctx.slope is None:
             x, weight = ctx.saved_tensors
+        elif ctx.out_premasked:
+            x, weight, y = ctx.saved_tensors
+            gw, gb = conv3x3_wgrad_thin_bias(x, grad_out) if need_w or need_b else (None, None)
+            if need_x:
+                gx = conv3x3_thin(grad_out, weight.flip(2, 3).transpose(0, 1), None, 0.0)
+            return gx, gw if need_w else None, gb if need_b else None, None, None, None, None, None
         else:
             x, weight, y = ctx.saved_tensors
             grad_out, gb = bias_lrelu_backward(grad_out, y, ctx.slope)
@@ -329,7 +358,7 @@ class _Conv3x3(torch.autograd.Function):
             grad_out.record_stream(side)
         elif need_w:
             gw = conv3x3_wgrad(x, grad_out, pad)
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None
 
 
 class _TcChain(torch.autograd.Function):
@@ -342,16 +371,21 @@ class _TcChain(torch.autograd.Function):
     activation signs travel as one 32-bit word per pixel written by the forward kernel."""
 
     @staticmethod
-    def forward(ctx, x, slope, out_premasked, *params):
+    def forward(ctx, x, slope, out_premasked, in_premask, *params):
         # out_premasked: the consumer of the output promises to multiply the gradient it sends
-        # back by the last activation's derivative (it gets the sign words for that)
+        # back by the last activation's derivative (it gets the sign words for that);
+        # in_premask: x is itself the output of a LeakyReLU(slope) whose producer expects the
+        # gradient returned for x to carry that derivative (the first kernel records x's signs)
         ws, bs = params[0::2], params[1::2]
-        acts, signs = [x], []
+        acts, signs, in_signs = [x], [], None
         for k, (w, b) in enumerate(zip(ws, bs)):
-            y, sg = conv3x3_tc_signs(acts[-1], w, b, slope)
+            y, sg, isg = conv3x3_tc_signs(acts[-1], w, b, slope, want_in_signs=bool(in_premask) and k == 0)
+            if k == 0:
+                in_signs = isg
             signs.append(sg)
             acts.append(y)
         ctx.slope, ctx.n, ctx.out_premasked = slope, len(ws), bool(out_premasked)
+        ctx.in_signs = in_signs
         ctx.save_for_backward(*acts, *ws, *signs[:-1])
         ctx.mark_non_differentiable(signs[-1])
         return acts[-1], signs[-1]
@@ -368,7 +402,7 @@ class _TcChain(torch.autograd.Function):
             gz, gb = bias_lrelu_backward(grad_out.contiguous(), acts[n], slope)
             have_gb = True
         for k in range(n - 1, -1, -1):          # layer k: input acts[k], output acts[k + 1]
-            need_w, need_b = ctx.needs_input_grad[3 + 2 * k], ctx.needs_input_grad[4 + 2 * k]
+            need_w, need_b = ctx.needs_input_grad[4 + 2 * k], ctx.needs_input_grad[5 + 2 * k]
             fresh = k < n - 1 or not have_gb    # gb of this layer not known yet
             if need_w and fresh:
                 grads[2 * k], gb = conv3x3_wgrad_bias(acts[k], gz)
@@ -380,11 +414,13 @@ class _TcChain(torch.autograd.Function):
                 grads[2 * k + 1] = gb
             if k > 0:                           # data gradient + derivative of layer k - 1's activation
                 gz = conv3x3_tc_masked(gz, ws[k], signs[k - 1], slope)
+            elif ctx.needs_input_grad[0] and ctx.in_signs is not None:
+                gz = conv3x3_tc_masked(gz, ws[0], ctx.in_signs, slope)
             elif ctx.needs_input_grad[0]:
                 gz = conv3x3_tc(gz, ws[0], None, 0.0, transpose_flip=True)
             else:
                 gz = None
-        return (gz, None, None) + tuple(grads)
+        return (gz, None, None, None) + tuple(grads)
 
 
 def tc_chain_eligible(x, convs):
@@ -411,21 +447,32 @@ def tc_chain_eligible(x, convs):
     return True
 
 
-def tc_chain(x, convs, last=None):
-    """Run ``convs`` (see :func:`tc_chain_eligible`) as one fused autograd node.  ``last``
-    (optional): the 32 -> 2 ``Conv2d`` that consumes the result - if it is the plain thin
-    layer (padding 1, bias, no activation) it is applied too, and its data gradient carries
-    the derivative of the run's last LeakyReLU (no separate pass for it either)."""
+def _plain_thin(m, cin, cout, with_act):
+    return isinstance(m, Conv2d) and m.bias is not None and tuple(m.weight.shape) == (cout, cin, 3, 3) and \
+        m.padding_mode == 'zeros' and not isinstance(m.padding, str) and tuple(m.padding) == (1, 1) and \
+        tuple(m.stride) == (1, 1) and tuple(m.dilation) == (1, 1) and m.groups == 1 and \
+        m.weight.is_contiguous() and m.weight.dtype == torch.float32 and \
+        ((m.fused_slope is not None and m.fused_slope > 0) if with_act else m.fused_slope is None)
+
+
+def tc_chain(x, convs, last=None, first=None):
+    """Run ``convs`` (see :func:`tc_chain_eligible`) as one fused autograd node.
+    ``last`` (optional): the 32 -> 2 ``Conv2d`` that consumes the result - if it is the plain
+    thin layer (padding 1, bias, no activation) it is applied too, and its data gradient carries
+    the derivative of the run's last LeakyReLU.  ``first`` (optional): the 2 -> 32 ``Conv2d``
+    with the same fused LeakyReLU that PRODUCES the run's input - then ``x`` is that layer's
+    input, it is applied first, and the run's data gradient carries its activation derivative.
+    With both, no LeakyReLU-backward pass is left in the block."""
     params = []
     for m in convs:
         params += [m.weight, m.bias]
     slope = float(convs[0].fused_slope)
-    fuse_last = last is not None and isinstance(last, Conv2d) and last.fused_slope is None and \
-        last.bias is not None and tuple(last.weight.shape) == (2, 32, 3, 3) and \
-        last.padding_mode == 'zeros' and not isinstance(last.padding, str) and \
-        tuple(last.padding) == (1, 1) and tuple(last.stride) == (1, 1) and \
-        tuple(last.dilation) == (1, 1) and last.groups == 1 and last.weight.is_contiguous()
-    y, signs = _TcChain.apply(x, slope, fuse_last, *params)
+    fuse_first = first is not None and _plain_thin(first, 2, 32, True) and float(first.fused_slope) == slope \
+        and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    if first is not None:
+        x = _Conv3x3.apply(x, first.weight, first.bias, 1, slope, None, 0.0, True) if fuse_first else first(x)
+    fuse_last = last is not None and _plain_thin(last, 32, 2, False)
+    y, signs = _TcChain.apply(x, slope, fuse_last, fuse_first, *params)
     if last is None:
         return y
     if fuse_last:

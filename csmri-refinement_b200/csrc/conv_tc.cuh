@@ -183,6 +183,9 @@ __device__ __forceinline__ TcItem tc_item(int item, int xsegs, int yblocks) {
 // (the data gradient of the same layer).  H % kTcRowBlock == 0, W % 128 == 0.
 // `debug` (tuning probes only): bit 0 skip the MMAs, bit 1 skip the global loads,
 // bit 2 skip the global stores.
+// `in_signs` (optional output, MASKED = false): the same kind of sign word for the INPUT x,
+// a by-product of the producer warps holding all 32 channels of a pixel - it lets the data
+// gradient of this layer carry the derivative of the activation that produced x.
 // `signs` (N,H,W) uint32, bit c of a pixel = (output channel c > 0):
 // MASKED = false: optional OUTPUT of the forward pass (one 4-byte store per pixel);
 // MASKED = true (the data gradient feeding a LeakyReLU layer): no bias, no activation, and
@@ -194,7 +197,7 @@ template <bool MASKED>
 __global__ void __launch_bounds__(kTcThreads, 1)
     conv3x3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w,
                       const float* __restrict__ bias, float* __restrict__ y, uint32_t* __restrict__ signs,
-                      int H, int W, int nitems,
+                      uint32_t* __restrict__ in_signs, int H, int W, int nitems,
                       float slope, int transpose_flip, int debug) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   unsigned char* B_s = tc_smem;                       // [kx][hi | lo][ci/4][ky co 0-95][ci%4]
@@ -279,14 +282,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     uint32_t q = g;                                // its ring index
     TcItem t = tc_item(item < nitems ? item : 0, xsegs, yblocks);
     float v[kTcC], vn[kTcC];
-    auto fetch = [&](float* dst) {
+    long long soff = -1, soff_next = -1;             // where the sign word of the row in v / vn goes (-1: nowhere)
+    auto fetch = [&](float* dst, long long& so) {
       const int gy = t.y0 - 1 + r;
       const bool ok = item < nitems && gy >= 0 && gy < H && !(kTcProbe && (debug & 2));
       const float* src = x + ((size_t)t.n * kTcC * H + (ok ? gy : 0)) * W + t.x0 + j;
 #pragma unroll
       for (int c = 0; c < kTcC; ++c) dst[c] = ok ? __ldg(src + (size_t)c * plane) : 0.0f;
+      // rows 1 .. 8 of an item are its own (0 and 9 are halo rows another item owns)
+      so = (!MASKED && in_signs != nullptr && ok && r >= 1 && r <= kTcRowBlock)
+               ? (long long)(((size_t)t.n * H + gy) * W + t.x0 + j)
+               : -1;
     };
-    fetch(v);
+    fetch(v, soff);
     while (item < nitems) {
       const uint32_t slot = q & 3;
       // advance the fetch position by two rows and get that row on its way
@@ -296,7 +304,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         item += gridDim.x;
         if (item < nitems) t = tc_item(item, xsegs, yblocks);
       }
-      fetch(vn);
+      fetch(vn, soff_next);
+      if (!MASKED && soff >= 0) {
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int c = 0; c < kTcC; ++c) bits |= (v[c] > 0.0f ? 1u : 0u) << c;
+        in_signs[soff] = bits;
+      }
+      soff = soff_next;
       TC_PROF_WAIT(0, row_free + 8 * slot, ((q >> 2) & 1) ^ 1);
       unsigned char* hi_s = A_s + (size_t)slot * 2 * kTcSlotPart + (j + 1) * 16;
       unsigned char* lo_s = hi_s + kTcSlotPart;

@@ -668,8 +668,10 @@ __global__ void __launch_bounds__(256, 2)
 // the tile is multiplied).  dw[o][c][tap], o < 32, c < 2.
 __global__ void __launch_bounds__(256, 2)
     conv3x3_wgrad_thin_out_staged_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                         float* __restrict__ partial, int H, int W, int tiles_x,
-                                         int tiles_y, int ntiles) {
+                                         float* __restrict__ partial, float* __restrict__ bias_partial,
+                                         int H, int W, int tiles_x, int tiles_y, int ntiles) {
+  // bias_partial (optional, gridDim.x x 32 floats): per-CTA sums of dy over all pixels = the bias
+  // gradient of the layer, a by-product of every thread holding its pixel's dY values
   constexpr int A = 2, B = 32, BT = 4, R = kThinInRows;
   constexpr int kBuf = kThinLead + A * (R + 2) * kThinPC;
   __shared__ __align__(16) float stage[2][kBuf];
@@ -683,6 +685,7 @@ __global__ void __launch_bounds__(256, 2)
     for (int t = 0; t < 9; ++t)
 #pragma unroll
       for (int o = 0; o < BT / 2; ++o) acc[c][t][o] = mk(0.0f, 0.0f);
+  float bsum[BT] = {0.0f, 0.0f, 0.0f, 0.0f};
   const size_t plane = (size_t)H * W;
   auto stage_tile = [&](int tile, float* buf) {
     const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
@@ -710,6 +713,15 @@ __global__ void __launch_bounds__(256, 2)
       for (int o = 0; o < BT; ++o) d[r][o] = __ldg(dn + (size_t)o * plane + (size_t)r * W);
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
+    if (bias_partial != nullptr) {          // two-level sum: tile (8 values) -> CTA
+#pragma unroll
+      for (int o = 0; o < BT; ++o) {
+        float ts = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) ts += d[r][o];
+        bsum[o] += ts;
+      }
+    }
     float win[A][3][3];
 #pragma unroll
     for (int c = 0; c < A; ++c)
@@ -760,6 +772,15 @@ __global__ void __launch_bounds__(256, 2)
           dst[((cob + 2 * o + 1) * A + c) * 9 + t] = b;
         }
       }
+  if (bias_partial != nullptr) {
+#pragma unroll
+    for (int o = 0; o < BT; ++o) {
+      float a = bsum[o];
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) a += __shfl_xor_sync(0xffffffffu, a, m);
+      if (lane == 0) bias_partial[blockIdx.x * B + cob + o] = a;
+    }
+  }
 }
 
 }  // namespace csmri

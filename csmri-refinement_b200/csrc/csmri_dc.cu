@@ -1604,6 +1604,12 @@ int csmri_conv3x3_wgrad_bias(const float* x, const float* dy, float* dw, float* 
   return conv3x3_wgrad_impl(x, dy, dw, db, workspace, N, kWtcC, kWtcC, H, W, 1, stream);
 }
 
+int csmri_conv3x3_wgrad_thin_bias(const float* x, const float* dy, float* dw, float* db, void* workspace,
+                                  int N, int H, int W, void* stream) {
+  CSMRI_TRY(check_ptr(db, "db"));
+  return conv3x3_wgrad_impl(x, dy, dw, db, workspace, N, 2, 32, H, W, 1, stream);
+}
+
 static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float* db, void* workspace, int N,
                               int CI, int CO, int H, int W, int pad, void* stream) {
   CSMRI_TRY(wgrad_check_channels(CI, CO));
@@ -1637,8 +1643,13 @@ static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float*
       ctas = sm_count() * 2;
       if (ctas > kWgMaxCtas) ctas = kWgMaxCtas;
       if (ctas > nt8) ctas = nt8;
-      conv3x3_wgrad_thin_out_staged_kernel<<<ctas, 256, 0, s>>>(x, dy, (float*)workspace, H, W,
-                                                                tiles_x, ty8, nt8);
+      float* bias_partial = db != nullptr ? (float*)workspace + (size_t)ctas * CI * CO * 9 : nullptr;
+      conv3x3_wgrad_thin_out_staged_kernel<<<ctas, 256, 0, s>>>(x, dy, (float*)workspace, bias_partial,
+                                                                H, W, tiles_x, ty8, nt8);
+      if (db != nullptr)
+        wgrad_thin_reduce_kernel<<<1, 64, 0, s>>>(bias_partial, db, CO, ctas);
+    } else if (db != nullptr) {
+      return fail(CSMRI_E_SHAPE, "conv3x3_wgrad_bias: shape not covered (2 -> 32 needs pad 1 and a 16-byte aligned x)");
     } else if (CI == 2) {
       conv3x3_wgrad_thin_kernel<2, 4, true><<<ctas, 256, 0, s>>>(
           x, dy, (float*)workspace, H, W, HI, WI, pad, tiles_x, tiles_y, ntiles);
@@ -1782,8 +1793,8 @@ int csmri_conv3x3_thin_masked(const float* x, const float* w, const unsigned* si
 
 // ---- 32 -> 32 convolution on the tensor cores, 3xTF32 (conv_tc.cuh) -------------
 static int conv3x3_tc_launch(const float* x, const float* w, const float* bias, float* y, unsigned* signs,
-                             int N, int C, int H, int W, float slope, int transpose_flip, bool masked,
-                             void* stream) {
+                             unsigned* in_signs, int N, int C, int H, int W, float slope,
+                             int transpose_flip, bool masked, void* stream) {
   if (C != kTcC) return fail(CSMRI_E_SHAPE, "conv3x3_tc handles %d -> %d channels (got %d)", kTcC, kTcC, C);
   if (N <= 0 || H <= 0 || W <= 0 || H % kTcRowBlock != 0 || W % kTcM != 0)
     return fail(CSMRI_E_SHAPE, "conv3x3_tc needs H %% %d == 0 and W %% %d == 0 (got %dx%dx%d)",
@@ -1801,11 +1812,11 @@ static int conv3x3_tc_launch(const float* x, const float* w, const float* bias, 
   if (masked) {
     CSMRI_TRY(set_smem(conv3x3_tc_kernel<true>, kTcSmemBytes));
     conv3x3_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(
-        x, w, nullptr, y, signs, H, W, (int)nitems_ll, slope, transpose_flip != 0, g_tc_debug);
+        x, w, nullptr, y, signs, nullptr, H, W, (int)nitems_ll, slope, transpose_flip != 0, g_tc_debug);
   } else {
     CSMRI_TRY(set_smem(conv3x3_tc_kernel<false>, kTcSmemBytes));
     conv3x3_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(
-        x, w, bias, y, signs, H, W, (int)nitems_ll, slope, transpose_flip != 0, g_tc_debug);
+        x, w, bias, y, signs, in_signs, H, W, (int)nitems_ll, slope, transpose_flip != 0, g_tc_debug);
   }
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
@@ -1813,18 +1824,18 @@ static int conv3x3_tc_launch(const float* x, const float* w, const float* bias, 
 
 int csmri_conv3x3_tc(const float* x, const float* w, const float* bias, float* y, int N, int C,
                      int H, int W, float slope, int transpose_flip, void* stream) {
-  return conv3x3_tc_launch(x, w, bias, y, nullptr, N, C, H, W, slope, transpose_flip, false, stream);
+  return conv3x3_tc_launch(x, w, bias, y, nullptr, nullptr, N, C, H, W, slope, transpose_flip, false, stream);
 }
 
 int csmri_conv3x3_tc_signs(const float* x, const float* w, const float* bias, float* y, unsigned* signs,
-                           int N, int C, int H, int W, float slope, void* stream) {
+                           unsigned* in_signs, int N, int C, int H, int W, float slope, void* stream) {
   CSMRI_TRY(check_ptr(signs, "signs"));
-  return conv3x3_tc_launch(x, w, bias, y, signs, N, C, H, W, slope, 0, false, stream);
+  return conv3x3_tc_launch(x, w, bias, y, signs, in_signs, N, C, H, W, slope, 0, false, stream);
 }
 
 int csmri_conv3x3_tc_masked(const float* x, const float* w, const unsigned* signs, float* y, int N,
                             int C, int H, int W, float act_slope, int transpose_flip, void* stream) {
-  return conv3x3_tc_launch(x, w, nullptr, y, const_cast<unsigned*>(signs), N, C, H, W, act_slope,
+  return conv3x3_tc_launch(x, w, nullptr, y, const_cast<unsigned*>(signs), nullptr, N, C, H, W, act_slope,
                            transpose_flip, true, stream);
 }
 

@@ -57,6 +57,21 @@ def _pad_and_conv(in_ch, out_ch, kernel_size, dilation, mode):
                                      bias=True, dilation=dilation)
 
 
+class _FakeAct(object):
+    """Shape / placement stand-in for the first layer's output (32 channels at the input's
+    spatial size), so that the run's eligibility can be decided before that layer runs."""
+
+    def __init__(self, x):
+        self.is_cuda, self.dtype = x.is_cuda, x.dtype
+        self.shape = (x.shape[0], 32, x.shape[2], x.shape[3])
+
+    def dim(self):
+        return 4
+
+    def is_contiguous(self):
+        return True
+
+
 class ConvBlock(nn.Module):
     """models/recnet.py:29-62: (pad, conv, lrelu) x (num_convs-1), pad, conv."""
 
@@ -105,9 +120,11 @@ class ConvBlock(nn.Module):
         if torch.is_grad_enabled() and len(inner) >= 1 and all(
                 isinstance(m, (nn.Conv2d, nn.Identity)) for m in mods) and convs[0].fused_slope is not None:
             from . import conv as _conv
+            # the run's eligibility depends on placement and spatial shape only, so it can be
+            # decided before the first layer has produced the run's actual input
+            if x.dim() == 4 and x.is_contiguous() and _conv.tc_chain_eligible(_FakeAct(x), inner):
+                return _conv.tc_chain(x, inner, last=convs[-1], first=convs[0])
             y = convs[0](x)
-            if _conv.tc_chain_eligible(y, inner):
-                return _conv.tc_chain(y, inner, last=convs[-1])
             for m in inner:
                 y = m(y)
             return convs[-1](y)

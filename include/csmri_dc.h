@@ -243,6 +243,10 @@ int csmri_conv3x3_wgrad(const float* x, const float* dy, float* dw, void* worksp
  * workspace.  Other shapes are CSMRI_E_SHAPE. */
 int csmri_conv3x3_wgrad_bias(const float* x, const float* dy, float* dw, float* db, void* workspace,
                              int N, int H, int W, void* stream);
+/* The same for RecNet's 2 -> 32 layer (x (N,2,H,W), dy (N,32,H,W), zero padding 1, H % 8 == 0,
+ * W % 32 == 0, x 16-byte aligned): dw (32,2,3,3) and db (32). */
+int csmri_conv3x3_wgrad_thin_bias(const float* x, const float* dy, float* dw, float* db,
+                                  void* workspace, int N, int H, int W, void* stream);
 
 /* RecNet's thin 3x3 convolutions (first / last layer of a block, models/recnet.py:
  * 45-48), stride 1, zero padding 1:  y = act(conv(x, w) + bias)
@@ -275,9 +279,11 @@ int csmri_conv3x3_thin_masked(const float* x, const float* w, const unsigned* si
 int csmri_conv3x3_tc(const float* x, const float* w, const float* bias, float* y,
                      int N, int C, int H, int W, float slope, int transpose_flip, void* stream);
 /* The forward form of the call above that also records the sign of every output:
- *   signs (N,H,W) uint32, bit c of a pixel = (y[n][c][h][w] > 0)   (4 bytes per pixel). */
+ *   signs (N,H,W) uint32, bit c of a pixel = (y[n][c][h][w] > 0)   (4 bytes per pixel),
+ * and optionally (in_signs != NULL) the same word for the INPUT x - when x is the output of
+ * a LeakyReLU, that is what the data gradient of this layer needs to carry its derivative. */
 int csmri_conv3x3_tc_signs(const float* x, const float* w, const float* bias, float* y, unsigned* signs,
-                           int N, int C, int H, int W, float slope, void* stream);
+                           unsigned* in_signs, int N, int C, int H, int W, float slope, void* stream);
 /* The same convolution without bias / activation, its result multiplied by the derivative
  * of the LeakyReLU that produced its consumer's input:
  *   y[n][c] = conv(x, wq)[n][c] * (bit c of signs[n] ? 1 : act_slope)

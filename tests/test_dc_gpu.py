@@ -952,10 +952,13 @@ def test_fused_leaky_relu_backward_and_bias_gradient_on_the_tensor_core_path():
     wt = torch.randn(32, 32, 3, 3, device='cuda', generator=g) * 0.08
     xa = torch.randn(n, 32, h, w, device='cuda', generator=g)
     ba = torch.randn(32, device='cuda', generator=g)
-    act, signs = conv.conv3x3_tc_signs(xa, wt, ba, slope)    # forward that records the output signs
+    xa[0, 3, 5, :7] = 0.0                                    # exact zeros take the `slope` branch
+    act, signs, in_signs = conv.conv3x3_tc_signs(xa, wt, ba, slope, want_in_signs=True)   # records output and input signs
     assert torch.equal(act, conv.conv3x3_tc(xa, wt, ba, slope))
-    bits = ((signs.unsqueeze(1) >> torch.arange(32, device='cuda').view(1, 32, 1, 1)) & 1).bool()
-    assert torch.equal(bits, act > 0)                        # exact zeros would take the `slope` branch
+    assert conv.conv3x3_tc_signs(xa, wt, ba, slope)[2] is None
+    shifts = torch.arange(32, device='cuda').view(1, 32, 1, 1)
+    assert torch.equal(((signs.unsqueeze(1) >> shifts) & 1).bool(), act > 0)
+    assert torch.equal(((in_signs.unsqueeze(1) >> shifts) & 1).bool(), xa > 0)
     want = torch.nn.functional.conv_transpose2d(gz.double(), wt.double(), None, 1, 1) * \
         torch.where(act > 0, 1.0, slope).double()
     got = conv.conv3x3_tc_masked(gz, wt, signs, slope)
@@ -967,37 +970,54 @@ def test_fused_leaky_relu_backward_and_bias_gradient_on_the_tensor_core_path():
     dw, db = conv.conv3x3_wgrad_bias(x, gz)
     assert orc.rel_l2(dw.cpu().numpy(), w64.grad.cpu().numpy()) < 2e-6
     assert orc.rel_l2(db.cpu().numpy(), b64.grad.cpu().numpy()) < 2e-6
+    # the 2 -> 32 layer's weight gradient with its bias gradient as a by-product
+    x2 = torch.randn(n, 2, h, w, device='cuda', generator=g)
+    w2 = (torch.randn(32, 2, 3, 3, device='cuda', generator=g) * 0.1).double().requires_grad_(True)
+    b2 = torch.zeros(32, device='cuda', dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(x2.double(), w2, b2, 1, 1).backward(gz.double())
+    dw2, db2 = conv.conv3x3_wgrad_thin_bias(x2, gz)
+    assert orc.rel_l2(dw2.cpu().numpy(), w2.grad.cpu().numpy()) < 2e-6
+    assert orc.rel_l2(db2.cpu().numpy(), b2.grad.cpu().numpy()) < 2e-6
+    assert torch.equal(dw2, conv.conv3x3_wgrad(x2, gz, 1))
     assert torch.equal(db, conv.conv3x3_wgrad_bias(x, gz)[1])
     with pytest.raises(RuntimeError):
         conv.conv3x3_wgrad_bias(x[:, :, :8].contiguous(), gz[:, :, :8].contiguous())   # H % 16 != 0
-    # the chain node vs the same modules one by one
+    # the chain node (+ the block's thin first / last layers) vs the same modules one by one
     torch.manual_seed(5)
     mods = [conv.Conv2d(32, 32, 3, padding=1).cuda() for _ in range(3)]
-    for m in mods:
+    head = conv.Conv2d(2, 32, 3, padding=1).cuda()           # the block's thin 2 -> 32 layer (+ LeakyReLU)
+    tail = conv.Conv2d(32, 2, 3, padding=1).cuda()           # the block's thin 32 -> 2 layer
+    for m in mods + [head]:
         m.fused_slope = slope
         torch.nn.init.normal_(m.bias, std=0.1)
-    tail = conv.Conv2d(32, 2, 3, padding=1).cuda()           # the block's thin 32 -> 2 layer
-    xin = torch.randn(n, 32, h, w, device='cuda', generator=g)
+    xin = torch.randn(n, 2, h, w, device='cuda', generator=g)
     seed = torch.randn(n, 2, h, w, device='cuda', generator=g)
-    res = []
-    for fused in (True, False):
-        for m in mods + [tail]:
-            m.zero_grad(set_to_none=True)
-        xi = xin.clone().requires_grad_(True)
-        assert conv.tc_chain_eligible(xi, mods)
-        if fused:
-            y = conv.tc_chain(xi, mods, last=tail)
-        else:
-            y = xi
-            for m in mods:
-                y = m(y)
-            y = tail(y)
-        (y * seed).sum().backward()
-        res.append([y.detach(), xi.grad] + [p.grad for m in mods + [tail] for p in (m.weight, m.bias)])
-    assert torch.equal(res[0][0], res[1][0])                 # same forward kernels
-    for a, b in zip(res[0][1:], res[1][1:]):
-        assert (a - b).norm().item() <= 2e-6 * b.norm().item()
-    assert not conv.tc_chain_eligible(xin[:, :, :, :64].contiguous(), mods)
+    every = [head] + mods + [tail]
+    for first, last in ((head, tail), (None, tail), (head, None), (None, None)):
+        res = []
+        for fused in (True, False):
+            for m in every:
+                m.zero_grad(set_to_none=True)
+            xi = xin.clone().requires_grad_(True)
+            y = xi if first is not None else head(xi)
+            assert conv.tc_chain_eligible(torch.empty(n, 32, h, w, device='cuda'), mods)
+            if fused:
+                y = conv.tc_chain(y, mods, last=last, first=first)
+            else:
+                if first is not None:
+                    y = first(y)
+                for m in mods:
+                    y = m(y)
+                if last is not None:
+                    y = last(y)
+            if last is None:
+                y = tail(y)
+            (y * seed).sum().backward()
+            res.append([y.detach(), xi.grad] + [p.grad for m in every for p in (m.weight, m.bias)])
+        assert torch.equal(res[0][0], res[1][0]), (first is not None, last is not None)   # same forward kernels
+        for a, b in zip(res[0][1:], res[1][1:]):
+            assert (a - b).norm().item() <= 2e-6 * b.norm().item(), (first is not None, last is not None)
+    assert not conv.tc_chain_eligible(torch.empty(n, 32, h, 64, device='cuda'), mods)
 
 
 def test_recnet_training_gradients_with_tensor_core_convs():

@@ -29,7 +29,7 @@ static int launch(const float* x, const float* w, const float* b, float* y, int 
   int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int nitems = N * (W / kTcM) * (H / kTcRowBlock);
   const int grid = nitems < sms ? nitems : sms;
-  conv3x3_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes>>>(x, w, b, y, nullptr, H, W, nitems, slope, tf, debug);
+  conv3x3_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes>>>(x, w, b, y, nullptr, nullptr, H, W, nitems, slope, tf, debug);
   return 0;
 }
 

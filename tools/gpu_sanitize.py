@@ -45,7 +45,9 @@ wt = torch.randn(32, 32, 3, 3, device=dev) * 0.1
 conv.conv3x3_tc(xt, wt, torch.randn(32, device=dev), 0.01)
 conv.conv3x3_tc(xt, wt, None, 0.0, transpose_flip=True)
 conv.conv3x3_wgrad(xt, torch.randn(2, 32, 16, 128, device=dev), 1)
-_, sg = conv.conv3x3_tc_signs(xt, wt, torch.randn(32, device=dev), 0.01)
+_, sg, _ = conv.conv3x3_tc_signs(xt, wt, torch.randn(32, device=dev), 0.01, want_in_signs=True)
+conv.conv3x3_wgrad_thin_bias(torch.randn(2, 2, 16, 128, device=dev), xt)
+conv.conv3x3_thin_masked(torch.randn(2, 2, 16, 128, device=dev), torch.randn(32, 2, 3, 3, device=dev), sg, 0.01)
 conv.conv3x3_tc_masked(xt, wt, sg, 0.01)
 conv.conv3x3_wgrad_bias(xt, torch.randn(2, 32, 16, 128, device=dev))
 torch.cuda.synchronize()

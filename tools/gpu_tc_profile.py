@@ -20,7 +20,7 @@ for _ in range(3):
     gx = conv.conv3x3_tc(gy, wt, None, 0.0, transpose_flip=True)
     dw = conv.conv3x3_wgrad(x, gy, 1)
 torch.cuda.synchronize()
-act, sg = conv.conv3x3_tc_signs(x, wt, b, 0.01)
+act, sg, _ = conv.conv3x3_tc_signs(x, wt, b, 0.01)
 for _ in range(3):
     gm = conv.conv3x3_tc_masked(gy, wt, sg, 0.01)
     dwb = conv.conv3x3_wgrad_bias(x, gy)
