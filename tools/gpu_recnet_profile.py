@@ -38,6 +38,6 @@ for e in prof.key_averages():
     rows_.append((t / 2.0, e.count // 2, e.key))
 rows_.sort(reverse=True)
 tot = sum(r[0] for r in rows_)
-print('tf32=%d  total kernel time per step %.2f ms' % (tf32, tot / 1e3))
-for t, c, k in rows_[:22]:
+print('tf32=%d  total kernel time per step %.2f ms in %d launches' % (tf32, tot / 1e3, sum(r[1] for r in rows_)))
+for t, c, k in rows_[:40]:
     print('%9.1f us %5.1f%% x%-4d %s' % (t, 100 * t / tot, c, k[:110]))
