@@ -2,7 +2,7 @@
 // layers of every ConvBlock) on the 5th-generation tensor cores - the one
 // GEMM-shaped piece of the training step - with fp32 accuracy.
 //
-// The fp32 step spends 21 of its 40 ms in cuDNN's fp32 forward / data-gradient
+// Round 1's fp32 step spent 21 of its 40 ms in cuDNN's fp32 forward / data-gradient
 // kernels for these layers (profiles/r1_recnet_step_kernels.txt; ~55 TFLOP/s
 // effective).  The parity gate is stated for fp32 arithmetic (1e-5), so plain
 // TF32 is out; the classic way to get fp32-accurate products out of TF32 tensor
@@ -32,15 +32,22 @@
 //   blocks that hold an output row's contributions in fp32 registers.
 // * work item = 8 output rows x 128 pixels (10 staged rows).  At the top / bottom
 //   of an item the N window shrinks to the taps that land inside it.
-// * staging = 4 producer warps: coalesced fp32 loads straight from the NCHW
+// * staging = two groups of 4 producer warps (even / odd ring rows, the next row
+//   already in registers) + a halo warp: coalesced fp32 loads straight from the NCHW
 //   tensor, hi / lo split in registers, two 16-byte shared stores per (pixel,
-//   4 channels), fence.proxy.async, mbarrier arrive.  A ring of 4 row slots, each
-//   released by a tcgen05.commit as soon as its 36 instructions have retired.
+//   4 channels), fence.proxy.async, one mbarrier arrival per warp.  A ring of 4 row
+//   slots, each released by a tcgen05.commit as soon as its 36 instructions have retired.
+// * two MMA-issuing warps (even / odd staged rows; a row owns its accumulator block,
+//   ring slot and barriers), each running its loop with warp-uniform control flow and
+//   an elected lane around the instructions.
 // * the two small split terms (lo*hi, hi*lo) of a row are issued before its hi*hi
 //   term: the accumulator is rounded toward zero after every instruction, and that
 //   rounding is relative to what the accumulator holds at the time.
-// * 4 epilogue warps: tcgen05.ld (lane = pixel, columns = output channels),
-//   bias + LeakyReLU, coalesced 128-byte row stores per channel.
+// * 4 epilogue warps: tcgen05.ld (lane = pixel, columns = output channels, 16 at a
+//   time), bias from shared memory + LeakyReLU, coalesced 128-byte row stores per
+//   channel, one 32-bit sign word per pixel (bit c = output channel c > 0).  The
+//   MASKED instantiation is the data gradient that also applies the derivative of the
+//   LeakyReLU in front of the layer, selected by such a sign word.
 // * B (the 9 x 32 x 32 weights, hi and lo) is split once per CTA into shared
 //   memory; `transpose_flip` builds the data-gradient operator (ci <-> co swapped,
 //   taps mirrored) from the same weight tensor, so backward-data is this kernel too.
