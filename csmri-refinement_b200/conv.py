@@ -366,9 +366,13 @@ class _TcChain(torch.autograd.Function):
     autograd node (models/recnet.py:37-47: the inner layers of a ConvBlock).  Forward is
     the fused conv + bias + LeakyReLU kernel per layer.  Backward applies the activation
     derivative of layer k inside the data-gradient kernel of layer k + 1 (its saved input IS
-    that activation's output) and takes the bias gradients from the weight-gradient kernel,
-    so only the last layer of the run needs a LeakyReLU-backward pass of its own.  The
-    activation signs travel as one 32-bit word per pixel written by the forward kernel."""
+    that activation's output) and takes the bias gradients from the weight-gradient kernel.
+    The activation signs travel as one 32-bit word per pixel written by the forward kernel.
+    The derivative of the run's LAST activation is a pass of its own unless the consumer
+    applies it (``out_premasked``: the block's 32 -> 2 layer does, in its data gradient), and
+    the gradient returned for ``x`` carries the derivative of the activation that produced
+    ``x`` when ``in_premask`` is set (the block's 2 -> 32 layer then skips its own pass): see
+    :func:`tc_chain`."""
 
     @staticmethod
     def forward(ctx, x, slope, out_premasked, in_premask, *params):
