@@ -77,7 +77,7 @@ int main() {
     cudaMemcpy(dx, x.data(), ne * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(ddy, dy.data(), ne * 4, cudaMemcpyHostToDevice);
     cudaMemset(ddw, 0xff, 9216 * 4);
-    launch(dx, ddy, ddw, ws, N, H, W);
+    launch(dx, ddy, ddw, ws, N, H, W, getenv("WTC_DEBUG") ? atoi(getenv("WTC_DEBUG")) : 0);   // skip bits, for sanitizer experiments
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(out.data(), ddw, 9216 * 4, cudaMemcpyDeviceToHost);
     double num = 0, den = 0, worst = 0; int wi = 0;
