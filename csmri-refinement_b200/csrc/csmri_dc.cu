@@ -737,6 +737,7 @@ static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_
 static int g_tc_debug = 0;       // conv3x3_tc_kernel probe bits (tuning key 6)
 static int g_wgrad_tc = 1;       // 32 -> 32 weight gradient on the tensor cores (tuning key 7; 0 = SIMT kernel)
 static int g_thin_tma = 1;       // 32 -> 2 thin convolution staged by TMA (tuning key 8; 0 = cp.async staging)
+static int g_general_chunk_mib = 0;   // general-mask path: MiB of hybrid scratch per chunk (tuning key 9; 0 = whole batch per pass)
 static long long* g_trace = nullptr;  // tuning probe: per-CTA timeline buffers (2 x 1024 x 40)
 static int g_trace_launch = 0;
 
@@ -1237,6 +1238,7 @@ int csmri_set_tuning(int key, int value) {
   else if (key == 6) g_tc_debug = value & 7;
   else if (key == 7) g_wgrad_tc = value != 0;
   else if (key == 8) g_thin_tma = value != 0;
+  else if (key == 9) g_general_chunk_mib = value < 0 ? 0 : value;
   else return fail(CSMRI_E_ARG, "unknown tuning key %d", key);
   return CSMRI_OK;
 }
@@ -1332,6 +1334,14 @@ int csmri_dc_adjoint_cartesian(const float* grad_out, const float* dtab, float* 
                           (cudaStream_t)stream);
 }
 
+// slices per chunk of the general path: g_general_chunk_mib of hybrid scratch
+static int general_chunk(int B, int H, int W) {
+  if (g_general_chunk_mib <= 0) return B;
+  const size_t per = (size_t)2 * H * W * sizeof(float);
+  const size_t n = ((size_t)g_general_chunk_mib << 20) / per;
+  return n < 1 ? 1 : (n > (size_t)B ? B : (int)n);
+}
+
 int csmri_dc_forward_general(const float* x, const float* residual, const float* k0,
                              const float* mask, float* out, int B, int H, int W, float noise_lvl,
                              void* scratch, void* stream) {
@@ -1346,9 +1356,21 @@ int csmri_dc_forward_general(const float* x, const float* residual, const float*
   float* hyb = (float*)scratch;
   const float sc = 1.0f / sqrtf((float)H * (float)W);
   const bool noisy = noise_lvl != 0.0f;
-  CSMRI_TRY(launch_fft_rows(x, residual, hyb, B, H, W, 1.0f, 0.0f, false, residual ? 1 : 0, s));
-  CSMRI_TRY(launch_strip_dense(hyb, k0, mask, hyb, B, H, W, sc, noise_lvl, noisy, false, s));
-  CSMRI_TRY(launch_fft_rows(hyb, nullptr, out, B, H, W, 1.0f, 0.0f, true, 0, s));
+  // Tuning key 9 runs the three passes chunk by chunk so that a chunk's hybrid scratch could
+  // stay in the 126 MB L2 between passes.  Measured (profiles/r2_general_chunk_sweep.json): every
+  // chunk size is slower than whole-batch passes (256^2, B=256: 186 us unchunked, 190 us with two
+  // 64 MiB chunks, 265 us at 16 MiB) - the extra kernel boundaries cost more than L2 hits save,
+  // so the default is one chunk.
+  const size_t slice = (size_t)2 * H * W;
+  for (int b0 = 0, nb = general_chunk(B, H, W); b0 < B; b0 += nb) {
+    const int n = B - b0 < nb ? B - b0 : nb;
+    const size_t o = (size_t)b0 * slice;
+    CSMRI_TRY(launch_fft_rows(x + o, residual ? residual + o : nullptr, hyb + o, n, H, W, 1.0f, 0.0f,
+                              false, residual ? 1 : 0, s));
+    CSMRI_TRY(launch_strip_dense(hyb + o, k0 + o, mask + o, hyb + o, n, H, W, sc, noise_lvl, noisy,
+                                 false, s));
+    CSMRI_TRY(launch_fft_rows(hyb + o, nullptr, out + o, n, H, W, 1.0f, 0.0f, true, 0, s));
+  }
   return CSMRI_OK;
 }
 
@@ -1364,9 +1386,15 @@ int csmri_dc_adjoint_general(const float* grad_out, const float* mask, float* gr
   float* hyb = (float*)scratch;
   const float sc = 1.0f / sqrtf((float)H * (float)W);
   const bool noisy = noise_lvl != 0.0f;
-  CSMRI_TRY(launch_fft_rows(grad_out, nullptr, hyb, B, H, W, 1.0f, 0.0f, false, 0, s));
-  CSMRI_TRY(launch_strip_dense(hyb, nullptr, mask, hyb, B, H, W, sc, noise_lvl, noisy, true, s));
-  CSMRI_TRY(launch_fft_rows(hyb, nullptr, grad_x, B, H, W, 1.0f, 0.0f, true, 0, s));
+  const size_t slice = (size_t)2 * H * W;
+  for (int b0 = 0, nb = general_chunk(B, H, W); b0 < B; b0 += nb) {   // see csmri_dc_forward_general
+    const int n = B - b0 < nb ? B - b0 : nb;
+    const size_t o = (size_t)b0 * slice;
+    CSMRI_TRY(launch_fft_rows(grad_out + o, nullptr, hyb + o, n, H, W, 1.0f, 0.0f, false, 0, s));
+    CSMRI_TRY(launch_strip_dense(hyb + o, nullptr, mask + o, hyb + o, n, H, W, sc, noise_lvl, noisy,
+                                 true, s));
+    CSMRI_TRY(launch_fft_rows(hyb + o, nullptr, grad_x + o, n, H, W, 1.0f, 0.0f, true, 0, s));
+  }
   return CSMRI_OK;
 }
 
