@@ -79,6 +79,12 @@ _SIGNATURES = {
                               [ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
     'csmri_psnr_sum': (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p] + [ctypes.c_int] * 3 +
                        [ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
+    'csmri_shift_crop': (ctypes.c_int, [_c_float_p, _c_float_p] + [ctypes.c_int] * 13 +
+                         [_c_float_p, ctypes.c_void_p]),
+    'csmri_plane_absmax': (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p]),
+    'csmri_plane_divide': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int, ctypes.c_int,
+                                                             ctypes.c_void_p]),
     'csmri_plane_minmax': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int, ctypes.c_int,
                                                              ctypes.c_longlong, ctypes.c_void_p]),
     'csmri_plane_scale': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int, ctypes.c_int,

@@ -46,6 +46,7 @@
 #include "dc_pipe.cuh"
 #include "dc_pipev.cuh"
 #include "refine_ops.cuh"
+#include "loader_tail.cuh"
 #include "conv_wgrad.cuh"
 #include "conv_epilogue.cuh"
 #include "conv_thin.cuh"
@@ -1495,6 +1496,64 @@ int csmri_psnr_sum(const float* pred, const float* target, double* sum_sq, int B
 }
 
 // ---- refinement-path pointwise ops (refine_ops.cuh) ---------------------------
+// ---- loader tail: index plumbing of CenterCropInKspace + max normalisation ----
+int csmri_shift_crop(const float* in, float* out, int B, int in_ch, int IH, int IW, int out_ch,
+                     int OH, int OW, int in_roll_y, int in_roll_x, int off_y, int off_x,
+                     int out_roll_y, int out_roll_x, float* absmax, void* stream) {
+  if (B <= 0 || B > 65535 || IH <= 0 || IW <= 0 || OH <= 0 || OH > 65535 || OW <= 0)
+    return fail(CSMRI_E_SHAPE, "bad shape: B=%d in %dx%d out %dx%d", B, IH, IW, OH, OW);
+  if ((in_ch != 1 && in_ch != 2) || (out_ch != 1 && out_ch != 2) || (out_ch == 1 && in_ch != 2))
+    return fail(CSMRI_E_ARG, "channels must be 1 -> 2, 2 -> 2 or 2 -> 1 (got %d -> %d)", in_ch, out_ch);
+  if (in_roll_y < 0 || in_roll_y >= IH || in_roll_x < 0 || in_roll_x >= IW || out_roll_y < 0 ||
+      out_roll_y >= OH || out_roll_x < 0 || out_roll_x >= OW)
+    return fail(CSMRI_E_ARG, "rolls must be reduced modulo the axis length");
+  if (absmax != nullptr && out_ch != 1)
+    return fail(CSMRI_E_ARG, "absmax needs the magnitude output (out_ch = 1)");
+  CSMRI_TRY(check_ptr(in, "in"));
+  CSMRI_TRY(check_ptr(out, "out"));
+  if (in == out) return fail(CSMRI_E_ARG, "out must not alias in");
+  cudaStream_t s = (cudaStream_t)stream;
+  const ShiftCropAxis ay = {IH, OH, in_roll_y, off_y, out_roll_y};
+  const ShiftCropAxis ax = {IW, OW, in_roll_x, off_x, out_roll_x};
+  const dim3 grid((OW + 255) / 256, (OH + kShiftCropRows - 1) / kShiftCropRows, B);
+  unsigned* km = reinterpret_cast<unsigned*>(absmax);
+  if (km != nullptr) CSMRI_CUDA(cudaMemsetAsync(km, 0, (size_t)B * sizeof(unsigned), s));
+  if (in_ch == 1) shift_crop_kernel<1, 2><<<grid, 256, 0, s>>>(in, out, ay, ax, nullptr);
+  else if (out_ch == 2) shift_crop_kernel<2, 2><<<grid, 256, 0, s>>>(in, out, ay, ax, nullptr);
+  else shift_crop_kernel<2, 1><<<grid, 256, 0, s>>>(in, out, ay, ax, km);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+int csmri_plane_absmax(const float* x, float* absmax, int planes, int n, void* stream) {
+  if (planes <= 0 || planes > 65535 || n <= 0)
+    return fail(CSMRI_E_SHAPE, "bad plane shape: planes=%d n=%d", planes, n);
+  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr(absmax, "absmax"));
+  cudaStream_t s = (cudaStream_t)stream;
+  CSMRI_CUDA(cudaMemsetAsync(absmax, 0, (size_t)planes * sizeof(float), s));
+  const dim3 grid((n + 2047) / 2048 > 32 ? 32 : (n + 2047) / 2048, planes);
+  plane_absmax_kernel<<<grid, 256, 0, s>>>(x, reinterpret_cast<unsigned*>(absmax), n);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
+int csmri_plane_divide(const float* x, const float* denom, float* out, int planes, int n,
+                       void* stream) {
+  if (planes <= 0 || planes > 65535 || n <= 0)
+    return fail(CSMRI_E_SHAPE, "bad plane shape: planes=%d n=%d", planes, n);
+  CSMRI_TRY(check_ptr(x, "x"));
+  CSMRI_TRY(check_ptr(denom, "denom"));
+  CSMRI_TRY(check_ptr(out, "out"));
+  const dim3 grid((n + 1023) / 1024 > 64 ? 64 : (n + 1023) / 1024, planes);
+  if (n % 4 == 0 && (((uintptr_t)x | (uintptr_t)out) & 15u) == 0)
+    plane_divide_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, denom, out, n);
+  else
+    plane_divide_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x, denom, out, n);
+  CSMRI_CUDA(cudaGetLastError());
+  return CSMRI_OK;
+}
+
 static const int kRefinePartials = 32;
 
 static int plane_chunks(int n) {

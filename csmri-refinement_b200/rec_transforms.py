@@ -3,7 +3,9 @@ reporting transform around the DC path).
 
 * ``center_crop_in_kspace``  myImageTransformations.CenterCropInKspace (:935-954):
   fft2c -> crop at the centre (``crop_image_at`` :105-117) -> ifft2c -> abs.
-  The FFTs are the library's ``csmri_fft2``; shifts / crop are index plumbing.
+  The FFTs are the library's ``csmri_fft2``; the shifts, the crop and its zero
+  padding are composed into one gather pass per stage (``csmri_shift_crop``,
+  csrc/loader_tail.cuh), bit-identical to the roll / slice / pad chain.
 * ``normalize_by_max``        ``x / np.max(np.abs(x))`` (rec_transforms.py:47,65)
 * ``TrainTransform`` / ``TestTransform``  rec_transforms.py:18-76 without the
   augmentations (``augmentation`` is None in the shipped configs,
@@ -27,38 +29,86 @@ def _check_images(img):
         raise ValueError('images must be a float32 CUDA tensor of shape (B,H,W)')
 
 
-def center_crop_in_kspace(images, size):
-    """(B,H,W) real -> (B,size,size): magnitude of the image whose centred
-    k-space has been cropped (or zero-padded) to size x size."""
+def _shift_crop(x, out_ch, out_hw, in_roll, off, out_roll, absmax=None):
+    """One gather pass through the composed roll / crop / pad / roll index map
+    (csmri_shift_crop, csrc/loader_tail.cuh)."""
+    if x.dim() == 3:
+        B, in_ch, (ih, iw) = x.shape[0], 1, x.shape[1:]
+    else:
+        B, in_ch, ih, iw = x.shape
+    oh, ow = out_hw
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, out_ch, oh, ow), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().csmri_shift_crop(
+            x.data_ptr(), out.data_ptr(), B, in_ch, ih, iw, out_ch, oh, ow,
+            in_roll[0] % ih, in_roll[1] % iw, off[0], off[1], out_roll[0] % oh, out_roll[1] % ow,
+            absmax.data_ptr() if absmax is not None else None, _stream()))
+    return out
+
+
+def _center_crop(images, size, want_max):
     _check_images(images)
     if isinstance(size, (tuple, list)):
         sx, sy = int(size[0]), int(size[1])
     else:
         sx = sy = int(size)
+    images = images.contiguous()
     B, nx, ny = images.shape
-    x = torch.stack([images, torch.zeros_like(images)], dim=1)
     # fft2c = fftshift(fft2(ifftshift(x)))   (deep_med_lib/utils/mymath.py:18-29)
-    x = torch.roll(x, shifts=(-(nx // 2), -(ny // 2)), dims=(2, 3))
-    k = ops.fft2_planar(x.contiguous())
-    k = torch.roll(k, shifts=(nx // 2, ny // 2), dims=(2, 3))
-    # crop_image_at(im_k, nx//2, ny//2, sx, sy): box [c - s//2, c + s//2), zero padded
-    cx, cy, r1, r2 = nx // 2, ny // 2, sx // 2, sy // 2
-    x1, x2, y1, y2 = cx - r1, cx + r1, cy - r2, cy + r2
-    crop = k[:, :, max(x1, 0):min(x2, nx), max(y1, 0):min(y2, ny)]
-    pad = (max(0, -y1), max(0, y2 - ny), max(0, -x1), max(0, x2 - nx))
-    if any(pad):
-        crop = torch.nn.functional.pad(crop, pad)
-    cnx, cny = crop.shape[2], crop.shape[3]
-    crop = torch.roll(crop, shifts=(-(cnx // 2), -(cny // 2)), dims=(2, 3))
-    y = ops.fft2_planar(crop.contiguous(), inverse=True)
-    y = torch.roll(y, shifts=(cnx // 2, cny // 2), dims=(2, 3))
-    return magnitude(y.contiguous())[:, 0]
+    # ifftshift = roll by -(n // 2): x'[i] = x[(i + n // 2) mod n]; the real image gets its zero
+    # imaginary plane in the same pass
+    x = _shift_crop(images, 2, (nx, ny), (nx // 2, ny // 2), (0, 0), (0, 0))
+    k = ops.fft2_planar(x)
+    # fftshift (roll by +n // 2), crop_image_at(im_k, nx//2, ny//2, sx, sy) = box
+    # [c - s//2, c + s//2) zero padded, then the ifftshift of ifft2c on the cropped size
+    r1, r2 = sx // 2, sy // 2
+    cnx, cny = 2 * r1, 2 * r2
+    if cnx < 1 or cny < 1:
+        raise ValueError('crop size %r is too small' % (size,))
+    crop = _shift_crop(k, 2, (cnx, cny), (-(nx // 2), -(ny // 2)), (nx // 2 - r1, ny // 2 - r2),
+                       (cnx // 2, cny // 2))
+    y = ops.fft2_planar(crop, inverse=True)
+    # the fftshift of ifft2c and np.abs, with max |.| per image as a by-product
+    amax = torch.empty((B,), dtype=torch.float32, device=images.device) if want_max else None
+    out = _shift_crop(y, 1, (cnx, cny), (-(cnx // 2), -(cny // 2)), (0, 0), (0, 0), absmax=amax)
+    return out[:, 0], amax
+
+
+def center_crop_in_kspace(images, size):
+    """(B,H,W) real -> (B,size,size): magnitude of the image whose centred
+    k-space has been cropped (or zero-padded) to size x size
+    (myImageTransformations.CenterCropInKspace :935-954).  Two library FFTs and
+    three gather passes (csmri_shift_crop); no torch kernels."""
+    return _center_crop(images, size, False)[0]
+
+
+def _divide(images, denom):
+    B, h, w = images.shape
+    with torch.cuda.device(images.device):
+        out = torch.empty_like(images)
+        _lib.check(_lib.lib().csmri_plane_divide(images.data_ptr(), denom.data_ptr(),
+                                                 out.data_ptr(), B, h * w, _stream()))
+    return out
 
 
 def normalize_by_max(images):
-    """x / max|x| per image (rec_transforms.py:47)."""
+    """x / max|x| per image (rec_transforms.py:47), bit-identical to the torch
+    expression ``x / x.abs().amax((1, 2), keepdim=True)``."""
     _check_images(images)
-    return images / images.abs().amax(dim=(1, 2), keepdim=True)
+    images = images.contiguous()
+    B, h, w = images.shape
+    with torch.cuda.device(images.device):
+        amax = torch.empty((B,), dtype=torch.float32, device=images.device)
+        _lib.check(_lib.lib().csmri_plane_absmax(images.data_ptr(), amax.data_ptr(), B, h * w,
+                                                 _stream()))
+    return _divide(images, amax)
+
+
+def crop_and_normalize(images, size):
+    """``normalize_by_max(center_crop_in_kspace(images, size))`` with the maximum
+    taken inside the last gather pass (train_transform :40-47)."""
+    x, amax = _center_crop(images, size, True)
+    return _divide(x.contiguous(), amax)
 
 
 def magnitude(x, lo=0.0, hi=float('inf')):
@@ -106,9 +156,7 @@ class _Transform(object):
             fixed_mask=fixed_mask, num_fixed_masks=num_images)
 
     def __call__(self, images):
-        x = center_crop_in_kspace(images, self.size)
-        x = normalize_by_max(x)
-        return self.undersample(x)
+        return self.undersample(crop_and_normalize(images, self.size))
 
 
 class TrainTransform(_Transform):

@@ -184,6 +184,29 @@ int csmri_magnitude_clamp(const float* x, float* out, int B, int H, int W,
 int csmri_psnr_sum(const float* pred, const float* target, double* sum_sq,
                    int B, int H, int W, float lo, float hi, void* stream);
 
+/* ---- loader tail (data/reconstruction/rec_transforms.py:40-47,62-65) -----------
+ * csmri_shift_crop is the index plumbing of CenterCropInKspace
+ * (myImageTransformations.py:935-954: fft2c -> crop_image_at (:105-117) -> ifft2c
+ * -> abs; fft2c = fftshift . fft2 . ifftshift, mymath.py:18-29) around the two
+ * csmri_fft2 calls: one gather pass per stage instead of roll / slice / pad / roll
+ * copies.  Per axis (y with IH/OH, x with IW/OW):
+ *   out[i] = in[(v + in_roll) mod I] with v = ((i + out_roll) mod O) + off,
+ *   0 where v is outside [0, I) (the zero padding of crop_image_at).
+ * in (B,in_ch,IH,IW), out (B,out_ch,OH,OW); in_ch = 1 reads a real image (imaginary
+ * plane 0); out_ch = 1 writes sqrt(re^2 + im^2) rounded like csmri_magnitude_clamp
+ * and, if absmax != NULL, the maximum per slice into absmax[B].  Rolls must lie in
+ * [0, axis length); off may be negative.
+ * csmri_plane_absmax / csmri_plane_divide are `x / np.max(np.abs(x))`
+ * (rec_transforms.py:47,65) per plane of n contiguous floats: absmax[p] = max |x|,
+ * out = x / denom[p] (IEEE division, bit-identical to the torch expression). */
+int csmri_shift_crop(const float* in, float* out, int B, int in_ch, int IH, int IW,
+                     int out_ch, int OH, int OW, int in_roll_y, int in_roll_x,
+                     int off_y, int off_x, int out_roll_y, int out_roll_x,
+                     float* absmax, void* stream);
+int csmri_plane_absmax(const float* x, float* absmax, int planes, int n, void* stream);
+int csmri_plane_divide(const float* x, const float* denom, float* out, int planes, int n,
+                       void* stream);
+
 /* ---- refinement-path pointwise ops --------------------------------------------
  * A "plane" is n contiguous floats; plane p starts at x + p*pitch (floats), so the
  * real channel of a (B,2,H,W) tensor is addressed with n = H*W, pitch = 2*H*W.

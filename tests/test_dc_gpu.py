@@ -627,6 +627,82 @@ def test_loader_tail_and_reporting_gpu(golden_dir):
         assert orc.rel_l2(batch['target'][i].cpu().numpy(), grp[6:8]) < TOL
 
 
+def _center_crop_torch(images, size):
+    """CenterCropInKspace as a chain of torch index ops around the library FFTs
+    (myImageTransformations.py:935-954, 105-117; mymath.py:18-29) - the formulation
+    the gather kernel replaces."""
+    from csmri_refinement_b200 import ops, rec_transforms as rt
+    sx, sy = (size, size) if isinstance(size, int) else size
+    B, nx, ny = images.shape
+    x = torch.stack([images, torch.zeros_like(images)], dim=1)
+    x = torch.roll(x, shifts=(-(nx // 2), -(ny // 2)), dims=(2, 3))
+    k = ops.fft2_planar(x.contiguous())
+    k = torch.roll(k, shifts=(nx // 2, ny // 2), dims=(2, 3))
+    cx, cy, r1, r2 = nx // 2, ny // 2, sx // 2, sy // 2
+    x1, x2, y1, y2 = cx - r1, cx + r1, cy - r2, cy + r2
+    crop = k[:, :, max(x1, 0):min(x2, nx), max(y1, 0):min(y2, ny)]
+    pad = (max(0, -y1), max(0, y2 - ny), max(0, -x1), max(0, x2 - nx))
+    if any(pad):
+        crop = torch.nn.functional.pad(crop, pad)
+    cnx, cny = crop.shape[2], crop.shape[3]
+    crop = torch.roll(crop, shifts=(-(cnx // 2), -(cny // 2)), dims=(2, 3))
+    y = ops.fft2_planar(crop.contiguous(), inverse=True)
+    y = torch.roll(y, shifts=(cnx // 2, cny // 2), dims=(2, 3))
+    return rt.magnitude(y.contiguous())[:, 0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape,size', [((3, 64, 64), 64), ((2, 64, 64), 32), ((2, 128, 64), (64, 32)),
+                                        ((2, 32, 32), 64), ((1, 64, 128), (128, 64)),
+                                        ((2, 256, 256), 128), ((1, 320, 320), 256),
+                                        ((2, 64, 64), 33)])
+def test_center_crop_gather_passes_equal_the_index_op_chain(shape, size):
+    """csmri_shift_crop (three gather passes) against roll / slice / pad / roll in torch
+    around the same FFTs: pure index maps, so the result is bit-identical - down-crop,
+    zero-padded up-crop, non-square, odd crop size (the reference's box is 2 * (s // 2))."""
+    from csmri_refinement_b200 import rec_transforms as rt
+    g = torch.Generator(device='cuda').manual_seed(sum(shape))
+    im = torch.rand(shape, device='cuda', generator=g)
+    got = rt.center_crop_in_kspace(im, size)
+    want = _center_crop_torch(im, size)
+    assert got.shape == want.shape
+    assert torch.equal(got, want)
+    # fused maximum + division == the torch expression on the cropped image
+    nrm = rt.crop_and_normalize(im, size)
+    assert torch.equal(nrm, want / want.abs().amax(dim=(1, 2), keepdim=True))
+
+
+@pytest.mark.gpu
+def test_normalize_by_max_is_the_torch_expression():
+    from csmri_refinement_b200 import rec_transforms as rt
+    g = torch.Generator(device='cuda').manual_seed(5)
+    for shape in ((1, 7, 5), (3, 64, 64), (2, 320, 320), (5, 33, 1000)):
+        x = torch.randn(shape, device='cuda', generator=g) * 3.0
+        x[0, 0, 0] = -20.0                                  # the maximum of |x| is a negative entry
+        assert torch.equal(rt.normalize_by_max(x), x / x.abs().amax(dim=(1, 2), keepdim=True))
+    with pytest.raises(ValueError):
+        rt.normalize_by_max(torch.zeros(4, 4, device='cuda'))
+
+
+@pytest.mark.gpu
+def test_shift_crop_argument_errors():
+    from csmri_refinement_b200 import _lib
+    lib = _lib.lib()
+    x = torch.zeros(1, 2, 8, 8, device='cuda')
+    y = torch.zeros(1, 2, 8, 8, device='cuda')
+    def call(**kw):
+        a = dict(in_ch=2, out_ch=2, ry=0, absmax=None, out=y)
+        a.update(kw)
+        return lib.csmri_shift_crop(x.data_ptr(), a['out'].data_ptr(), 1, a['in_ch'], 8, 8, a['out_ch'],
+                                    8, 8, a['ry'], 0, 0, 0, 0, 0, a['absmax'], None)
+    assert call() == 0
+    assert call(in_ch=1, out_ch=1) != 0 and b'channels' in lib.csmri_last_error()
+    assert call(ry=8) != 0 and b'modulo' in lib.csmri_last_error()
+    assert call(absmax=y.data_ptr()) != 0 and b'absmax' in lib.csmri_last_error()
+    assert call(out=x) != 0 and b'alias' in lib.csmri_last_error()
+    torch.cuda.synchronize()
+
+
 def test_integration_md_binding_runs_as_written():
     """The ctypes stub INTEGRATION.md shows a reference maintainer (unified
     csmri_dc_prepare / csmri_dc_forward / csmri_dc_adjoint entry points) is
