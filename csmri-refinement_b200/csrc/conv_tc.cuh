@@ -234,13 +234,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < kTcC) bias_s[tid] = (!MASKED && bias != nullptr) ? __ldg(bias + tid) : 0.0f;
   if (warp == kTcMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
                      tc_s32(tmem_slot))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // Programmatic dependent launch: everything above overlaps the tail of the previous kernel
+  // in the stream; nothing it wrote is read before this point.  debug bit 8 (tuning key 10 = 2)
+  // moves the wait behind the weight staging - only valid when the previous kernel does not
+  // write `w` or `bias`.
+  const bool late_wait = (debug & 256) != 0;
+  if (!late_wait) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+  if (tid < kTcC) bias_s[tid] = (!MASKED && bias != nullptr) ? __ldg(bias + tid) : 0.0f;
   // weights: split into hi / lo, laid out as the B operand of each horizontal tap.  All of a
   // thread's loads are issued before the first is used (a rolled loop paid one global-memory
   // round trip per element: ~12 us of the ~20 us fixed cost of a launch).
@@ -270,6 +279,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         *reinterpret_cast<float*>(B_s + off + kTcBPart) = lo;
       }
     }
+  }
+  if (late_wait) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -166,7 +166,6 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
             for (int o = 0; o < BT / 2; ++o)
               acc[o] = f2fma(wp[c][ky * 3 + kx][o], mk(win[c][ky][kx], win[c][ky][kx]), acc[o]);
-#pragma unroll
       const unsigned bits = sw[r] >> cob;
 #pragma unroll
       for (int o = 0; o < BT / 2; ++o) {

@@ -203,6 +203,9 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // programmatic dependent launch: the setup above overlaps the previous kernel's tail
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -444,6 +447,8 @@ __global__ void __launch_bounds__(128)
     conv3x3_wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                    const float* __restrict__ bias_partial, float* __restrict__ db, int nctas) {
   const int e = blockIdx.x * 128 + threadIdx.x;                // (kx, co, ky, ci), then 32 bias entries
+  asm volatile("griddepcontrol.wait;" ::: "memory");           // the partial blocks of the kernel before
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (e >= kWtcPartial) {
     const int co = e - kWtcPartial;
     if (co < kWtcC && db != nullptr) {

@@ -738,6 +738,12 @@ static int g_strip_variant = 0;  // tuning knobs, see csmri_set_variant / csmri_
 static int g_tc_debug = 0;       // conv3x3_tc_kernel probe bits (tuning key 6)
 static int g_wgrad_tc = 1;       // 32 -> 32 weight gradient on the tensor cores (tuning key 7; 0 = SIMT kernel)
 static int g_thin_tma = 1;       // 32 -> 2 thin convolution staged by TMA (tuning key 8; 0 = cp.async staging)
+static int g_conv_pdl = 0;       // programmatic dependent launch for the tensor-core convolution kernels
+                                 // (tuning key 10; 0 = plain launches, 1 = wait before the first global read,
+                                 // 2 = wait after the weight staging).  Measured: no gain - D5C5 step 13.56 /
+                                 // 13.67-13.93 / 13.71-13.75 ms for 0 / 1 / 2 (profiles/r2_conv_pdl.json): a
+                                 // 200 KB-smem CTA cannot share an SM with its predecessor, so there is no
+                                 // prologue to overlap.  Off by default.
 static int g_general_chunk_mib = 0;   // general-mask path: MiB of hybrid scratch per chunk (tuning key 9; 0 = whole batch per pass)
 static long long* g_trace = nullptr;  // tuning probe: per-CTA timeline buffers (2 x 1024 x 40)
 static int g_trace_launch = 0;
@@ -791,6 +797,25 @@ static int make_tile_map(CUtensorMap* m, const float* ptr, int B, int H, int W, 
 
 // (N,32,H,W) fp32 viewed as {W, H, 32 N}; one box = 32 channels x 32 pixels of one row,
 // 128-byte swizzled (the K-major UMMA operand layout), out-of-range rows / columns zero-filled
+// Launch with the programmatic-stream-serialization attribute: the kernel may start while the
+// previous kernel in the stream drains and blocks in griddepcontrol.wait before its first
+// dependent access (conv_tc.cuh, conv_wgrad_tc.cuh).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_conv_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 static int make_conv_map(CUtensorMap* m, const float* ptr, int N, int C, int H, int W) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) return fail(CSMRI_E_CUDA, "cuTensorMapEncodeTiled is unavailable");
@@ -1240,6 +1265,7 @@ int csmri_set_tuning(int key, int value) {
   else if (key == 7) g_wgrad_tc = value != 0;
   else if (key == 8) g_thin_tma = value != 0;
   else if (key == 9) g_general_chunk_mib = value < 0 ? 0 : value;
+  else if (key == 10) g_conv_pdl = value < 0 || value > 2 ? 0 : value;
   else return fail(CSMRI_E_ARG, "unknown tuning key %d", key);
   return CSMRI_OK;
 }
@@ -1788,10 +1814,10 @@ static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float*
     if (ctas > nitems) ctas = nitems;
     CSMRI_TRY(set_smem(conv3x3_wgrad_tc_kernel, kWtcSmemBytes));
     float* bias_partial = db != nullptr ? (float*)workspace + (size_t)ctas * kWtcPartial : nullptr;
-    conv3x3_wgrad_tc_kernel<<<ctas, kWtcThreads, kWtcSmemBytes, s>>>(tm_x, tm_dy, dy, (float*)workspace,
-                                                                     bias_partial, H, W, nitems, 0);
-    conv3x3_wgrad_tc_reduce_kernel<<<(kWtcPartial + kWtcC + 127) / 128, 128, 0, s>>>(
-        (const float*)workspace, dw, bias_partial, db, ctas);
+    CSMRI_CUDA(launch_pdl(conv3x3_wgrad_tc_kernel, dim3(ctas), dim3(kWtcThreads), kWtcSmemBytes, s, tm_x,
+                          tm_dy, dy, (float*)workspace, bias_partial, H, W, nitems, 0));
+    CSMRI_CUDA(launch_pdl(conv3x3_wgrad_tc_reduce_kernel, dim3((kWtcPartial + kWtcC + 127) / 128), dim3(128),
+                          0, s, (const float*)workspace, dw, (const float*)bias_partial, db, ctas));
     CSMRI_CUDA(cudaGetLastError());
     return CSMRI_OK;
   }
@@ -1896,14 +1922,17 @@ static int conv3x3_tc_launch(const float* x, const float* w, const float* bias, 
   if (nitems_ll > 0x7fffffffLL) return fail(CSMRI_E_SHAPE, "too many tiles");
   int grid = sm_count();
   if (grid > nitems_ll) grid = (int)nitems_ll;
+  const int dbg = g_tc_debug | (g_conv_pdl == 2 ? 256 : 0);
+  cudaStream_t s = (cudaStream_t)stream;
   if (masked) {
     CSMRI_TRY(set_smem(conv3x3_tc_kernel<true>, kTcSmemBytes));
-    conv3x3_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(
-        x, w, nullptr, y, signs, nullptr, H, W, (int)nitems_ll, slope, transpose_flip != 0, g_tc_debug);
+    CSMRI_CUDA(launch_pdl(conv3x3_tc_kernel<true>, dim3(grid), dim3(kTcThreads), kTcSmemBytes, s, x, w,
+                          (const float*)nullptr, y, signs, (uint32_t*)nullptr, H, W, (int)nitems_ll, slope,
+                          (int)(transpose_flip != 0), dbg));
   } else {
     CSMRI_TRY(set_smem(conv3x3_tc_kernel<false>, kTcSmemBytes));
-    conv3x3_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(
-        x, w, bias, y, signs, in_signs, H, W, (int)nitems_ll, slope, transpose_flip != 0, g_tc_debug);
+    CSMRI_CUDA(launch_pdl(conv3x3_tc_kernel<false>, dim3(grid), dim3(kTcThreads), kTcSmemBytes, s, x, w, bias,
+                          y, signs, in_signs, H, W, (int)nitems_ll, slope, (int)(transpose_flip != 0), dbg));
   }
   CSMRI_CUDA(cudaGetLastError());
   return CSMRI_OK;
