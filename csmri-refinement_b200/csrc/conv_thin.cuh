@@ -321,8 +321,10 @@ __global__ void __launch_bounds__(256, 2)
   const cf bp = bias != nullptr ? mk(__ldg(bias), __ldg(bias + 1)) : mk(0.0f, 0.0f);
   const size_t plane = (size_t)H * W;
   __syncthreads();
-  auto stage_tile = [&](int tile, int b) {          // one thread: expect the bytes, fire the box
-    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
+  // Tile coordinates are decoded once per tile (two runtime divisions) and shared by the TMA
+  // issue, the halo loads and the output addresses; the halo entry (channel, row) a thread
+  // owns does not depend on the tile.
+  auto stage_tile = [&](const ThinTile t, int b) {   // one thread: expect the bytes, fire the box
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(thin_smem + b * kThinTmaBuf);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full + 8 * b),
                  "r"((uint32_t)(kThinTmaBox * 4))
@@ -335,27 +337,31 @@ __global__ void __launch_bounds__(256, 2)
   };
   // right halo column: 32 channels x 10 rows = 320 values per tile, thread i takes entries i and
   // i + 256 (entry e = channel * 10 + row), requested one tile ahead
-  auto fetch_halo = [&](int tile, int e) -> float {
-    if (e >= A * (R + 2)) return 0.0f;
-    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
-    const int c = e / (R + 2), r = e - c * (R + 2);
-    const int gy = t.y0 - 1 + r, gx = t.x0 + 32;
-    if (gy < 0 || gy >= H || gx >= W) return 0.0f;
-    return __ldg(x + ((size_t)t.n * A + c) * plane + (size_t)gy * W + gx);
+  const int e1 = threadIdx.x + 256;
+  const bool has1 = e1 < A * (R + 2);
+  const int hc0 = threadIdx.x / (R + 2), hr0 = threadIdx.x - hc0 * (R + 2) - 1;
+  const int hc1 = has1 ? e1 / (R + 2) : 0, hr1 = has1 ? e1 - hc1 * (R + 2) - 1 : 0;
+  const size_t ho0 = (size_t)hc0 * plane, ho1 = (size_t)hc1 * plane;
+  auto fetch_halo = [&](const ThinTile t, int hr, size_t ho, bool have) -> float {
+    const int gy = t.y0 + hr, gx = t.x0 + 32;
+    if (!have || gy < 0 || gy >= H || gx >= W) return 0.0f;
+    return __ldg(x + (size_t)t.n * A * plane + ho + (size_t)gy * W + gx);
   };
   int tile = blockIdx.x;
   float h0 = 0.0f, h1 = 0.0f;
+  ThinTile tc = thin_tile(tile < ntiles ? tile : 0, tiles_x, tiles_y, R);
   if (tile < ntiles) {
-    if (threadIdx.x == 0) stage_tile(tile, 0);
-    h0 = fetch_halo(tile, threadIdx.x);
-    h1 = fetch_halo(tile, threadIdx.x + 256);
+    if (threadIdx.x == 0) stage_tile(tc, 0);
+    h0 = fetch_halo(tc, hr0, ho0, true);
+    h1 = fetch_halo(tc, hr1, ho1, has1);
   }
   for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
     const int b = it & 1;
     const float* cur = thin_smem + b * kThinTmaBuf + cib * (R + 2) * kThinTmaPC;
     const int next = tile + gridDim.x;
+    const ThinTile tn = thin_tile(next < ntiles ? next : 0, tiles_x, tiles_y, R);
     // buffer b ^ 1 was last read in iteration it - 1, whose trailing __syncthreads has passed
-    if (threadIdx.x == 0 && next < ntiles) stage_tile(next, b ^ 1);
+    if (threadIdx.x == 0 && next < ntiles) stage_tile(tn, b ^ 1);
     {
       uint32_t done;
       do {
@@ -370,11 +376,11 @@ __global__ void __launch_bounds__(256, 2)
     {   // the box has landed: drop this tile's right halo column into the slots behind the rows
       float* buf = thin_smem + b * kThinTmaBuf;
       buf[(threadIdx.x + 1) * kThinTmaPC] = h0;
-      if (threadIdx.x + 256 < A * (R + 2)) buf[(threadIdx.x + 256 + 1) * kThinTmaPC] = h1;
+      if (has1) buf[(e1 + 1) * kThinTmaPC] = h1;
     }
     if (next < ntiles) {
-      h0 = fetch_halo(next, threadIdx.x);
-      h1 = fetch_halo(next, threadIdx.x + 256);
+      h0 = fetch_halo(tn, hr0, ho0, true);
+      h1 = fetch_halo(tn, hr1, ho1, has1);
     }
     __syncthreads();
     float win[AT][3][3];
@@ -406,8 +412,7 @@ __global__ void __launch_bounds__(256, 2)
       part[(warp * R + r) * 32 + lane] = acc;
     }
     __syncthreads();   // partial sums complete; everyone is done reading the tile
-    const ThinTile t = thin_tile(tile, tiles_x, tiles_y, R);
-    float* yn = y + (size_t)t.n * 2 * plane + (size_t)t.y0 * W + t.x0;
+    float* yn = y + (size_t)tc.n * 2 * plane + (size_t)tc.y0 * W + tc.x0;
     {
       const int r = threadIdx.x >> 5;                 // 8 rows x 32 pixels = 256 threads
       cf sum = bp;
@@ -416,6 +421,7 @@ __global__ void __launch_bounds__(256, 2)
       yn[(size_t)r * W + lane] = sum.x;
       yn[plane + (size_t)r * W + lane] = sum.y;
     }
+    tc = tn;
     __syncthreads();   // partial sums consumed before the next tile overwrites them
   }
 }
