@@ -19,6 +19,7 @@ Anything else (other kernel sizes, strides, dilations, channels_last, autocast,
 CPU tensors) keeps torch's own kernels.
 """
 import torch
+from torch.autograd.function import once_differentiable
 from torch import nn
 
 from . import _lib
@@ -301,6 +302,7 @@ class _Conv3x3(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable     # raw kernels on data pointers: a second derivative would be silently wrong
     def backward(ctx, grad_out):
         pad = ctx.pad
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
@@ -395,6 +397,7 @@ class _TcChain(torch.autograd.Function):
         return acts[-1], signs[-1]
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_out, _grad_signs):
         n, slope = ctx.n, ctx.slope
         saved = ctx.saved_tensors

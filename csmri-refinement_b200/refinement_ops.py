@@ -15,6 +15,7 @@ float32 expression op by op, so results are bit-identical to the torch
 evaluation.  CUDA tensors only; no fallback.
 """
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib, rec_transforms
 
@@ -96,6 +97,7 @@ class _RefineRealPenaltyAdd(torch.autograd.Function):
         return pred
 
     @staticmethod
+    @once_differentiable     # raw kernel on data pointers
     def backward(ctx, grad_pred):
         out_learnable, scale_param, maximum = ctx.saved_tensors
         grad_pred = grad_pred.contiguous()

@@ -703,6 +703,19 @@ def test_shift_crop_argument_errors():
     torch.cuda.synchronize()
 
 
+@pytest.mark.gpu
+def test_conv_double_backward_is_refused():
+    """The convolution backward passes are raw kernels; asking autograd for a second
+    derivative through them must raise instead of returning a silently wrong value."""
+    from csmri_refinement_b200 import conv
+    torch.manual_seed(0)
+    layer = conv.Conv2d(32, 32, 3, padding=1).cuda()
+    x = torch.randn(1, 32, 16, 128, device='cuda', requires_grad=True)
+    (g,) = torch.autograd.grad(layer(x).square().sum(), x, create_graph=True)
+    with pytest.raises(RuntimeError, match='once_differentiable|twice'):
+        g.sum().backward()
+
+
 def test_integration_md_binding_runs_as_written():
     """The ctypes stub INTEGRATION.md shows a reference maintainer (unified
     csmri_dc_prepare / csmri_dc_forward / csmri_dc_adjoint entry points) is
