@@ -100,6 +100,10 @@ _SIGNATURES = {
                             [ctypes.c_void_p]),
     'csmri_conv3x3_wgrad_thin_bias': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_void_p] + [ctypes.c_int] * 3 +
                                       [ctypes.c_void_p]),
+    'csmri_conv3x3_wgrad_thin_in_bias': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_void_p] + [ctypes.c_int] * 3 +
+                                      [ctypes.c_void_p]),
+    'csmri_conv3x3_thin_dgrad': (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p, _c_float_p] +
+                                 [ctypes.c_int] * 5 + [ctypes.c_float, ctypes.c_void_p]),
     'csmri_conv3x3_thin_masked': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 3 +
                                   [ctypes.c_float, ctypes.c_void_p]),
     'csmri_conv3x3_wgrad_bias': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_void_p] + [ctypes.c_int] * 3 +

@@ -26,6 +26,7 @@ from . import _lib
 
 _ENABLED = True
 _TC_ENABLED = True
+_THIN_IN_BIAS = True      # 32 -> 2 layer: bias gradient from the weight-gradient kernel
 # experimental: weight gradient on a side stream, concurrently with the data gradient
 import os as _os
 _WGRAD_STREAM = _os.environ.get('CSMRI_WGRAD_STREAM', '0') == '1'
@@ -234,6 +235,23 @@ def conv3x3_wgrad_thin_bias(x, grad_out):
     return dw, db
 
 
+def conv3x3_wgrad_thin_in_bias(x, grad_out):
+    """(dW, db) of RecNet's 32 -> 2 layer (zero padding 1), bias gradient as a by-product."""
+    _require_cuda_f32(x, grad_out)
+    x, grad_out = _aligned16(x.contiguous()), _aligned16(grad_out.contiguous())
+    n, _, h, w = grad_out.shape
+    lib = _lib.lib()
+    with torch.cuda.device(x.device):
+        dw = torch.empty((2, 32, 3, 3), dtype=torch.float32, device=x.device)
+        db = torch.empty((2,), dtype=torch.float32, device=x.device)
+        ws = torch.empty((lib.csmri_conv3x3_wgrad_workspace_bytes(32, 2) // 4,),
+                         dtype=torch.float32, device=x.device)
+        _lib.check(lib.csmri_conv3x3_wgrad_thin_in_bias(
+            x.data_ptr(), grad_out.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), n, h, w,
+            torch.cuda.current_stream().cuda_stream))
+    return dw, db
+
+
 def _is_tc(x, weight, pad):
     """Shapes csmri_conv3x3_tc covers: 32 -> 32 channels, padding 1, H % 8 == 0, W % 128 == 0."""
     return (_TC_ENABLED and pad == 1 and tuple(weight.shape[:2]) == (32, 32) and
@@ -260,6 +278,28 @@ def conv3x3_thin_masked(x, weight, signs, act_slope):
             x.data_ptr(), weight.data_ptr(), signs.data_ptr(), y.data_ptr(), n, h, w,
             float(act_slope), torch.cuda.current_stream().cuda_stream))
     return y
+
+
+def conv3x3_thin_dgrad(grad_out, weight, signs=None, act_slope=0.0):
+    """Data gradient of a thin layer (2 -> 32 or 32 -> 2, padding 1) from the layer's own
+    weights - no flipped / transposed copy.  ``signs`` (32 -> 2 layer only): also apply the
+    derivative of the LeakyReLU(act_slope) that produced the layer's input."""
+    _require_cuda_f32(grad_out, weight)
+    grad_out, weight = _aligned16(grad_out.contiguous()), weight.contiguous()
+    n, co, h, w = grad_out.shape
+    ci = weight.shape[1]
+    if tuple(weight.shape) != (co, ci, 3, 3) or (ci, co) not in ((2, 32), (32, 2)):
+        raise RuntimeError('conv3x3_thin_dgrad covers the 2 -> 32 and 32 -> 2 layers (got %s, %s)'
+                           % (tuple(grad_out.shape), tuple(weight.shape)))
+    if signs is not None and (signs.dtype != torch.int32 or tuple(signs.shape) != (n, h, w)
+                              or not signs.is_cuda or not signs.is_contiguous()):
+        raise RuntimeError('signs must be a contiguous CUDA int32 tensor of shape (N, H, W)')
+    with torch.cuda.device(grad_out.device):
+        dx = torch.empty((n, ci, h, w), dtype=torch.float32, device=grad_out.device)
+        _lib.check(_lib.lib().csmri_conv3x3_thin_dgrad(
+            grad_out.data_ptr(), weight.data_ptr(), signs.data_ptr() if signs is not None else None,
+            dx.data_ptr(), n, ci, co, h, w, float(act_slope), torch.cuda.current_stream().cuda_stream))
+    return dx
 
 
 def _is_thin(weight, pad):
@@ -315,7 +355,7 @@ class _Conv3x3(torch.autograd.Function):
             x, weight, y = ctx.saved_tensors
             gw, gb = conv3x3_wgrad_thin_bias(x, grad_out) if need_w or need_b else (None, None)
             if need_x:
-                gx = conv3x3_thin(grad_out, weight.flip(2, 3).transpose(0, 1), None, 0.0)
+                gx = conv3x3_thin_dgrad(grad_out, weight)
             return gx, gw if need_w else None, gb if need_b else None, None, None, None, None, None
         else:
             x, weight, y = ctx.saved_tensors
@@ -332,13 +372,16 @@ class _Conv3x3(torch.autograd.Function):
                 gw = conv3x3_wgrad(x, grad_out, pad)
             fork = (cur, side)
         if ctx.thin:
-            if need_b and gb is None:
+            if need_b and gb is None and need_w and weight.shape[0] == 2 and _THIN_IN_BIAS \
+                    and x.shape[2] % 8 == 0 and x.shape[3] % 32 == 0:
+                gw, gb = conv3x3_wgrad_thin_in_bias(x, grad_out)   # db rides on the weight gradient
+                need_w = False
+            elif need_b and gb is None:
                 gb = grad_out.sum(dim=(0, 2, 3))
             if need_x and ctx.in_signs is not None:
-                gx = conv3x3_thin_masked(grad_out, weight.flip(2, 3).transpose(0, 1), ctx.in_signs,
-                                         ctx.in_slope)
+                gx = conv3x3_thin_dgrad(grad_out, weight, ctx.in_signs, ctx.in_slope)
             elif need_x:   # the same kernel family on flipped, transposed weights
-                gx = conv3x3_thin(grad_out, weight.flip(2, 3).transpose(0, 1), None, 0.0)
+                gx = conv3x3_thin_dgrad(grad_out, weight)
         elif ctx.tc:
             if need_b and gb is None:
                 gb = grad_out.sum(dim=(0, 2, 3))
@@ -358,7 +401,7 @@ class _Conv3x3(torch.autograd.Function):
             cur.wait_stream(side)
             gw.record_stream(cur)
             grad_out.record_stream(side)
-        elif need_w:
+        elif need_w and gw is None:
             gw = conv3x3_wgrad(x, grad_out, pad)
         return gx, gw, gb, None, None, None, None, None
 

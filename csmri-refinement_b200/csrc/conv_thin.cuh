@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256, 2)
     conv3x3_thin_out_kernel(const float* __restrict__ x, const float* __restrict__ w,
                             const float* __restrict__ bias, float* __restrict__ y, int H, int W,
                             int tiles_x, int tiles_y, int ntiles, float slope,
-                            const unsigned* __restrict__ msigns, float mslope) {
+                            const unsigned* __restrict__ msigns, float mslope, int wtf) {
   // msigns (optional; (N,H,W) uint32 sign words, see csmri_conv3x3_tc_signs): the result of
   // channel c is multiplied by (bit c ? 1 : mslope) - this kernel as the data gradient of the
   // 32 -> 2 layer, followed by the backward of the LeakyReLU in front of that layer
@@ -103,8 +103,10 @@ __global__ void __launch_bounds__(256, 2)
     for (int t = 0; t < 9; ++t)
 #pragma unroll
       for (int o = 0; o < BT / 2; ++o)
-        wp[c][t][o] = mk(__ldg(w + ((cob + 2 * o) * A + c) * 9 + t),
-                         __ldg(w + ((cob + 2 * o + 1) * A + c) * 9 + t));
+        wp[c][t][o] = wtf ? mk(__ldg(w + (c * B + cob + 2 * o) * 9 + 8 - t),       // w is (A, B, 3, 3): the
+                               __ldg(w + (c * B + cob + 2 * o + 1) * 9 + 8 - t))   // operator transposed + mirrored
+                          : mk(__ldg(w + ((cob + 2 * o) * A + c) * 9 + t),
+                               __ldg(w + ((cob + 2 * o + 1) * A + c) * 9 + t));
   cf bp[BT / 2];
 #pragma unroll
   for (int o = 0; o < BT / 2; ++o)
@@ -196,7 +198,7 @@ constexpr int kThinInSmem = (2 * kThinInBuf + 8 * kThinInRows * 32 * 2) * 4;    
 __global__ void __launch_bounds__(256, 2)
     conv3x3_thin_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                            const float* __restrict__ bias, float* __restrict__ y, int H, int W,
-                           int tiles_x, int tiles_y, int ntiles) {
+                           int tiles_x, int tiles_y, int ntiles, int wtf) {
   constexpr int A = 32, AT = 4, R = kThinInRows;
   extern __shared__ __align__(16) float thin_smem[];
   cf* part = reinterpret_cast<cf*>(thin_smem + 2 * kThinInBuf);   // [8][R][32]
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(256, 2)
   for (int c = 0; c < AT; ++c)
 #pragma unroll
     for (int t = 0; t < 9; ++t)
-      wp[c][t] = mk(__ldg(w + (cib + c) * 9 + t), __ldg(w + (A + cib + c) * 9 + t));
+      wp[c][t] = wtf ? mk(__ldg(w + ((cib + c) * 2 + 0) * 9 + 8 - t), __ldg(w + ((cib + c) * 2 + 1) * 9 + 8 - t))
+                     : mk(__ldg(w + (cib + c) * 9 + t), __ldg(w + (A + cib + c) * 9 + t));
   const cf bp = bias != nullptr ? mk(__ldg(bias), __ldg(bias + 1)) : mk(0.0f, 0.0f);
   const size_t plane = (size_t)H * W;
   auto stage_tile = [&](int tile, float* buf) {   // warp g stages its own four channels
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(256, 2)
     conv3x3_thin_in_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ x,
                                const float* __restrict__ w, const float* __restrict__ bias,
                                float* __restrict__ y, int H, int W,
-                               int tiles_x, int tiles_y, int ntiles) {
+                               int tiles_x, int tiles_y, int ntiles, int wtf) {
   constexpr int A = 32, AT = 4, R = kThinInRows;
   extern __shared__ unsigned char thin_tma_raw[];
   // TMA destinations are 128-byte aligned (the dynamic shared-memory base is only 16)
@@ -317,7 +320,8 @@ __global__ void __launch_bounds__(256, 2)
   for (int c = 0; c < AT; ++c)
 #pragma unroll
     for (int t = 0; t < 9; ++t)
-      wp[c][t] = mk(__ldg(w + (cib + c) * 9 + t), __ldg(w + (A + cib + c) * 9 + t));
+      wp[c][t] = wtf ? mk(__ldg(w + ((cib + c) * 2 + 0) * 9 + 8 - t), __ldg(w + ((cib + c) * 2 + 1) * 9 + 8 - t))
+                     : mk(__ldg(w + (cib + c) * 9 + t), __ldg(w + (A + cib + c) * 9 + t));
   const cf bp = bias != nullptr ? mk(__ldg(bias), __ldg(bias + 1)) : mk(0.0f, 0.0f);
   const size_t plane = (size_t)H * W;
   __syncthreads();
@@ -533,8 +537,11 @@ constexpr int kThinWgTmaSmem = 2 * kThinTmaBuf * 4 + 64 + 128;   // two tile buf
 
 __global__ void __launch_bounds__(256, 2)
     conv3x3_wgrad_thin_staged_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const float* __restrict__ x,
-                                         const float* __restrict__ dy, float* __restrict__ partial, int H,
-                                         int W, int tiles_x, int tiles_y, int ntiles) {
+                                         const float* __restrict__ dy, float* __restrict__ partial,
+                                         float* __restrict__ bias_partial, int H, int W, int tiles_x,
+                                         int tiles_y, int ntiles) {
+  // bias_partial (optional, gridDim.x x 2 floats): per-CTA sums of dy = the layer's bias gradient;
+  // every warp holds its pixels' two dY values anyway, warp 0 adds them up
   constexpr int A = 32, AT = 4, R = kThinInRows;
   extern __shared__ unsigned char thin_tma_raw[];
   float* thin_smem = reinterpret_cast<float*>(
@@ -555,6 +562,8 @@ __global__ void __launch_bounds__(256, 2)
   for (int c = 0; c < AT; ++c)
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[c][t] = mk(0.0f, 0.0f);
+  cf bsum = mk(0.0f, 0.0f);                  // warp 0: sum of dY over this lane's pixels
+  const bool want_bias = bias_partial != nullptr && warp == 0;
   const size_t plane = (size_t)H * W;
   __syncthreads();
   auto stage_tile = [&](int tile, int b) {
@@ -645,8 +654,21 @@ __global__ void __launch_bounds__(256, 2)
           for (int kx = 0; kx < 3; ++kx)
             acc[c][ky * 3 + kx] =
                 f2fma(d, mk(win[c][ky][kx], win[c][ky][kx]), acc[c][ky * 3 + kx]);
+      if (want_bias) bsum = f2add(bsum, d);
     }
     __syncthreads();   // everyone is done with buffer b before it becomes a TMA target again
+  }
+  if (want_bias) {
+    float a = bsum.x, b = bsum.y;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, m);
+      b += __shfl_xor_sync(0xffffffffu, b, m);
+    }
+    if (lane == 0) {
+      bias_partial[blockIdx.x * 2 + 0] = a;
+      bias_partial[blockIdx.x * 2 + 1] = b;
+    }
   }
   // fold the 32 pixel-lanes; lane 0 writes the warp's sums in dW order [o][c][tap]
   float* dst = partial + (size_t)blockIdx.x * (A * 2 * 9);

@@ -1723,6 +1723,12 @@ int csmri_conv3x3_wgrad_thin_bias(const float* x, const float* dy, float* dw, fl
   return conv3x3_wgrad_impl(x, dy, dw, db, workspace, N, 2, 32, H, W, 1, stream);
 }
 
+int csmri_conv3x3_wgrad_thin_in_bias(const float* x, const float* dy, float* dw, float* db, void* workspace,
+                                     int N, int H, int W, void* stream) {
+  CSMRI_TRY(check_ptr(db, "db"));
+  return conv3x3_wgrad_impl(x, dy, dw, db, workspace, N, 32, 2, H, W, 1, stream);
+}
+
 static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float* db, void* workspace, int N,
                               int CI, int CO, int H, int W, int pad, void* stream) {
   CSMRI_TRY(wgrad_check_channels(CI, CO));
@@ -1761,8 +1767,10 @@ static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float*
                                                                 H, W, tiles_x, ty8, nt8);
       if (db != nullptr)
         wgrad_thin_reduce_kernel<<<1, 64, 0, s>>>(bias_partial, db, CO, ctas);
-    } else if (db != nullptr) {
-      return fail(CSMRI_E_SHAPE, "conv3x3_wgrad_bias: shape not covered (2 -> 32 needs pad 1 and a 16-byte aligned x)");
+    } else if (db != nullptr && !(CI == 32 && pad == 1 && ((uintptr_t)x & 15u) == 0 && g_thin_tma &&
+                                  encode_tiled_fn() != nullptr)) {
+      return fail(CSMRI_E_SHAPE, "conv3x3_wgrad_bias: shape not covered (the thin layers need pad 1 and a "
+                                 "16-byte aligned x, 32 -> 2 also the TMA-staged kernel)");
     } else if (CI == 2) {
       conv3x3_wgrad_thin_kernel<2, 4, true><<<ctas, 256, 0, s>>>(
           x, dy, (float*)workspace, H, W, HI, WI, pad, tiles_x, tiles_y, ntiles);
@@ -1785,8 +1793,10 @@ static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float*
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(CSMRI_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
         CSMRI_TRY(set_smem(conv3x3_wgrad_thin_staged_tma_kernel, kThinWgTmaSmem));
+        float* bias_partial = db != nullptr ? (float*)workspace + (size_t)ctas * CI * CO * 9 : nullptr;
         conv3x3_wgrad_thin_staged_tma_kernel<<<ctas, 256, kThinWgTmaSmem, s>>>(
-            tm, x, dy, (float*)workspace, H, W, tiles_x, ty8, nt8);
+            tm, x, dy, (float*)workspace, bias_partial, H, W, tiles_x, ty8, nt8);
+        if (db != nullptr) wgrad_thin_reduce_kernel<<<1, 64, 0, s>>>(bias_partial, db, CO, ctas);
       } else {
         CSMRI_TRY(set_smem(conv3x3_wgrad_thin_staged_kernel, smem_staged));
         conv3x3_wgrad_thin_staged_kernel<<<ctas, 256, smem_staged, s>>>(x, dy, (float*)workspace, H, W,
@@ -1843,7 +1853,7 @@ static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float*
 
 static int conv3x3_thin_impl(const float* x, const float* w, const float* bias, float* y, int N, int A,
                              int B, int H, int W, float slope, const unsigned* msigns, float mslope,
-                             void* stream) {
+                             void* stream, int wtf = 0) {
   if (!wgrad_thin(A, B))
     return fail(CSMRI_E_SHAPE, "conv3x3_thin handles 2 -> 32 and 32 -> 2 channels (got %d -> %d)", A, B);
   if (N <= 0 || H <= 0 || W <= 0 || H % kThinOutRows != 0 || W % 32 != 0)
@@ -1864,7 +1874,7 @@ static int conv3x3_thin_impl(const float* x, const float* w, const float* bias, 
   cudaStream_t s = (cudaStream_t)stream;
   if (A == 2) {
     conv3x3_thin_out_kernel<<<ctas, 256, 0, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
-                                                 (int)ntiles_ll, slope, msigns, mslope);
+                                                 (int)ntiles_ll, slope, msigns, mslope, wtf);
   } else {
     if (g_thin_tma) {
       // input tiles by TMA (box {36, 10, 32} from (x0 - 4, y0 - 1), zero-filled outside the image)
@@ -1881,11 +1891,11 @@ static int conv3x3_thin_impl(const float* x, const float* w, const float* bias, 
       if (r != CUDA_SUCCESS) return fail(CSMRI_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
       CSMRI_TRY(set_smem(conv3x3_thin_in_tma_kernel, kThinTmaSmem));
       conv3x3_thin_in_tma_kernel<<<ctas, 256, kThinTmaSmem, s>>>(tm, x, w, bias, y, H, W, tiles_x, tiles_y,
-                                                                 (int)ntiles_ll);
+                                                                 (int)ntiles_ll, wtf);
     } else {
       CSMRI_TRY(set_smem(conv3x3_thin_in_kernel, kThinInSmem));
       conv3x3_thin_in_kernel<<<ctas, 256, kThinInSmem, s>>>(x, w, bias, y, H, W, tiles_x, tiles_y,
-                                                            (int)ntiles_ll);
+                                                            (int)ntiles_ll, wtf);
     }
   }
   CSMRI_CUDA(cudaGetLastError());
@@ -1902,6 +1912,16 @@ int csmri_conv3x3_thin_masked(const float* x, const float* w, const unsigned* si
   CSMRI_TRY(check_ptr(signs, "signs"));
   if (!(act_slope >= 0.0f)) return fail(CSMRI_E_ARG, "act_slope must be >= 0 (got %g)", act_slope);
   return conv3x3_thin_impl(x, w, nullptr, y, N, 2, 32, H, W, 0.0f, signs, act_slope, stream);
+}
+
+int csmri_conv3x3_thin_dgrad(const float* dy, const float* w, const unsigned* signs, float* dx, int N,
+                             int CI, int CO, int H, int W, float act_slope, void* stream) {
+  // dx = conv(dy, w transposed and mirrored): the thin kernel of the opposite shape reading the
+  // layer's own (CO, CI, 3, 3) weights through the transposed index map
+  if (signs != nullptr && CI != 32)
+    return fail(CSMRI_E_ARG, "signs (the derivative of the activation that produced x) need CI = 32");
+  if (!(act_slope >= 0.0f)) return fail(CSMRI_E_ARG, "act_slope must be >= 0 (got %g)", act_slope);
+  return conv3x3_thin_impl(dy, w, nullptr, dx, N, CO, CI, H, W, 0.0f, signs, act_slope, stream, 1);
 }
 
 // ---- 32 -> 32 convolution on the tensor cores, 3xTF32 (conv_tc.cuh) -------------

@@ -270,6 +270,10 @@ int csmri_conv3x3_wgrad_bias(const float* x, const float* dy, float* dw, float* 
  * W % 32 == 0, x 16-byte aligned): dw (32,2,3,3) and db (32). */
 int csmri_conv3x3_wgrad_thin_bias(const float* x, const float* dy, float* dw, float* db,
                                   void* workspace, int N, int H, int W, void* stream);
+/* And for the 32 -> 2 layer that closes a block (models/recnet.py:48; x (N,32,H,W), dy (N,2,H,W),
+ * same shape rules): dw (2,32,3,3) and db (2).  Workspace of csmri_conv3x3_wgrad_workspace_bytes(32, 2). */
+int csmri_conv3x3_wgrad_thin_in_bias(const float* x, const float* dy, float* dw, float* db,
+                                     void* workspace, int N, int H, int W, void* stream);
 
 /* RecNet's thin 3x3 convolutions (first / last layer of a block, models/recnet.py:
  * 45-48), stride 1, zero padding 1:  y = act(conv(x, w) + bias)
@@ -287,6 +291,14 @@ int csmri_conv3x3_thin(const float* x, const float* w, const float* bias, float*
  * 45-48), in one pass.  x (N,2,H,W), w (32,2,3,3), signs (N,H,W) uint32, y (N,32,H,W). */
 int csmri_conv3x3_thin_masked(const float* x, const float* w, const unsigned* signs, float* y,
                               int N, int H, int W, float act_slope, void* stream);
+/* Data gradient of a thin layer with weights w (CO,CI,3,3), zero padding 1 - what autograd's
+ * convolution backward returns for the layer's input: dy (N,CO,H,W) -> dx (N,CI,H,W).  The
+ * kernel of the opposite shape reads w through the transposed, mirrored index map (no flipped
+ * copy of the weights is made).  signs (optional, CI = 32 only): as csmri_conv3x3_thin_masked,
+ * dx is also multiplied by (bit c ? 1 : act_slope) - the derivative of the LeakyReLU that
+ * produced the layer's input. */
+int csmri_conv3x3_thin_dgrad(const float* dy, const float* w, const unsigned* signs, float* dx,
+                             int N, int CI, int CO, int H, int W, float act_slope, void* stream);
 
 /* RecNet's 32 -> 32 channel 3x3 convolutions (the inner layers of every ConvBlock,
  * models/recnet.py:37-44), stride 1, zero padding 1, on the tcgen05 tensor cores

@@ -704,6 +704,62 @@ def test_shift_crop_argument_errors():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(2, 16, 32), (3, 64, 128), (5, 256, 256)])
+def test_thin_32_to_2_weight_gradient_carries_the_bias_gradient(shape):
+    """csmri_conv3x3_wgrad_thin_in_bias (the block-closing 32 -> 2 layer, models/recnet.py:48):
+    dw equals the plain weight-gradient entry bit for bit, db = sum of dy against float64, and
+    the autograd node uses it (no separate reduction)."""
+    from csmri_refinement_b200 import conv
+    n, h, w = shape
+    g = torch.Generator(device='cuda').manual_seed(sum(shape))
+    x = torch.randn(n, 32, h, w, device='cuda', generator=g)
+    gy = torch.randn(n, 2, h, w, device='cuda', generator=g) * 0.05 + 0.01
+    dw, db = conv.conv3x3_wgrad_thin_in_bias(x, gy)
+    assert torch.equal(dw, conv.conv3x3_wgrad(x, gy, 1))
+    truth = gy.double().sum(dim=(0, 2, 3))
+    assert ((db.double() - truth).norm() / truth.norm()).item() < 1e-6
+    layer = conv.Conv2d(32, 2, 3, padding=1).cuda()
+    ref = torch.nn.Conv2d(32, 2, 3, padding=1).cuda()
+    ref.load_state_dict(layer.state_dict())
+    xr = x.clone().requires_grad_(True)
+    xl = x.clone().requires_grad_(True)
+    layer(xl).backward(gy)
+    torch.backends.cudnn.allow_tf32 = False
+    ref(xr).backward(gy)
+    assert ((layer.bias.grad.double() - truth).norm() / truth.norm()).item() < 1e-6
+    assert orc.rel_l2(layer.weight.grad.cpu().numpy(), ref.weight.grad.cpu().numpy()) < TOL
+    assert orc.rel_l2(xl.grad.cpu().numpy(), xr.grad.cpu().numpy()) < TOL
+    try:
+        conv._THIN_IN_BIAS = False
+        layer.zero_grad()
+        layer(x.clone().requires_grad_(True)).backward(gy)
+        assert torch.equal(layer.weight.grad, dw)
+    finally:
+        conv._THIN_IN_BIAS = True
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('ci,co', [(2, 32), (32, 2)])
+def test_thin_data_gradient_reads_the_layer_weights_directly(ci, co):
+    """csmri_conv3x3_thin_dgrad (transposed, mirrored index map inside the kernel) against
+    autograd's convolution backward and against the same kernel fed a flipped / transposed copy."""
+    from csmri_refinement_b200 import conv
+    g = torch.Generator(device='cuda').manual_seed(ci)
+    wt = torch.randn(co, ci, 3, 3, device='cuda', generator=g) * 0.2
+    gy = torch.randn(3, co, 64, 96, device='cuda', generator=g)
+    got = conv.conv3x3_thin_dgrad(gy, wt)
+    x = torch.zeros(3, ci, 64, 96, device='cuda', dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(x, wt.double(), None, 1, 1).backward(gy.double())
+    assert ((got.double() - x.grad).norm() / x.grad.norm()).item() < 1e-6
+    assert torch.equal(got, conv.conv3x3_thin(gy, wt.flip(2, 3).transpose(0, 1).contiguous(), None, 0.0))
+    if ci == 32:                                            # + derivative of the activation that produced x
+        signs = torch.randint(-2 ** 31, 2 ** 31 - 1, (3, 64, 96), device='cuda', dtype=torch.int64).to(torch.int32)
+        m = conv.conv3x3_thin_dgrad(gy, wt, signs, 0.01)
+        bits = ((signs.to(torch.int64).unsqueeze(1) >> torch.arange(32, device='cuda').view(1, 32, 1, 1)) & 1).bool()
+        assert torch.equal(m, torch.where(bits, got, got * 0.01))
+
+
+@pytest.mark.gpu
 def test_conv_double_backward_is_refused():
     """The convolution backward passes are raw kernels; asking autograd for a second
     derivative through them must raise instead of returning a silently wrong value."""
