@@ -755,6 +755,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn encode_tiled_fn() {
+  // cuTensorMapEncodeTiled is a driver-API call: it needs the device's primary context current
+  // on the CALLING thread (CUDA_ERROR_INVALID_CONTEXT otherwise).  A thread that has only ever
+  // been handed work by another one - torch's autograd worker running a backward pass - may
+  // not have it bound yet; cudaSetDevice binds it and is legal during stream capture.
+  static thread_local int bound_dev = -1;
+  int dev = -1;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev != bound_dev && cudaSetDevice(dev) == cudaSuccess)
+    bound_dev = dev;
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* p = nullptr;
