@@ -441,25 +441,38 @@ __global__ void __launch_bounds__(kWtcThreads, 1)
   if (warp == kWtcMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-// dw[co][ci][ky][kx] = sum over CTAs, in CTA order, of partial[cta][(kx, co)][(ky, ci)];
-// db[co] (optional) = sum over CTAs of bias_partial[cta][co]
-__global__ void __launch_bounds__(128)
+// dw[co][ci][ky][kx] = sum over CTAs, in a fixed order, of partial[cta][(kx, co)][(ky, ci)];
+// db[co] (optional) = sum over CTAs of bias_partial[cta][co].
+// Block = 32 elements x 4 groups of CTAs: group g adds the CTAs g, g + 4, ... (coalesced
+// 128-byte loads, four independent chains per element instead of one 148-long one), the four
+// group sums meet in shared memory.
+constexpr int kWtcReduceGroups = 4;
+constexpr int kWtcReduceBlocks = (kWtcPartial + kWtcC + 31) / 32;
+
+__global__ void __launch_bounds__(32 * kWtcReduceGroups)
     conv3x3_wgrad_tc_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                    const float* __restrict__ bias_partial, float* __restrict__ db, int nctas) {
-  const int e = blockIdx.x * 128 + threadIdx.x;                // (kx, co, ky, ci), then 32 bias entries
+  __shared__ float part[kWtcReduceGroups][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;                        // (kx, co, ky, ci), then 32 bias entries
   asm volatile("griddepcontrol.wait;" ::: "memory");           // the partial blocks of the kernel before
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (e >= kWtcPartial) {
-    const int co = e - kWtcPartial;
-    if (co < kWtcC && db != nullptr) {
-      float s = 0.0f;
-      for (int c = 0; c < nctas; ++c) s += bias_partial[c * kWtcC + co];
-      db[co] = s;
-    }
+  const bool is_bias = e >= kWtcPartial;
+  const int co_b = e - kWtcPartial;
+  float s = 0.0f;
+  if (!is_bias) {
+    for (int c = g; c < nctas; c += kWtcReduceGroups) s += partial[(size_t)c * kWtcPartial + e];
+  } else if (co_b < kWtcC && db != nullptr) {
+    for (int c = g; c < nctas; c += kWtcReduceGroups) s += bias_partial[c * kWtcC + co_b];
+  }
+  part[g][lane] = s;
+  __syncthreads();
+  if (g != 0) return;
+  s = (part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane]);
+  if (is_bias) {
+    if (co_b < kWtcC && db != nullptr) db[co_b] = s;
     return;
   }
-  float s = 0.0f;
-  for (int c = 0; c < nctas; ++c) s += partial[(size_t)c * kWtcPartial + e];
   const int row = e / 96, col = e - row * 96;
   const int kx = row >> 5, co = row & 31, ky = col >> 5, ci = col & 31;
   dw[((co * kWtcC + ci) * 3 + ky) * 3 + kx] = s;

@@ -1774,7 +1774,7 @@ static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float*
       conv3x3_wgrad_thin_out_staged_kernel<<<ctas, 256, 0, s>>>(x, dy, (float*)workspace, bias_partial,
                                                                 H, W, tiles_x, ty8, nt8);
       if (db != nullptr)
-        wgrad_thin_reduce_kernel<<<1, 64, 0, s>>>(bias_partial, db, CO, ctas);
+        wgrad_thin_reduce_kernel<<<(CO + 31) / 32, 32 * kThinReduceGroups, 0, s>>>(bias_partial, db, CO, ctas);
     } else if (db != nullptr && !(CI == 32 && pad == 1 && ((uintptr_t)x & 15u) == 0 && g_thin_tma &&
                                   encode_tiled_fn() != nullptr)) {
       return fail(CSMRI_E_SHAPE, "conv3x3_wgrad_bias: shape not covered (the thin layers need pad 1 and a "
@@ -1804,7 +1804,7 @@ static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float*
         float* bias_partial = db != nullptr ? (float*)workspace + (size_t)ctas * CI * CO * 9 : nullptr;
         conv3x3_wgrad_thin_staged_tma_kernel<<<ctas, 256, kThinWgTmaSmem, s>>>(
             tm, x, dy, (float*)workspace, bias_partial, H, W, tiles_x, ty8, nt8);
-        if (db != nullptr) wgrad_thin_reduce_kernel<<<1, 64, 0, s>>>(bias_partial, db, CO, ctas);
+        if (db != nullptr) wgrad_thin_reduce_kernel<<<(CO + 31) / 32, 32 * kThinReduceGroups, 0, s>>>(bias_partial, db, CO, ctas);
       } else {
         CSMRI_TRY(set_smem(conv3x3_wgrad_thin_staged_kernel, smem_staged));
         conv3x3_wgrad_thin_staged_kernel<<<ctas, 256, smem_staged, s>>>(x, dy, (float*)workspace, H, W,
@@ -1814,7 +1814,7 @@ static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float*
       conv3x3_wgrad_thin_kernel<4, 2, false><<<ctas, 256, 0, s>>>(
           x, dy, (float*)workspace, H, W, HI, WI, pad, tiles_x, tiles_y, ntiles);
     }
-    wgrad_thin_reduce_kernel<<<(CI * CO * 9 + 63) / 64, 64, 0, s>>>((const float*)workspace, dw,
+    wgrad_thin_reduce_kernel<<<(CI * CO * 9 + 31) / 32, 32 * kThinReduceGroups, 0, s>>>((const float*)workspace, dw,
                                                                     CI * CO * 9, ctas);
     CSMRI_CUDA(cudaGetLastError());
     return CSMRI_OK;
@@ -1834,7 +1834,7 @@ static int conv3x3_wgrad_impl(const float* x, const float* dy, float* dw, float*
     float* bias_partial = db != nullptr ? (float*)workspace + (size_t)ctas * kWtcPartial : nullptr;
     CSMRI_CUDA(launch_pdl(conv3x3_wgrad_tc_kernel, dim3(ctas), dim3(kWtcThreads), kWtcSmemBytes, s, tm_x,
                           tm_dy, dy, (float*)workspace, bias_partial, H, W, nitems, 0));
-    CSMRI_CUDA(launch_pdl(conv3x3_wgrad_tc_reduce_kernel, dim3((kWtcPartial + kWtcC + 127) / 128), dim3(128),
+    CSMRI_CUDA(launch_pdl(conv3x3_wgrad_tc_reduce_kernel, dim3(kWtcReduceBlocks), dim3(32 * kWtcReduceGroups),
                           0, s, (const float*)workspace, dw, (const float*)bias_partial, db, ctas));
     CSMRI_CUDA(cudaGetLastError());
     return CSMRI_OK;

@@ -42,7 +42,7 @@ static void launch(const float* x, const float* dy, float* dw, float* ws, int N,
   const int nitems = N * (W / kWtcPx) * (H / kWtcRows);
   const int grid = nitems < g_sms ? nitems : g_sms;
   conv3x3_wgrad_tc_kernel<<<grid, kWtcThreads, kWtcSmemBytes>>>(tx, td, dy, ws, nullptr, H, W, nitems, debug);
-  conv3x3_wgrad_tc_reduce_kernel<<<(kWtcPartial + 127) / 128, 128>>>(ws, dw, nullptr, nullptr, grid);
+  conv3x3_wgrad_tc_reduce_kernel<<<kWtcReduceBlocks, 32 * kWtcReduceGroups>>>(ws, dw, nullptr, nullptr, grid);
 }
 
 int main() {
