@@ -23,13 +23,21 @@ static void reference(const std::vector<float>& x, const std::vector<float>& w, 
   }
 }
 
+static uint32_t* g_signs = nullptr;   // != nullptr: time the MASKED kernel (data gradient x LeakyReLU derivative)
 static int launch(const float* x, const float* w, const float* b, float* y, int N, int H, int W, float slope, int tf, int debug = 0) {
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    attr = true;
+  }
   int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int nitems = N * (W / kTcM) * (H / kTcRowBlock);
   const int grid = nitems < sms ? nitems : sms;
-  conv3x3_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes>>>(x, w, b, y, nullptr, nullptr, H, W, nitems, slope, tf, debug);
+  if (g_signs != nullptr)
+    conv3x3_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes>>>(x, w, nullptr, y, g_signs, nullptr, H, W, nitems, slope, 1, debug);
+  else
+    conv3x3_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes>>>(x, w, b, y, nullptr, nullptr, H, W, nitems, slope, tf, debug);
   return 0;
 }
 
@@ -74,10 +82,15 @@ int main() {
     float *dx, *dw, *db, *dy;
     cudaMalloc(&dx, ne * 4); cudaMalloc(&dw, 9216 * 4); cudaMalloc(&db, 128); cudaMalloc(&dy, ne * 4);
     cudaMemset(dx, 0, ne * 4); cudaMemset(dw, 0, 9216 * 4); cudaMemset(db, 0, 128);
-    const int dbg_list[7] = {0, 128, 128 | 55, 128 | 50, 128 | 7, 128 | 2, 128 | 1};
-    for (int di = 0; di < 7; ++di) {
+    const int dbg_list[9] = {0, 128, 128 | 55, 128 | 50, 128 | 7, 128 | 2, 128 | 1, 0, 128};
+    for (int di = 0; di < 9; ++di) {
       const int debug = dbg_list[di];
       if (ti == 1 && debug) break;
+      if (di == 7) {                        // the last two entries: the MASKED kernel
+        cudaMalloc(&g_signs, (size_t)N * H * W * 4);
+        cudaMemset(g_signs, 0x5a, (size_t)N * H * W * 4);
+        printf("  -- MASKED kernel (data gradient x LeakyReLU derivative from sign words) --\n");
+      }
       for (int i = 0; i < 3; ++i) launch(dx, dw, db, dy, N, H, W, 0.01f, 0, debug);
       cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
       cudaEventRecord(e0);
@@ -97,6 +110,7 @@ int main() {
       }
     }
     cudaFree(dx); cudaFree(dw); cudaFree(db); cudaFree(dy);
+    if (g_signs != nullptr) { cudaFree(g_signs); g_signs = nullptr; }
   }
   printf(fails ? "CONV TC PROBE FAILED\n" : "CONV TC PROBE OK\n");
   return fails != 0;
