@@ -521,6 +521,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               }
             }
           }
+          float* dp = dst + (size_t)(16 * h) * plane;      // one live pointer, advanced per channel
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             const float o = (kTcProbe && (debug & 32)) ? 0.0f : (v0[c] + v2[c]) + v1[c];
@@ -533,8 +534,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               if (slope > 0.0f) ov = ov > 0.0f ? ov : ov * slope;
             }
             if (!(kTcProbe && (debug & 4)))
-              asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(dst + (size_t)(16 * h + c) * plane), "f"(ov)
-                           : "memory");
+              asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(dp), "f"(ov) : "memory");
+            asm volatile("add.u64 %0, %0, %1;" : "+l"(dp) : "l"((unsigned long long)plane * 4ull));
           }
         }
         if (!MASKED && signs != nullptr) signs[((size_t)t.n * H + (t.y0 + r)) * W + t.x0 + tid] = positive;
